@@ -1,0 +1,140 @@
+/*
+ * mpcqp.h -- C ABI of libmpcqp.so, the B200-native batched centroidal-MPC QP engine.
+ *
+ * This is the drop-in boundary for ONE hot path of thomascbrs/mpc-tsid: the per-tick QP build in
+ * MPC.py and the OSQP solve it drives.  Each entry point names the reference interface it
+ * replaces (file:line under /root/reference).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions (reference: MPC.py:460-514)
+ *   - all arrays are float64, C order, one instance after another (leading batch dimension B);
+ *   - xref   : B x 12 x (N+1)   column 0 = measured state [x y z roll pitch yaw vx vy vz wx wy wz]
+ *                               in the local frame, columns 1..N = reference trajectory;
+ *   - fsteps : B x 20 x 13      row r = [steps left in phase r | (x,y,z) of FL, FR, HL, HR],
+ *                               NaN (or x == 0.0) marks a swing foot, a 0 in column 0 ends the table;
+ *   - forces : B x 12           (FL, FR, HL, HR) x (fx, fy, fz) of the first horizon step
+ *                               == MPC.f_applied (MPC.py:441);
+ *   - x      : B x 24N          [X_1 - xref_1 .. X_N - xref_N ; f_0 .. f_{N-1}] == MPC.x (MPC.py:428);
+ *   - every function returns 0 on success (the reference's methods all `return 0`) or a negative
+ *     MPCQP_ERR_* code; mpcqp_last_error() returns a thread-local message.  Inputs are never
+ *     written (the reference overwrites NaNs in the caller's fsteps, MPC.py:327; we do not).
+ *   - `location` says where a caller buffer lives: MPCQP_HOST or MPCQP_DEVICE (same device as the handle).
+ *   - one handle owns one CUDA stream; calls on one handle must not race.  No global state.
+ */
+#ifndef MPCQP_H_
+#define MPCQP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCQP_HOST 0
+#define MPCQP_DEVICE 1
+
+#define MPCQP_OK 0
+#define MPCQP_ERR_INVALID (-1)      /* bad argument / unsupported size */
+#define MPCQP_ERR_CUDA (-2)         /* CUDA runtime error, see mpcqp_last_error() */
+#define MPCQP_ERR_NO_DEVICE (-3)    /* no CUDA device: there is NO CPU fallback */
+#define MPCQP_ERR_STATE (-4)        /* call order (e.g. result requested before any run) */
+
+/* per-instance status written by mpcqp_run */
+#define MPCQP_STATUS_UNSOLVED 0
+#define MPCQP_STATUS_SOLVED 1          /* active-set polished, KKT-verified (exact to rounding) */
+#define MPCQP_STATUS_MAX_ITER 2        /* ADMM iterate returned at max_iter, not polished */
+#define MPCQP_STATUS_BAD_INPUT 3       /* non-finite state / malformed gait table; forces are 0 */
+
+/* solver stages that may run (bit mask in mpcqp_params.mode) */
+#define MPCQP_MODE_ACTIVE_SET 1     /* warm-started primal-dual active-set sweeps (fast path)   */
+#define MPCQP_MODE_ADMM 2           /* fixed-rho ADMM + guarded polish (globally convergent)    */
+
+typedef struct mpcqp_handle mpcqp_handle;
+
+/* Everything MPC.__init__ hard-codes (MPC.py:22-82) plus solver settings.  Fill with
+ * mpcqp_default_params() first, then override. */
+typedef struct mpcqp_params {
+    int32_t struct_size;        /* = sizeof(mpcqp_params), ABI check */
+    int32_t n_steps;            /* horizon N            (MPC.py:42)   */
+    int32_t batch;              /* B independent robots               */
+    int32_t device;             /* CUDA device ordinal                */
+    double dt;                  /* MPC.py:25 */
+    double T_gait;              /* MPC.py:45 (kept for API parity; unused by the QP) */
+    double mass;                /* MPC.py:28 */
+    double mu;                  /* MPC.py:39 */
+    double fz_max;              /* MPC.py:228 */
+    double gravity;             /* MPC.py:201 (9.81) */
+    double gI[9];               /* body inertia, row major   (MPC.py:35-37) */
+    double footholds[12];       /* 3 x 4 row major, default footholds used at k == 0 (MPC.py:67-70, 176) */
+    double w_state[12];         /* diagonal state weights    (MPC.py:255-275) */
+    double w_force;             /* force weight              (MPC.py:282-284) */
+    /* solver */
+    int32_t mode;               /* MPCQP_MODE_* mask, default both */
+    int32_t max_sweeps;         /* active-set sweeps before falling back to ADMM */
+    int32_t max_iter;           /* ADMM iteration cap */
+    int32_t min_iter;           /* ADMM iterations before the first polish attempt */
+    int32_t check_every;        /* ADMM iterations between active-set stability checks */
+    int32_t warm_start;         /* 1 = shift the previous tick's solution (MPC.py:403-406) */
+    double rho;                 /* ADMM penalty on the pyramid rows */
+    double sigma;               /* ADMM proximal weight */
+    double alpha;               /* ADMM relaxation */
+    double feas_tol;            /* primal feasibility tolerance of the KKT guard [N] */
+    double dual_tol;            /* multiplier sign tolerance of the KKT guard */
+} mpcqp_params;
+
+/* Reference constants of MPC.py:22-82 for the Solo trot configuration (dt 0.02, N 16, T_gait 0.32). */
+void mpcqp_default_params(mpcqp_params* p);
+
+/* replaces MPC.__init__ (MPC.py:22-82) / MPC_Wrapper.__init__ (MPC_Wrapper.py:20-37) */
+int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out);
+int mpcqp_destroy(mpcqp_handle* h);
+
+/* replaces MPC.run(k, xref, fsteps) (MPC.py:460-514) for B instances: build + solve + extract.
+ * k == 0 mirrors the reference's first tick (default footholds as lever arms, no warm start,
+ * MPC.py:176,413); any k > 0 is a regular tick.  Asynchronous on the handle's stream. */
+int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fsteps, int location);
+
+/* replaces MPC_Wrapper.get_latest_result() (MPC_Wrapper.py:57-78) / MPC.f_applied (MPC.py:441):
+ * B x 12 forces of the last run.  Synchronises the handle's stream when location == MPCQP_HOST. */
+int mpcqp_get_latest_result(mpcqp_handle* h, double* forces, int location);
+
+/* MPC.x (MPC.py:428): B x 24N.  MPC.x_robot (MPC.py:437-447) is x[:12N] + xref[:,1:]. */
+int mpcqp_get_solution(mpcqp_handle* h, double* x, int location);
+
+/* Per-instance diagnostics the reference never exposes (it ignores sol.info.status, MPC.py:427):
+ * any pointer may be NULL.  status[B], sweeps[B] (active-set factorizations), iters[B] (ADMM
+ * iterations), obj[B] (1/2 x'Px), contact[B*2] (4N bits: bit 4k+j = foot j in stance at step k),
+ * active[B*ceil(20N/32)] (bit 20k+5j+r = pyramid row r of foot j at step k holds with equality),
+ * y[B*20N] multipliers of the pyramid rows (rows of L in MPC.py:136-148). */
+int mpcqp_get_info(mpcqp_handle* h, int32_t* status, int32_t* sweeps, int32_t* iters, double* obj,
+                   uint32_t* contact, uint32_t* active, double* y, int location);
+
+/* Number of instances the last run sent to the ADMM stage (host int). */
+int mpcqp_get_fallback_count(mpcqp_handle* h, int32_t* count);
+
+/* Forget the carried solution (what a fresh osqp.OSQP() + k == 0 does in the reference). */
+int mpcqp_reset_warm_start(mpcqp_handle* h);
+
+int mpcqp_synchronize(mpcqp_handle* h);
+/* the CUDA stream (cudaStream_t) work is enqueued on; owned by the handle */
+void* mpcqp_stream(mpcqp_handle* h);
+/* kernels launched by this handle since creation (for bench.py's gpu_launches claim) */
+int64_t mpcqp_launch_count(mpcqp_handle* h);
+
+/* Parity hook for the build half: the coefficients MPC.update_ML / update_NK write each tick.
+ *   B_vals : B x N x 48   == ML.data[i_update_B + 96k]      (MPC.py:349)
+ *   S_vals : B x 12N      == ML.data[i_update_S]            (MPC.py:355-358)
+ *   NK     : B x 12N      == NK[:12N]                        (MPC.py:362-378)
+ * Synchronous. */
+int mpcqp_export_build(mpcqp_handle* h, double k, const double* xref, const double* fsteps, int location,
+                       double* B_vals, double* S_vals, double* NK);
+
+/* Measured FP64 peak of the device in TFLOP/s (DMMA m8n8k4 issue loop), for roofline reporting. */
+int mpcqp_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);
+
+const char* mpcqp_last_error(void);
+const char* mpcqp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCQP_H_ */

@@ -1,0 +1,432 @@
+// mpcqp_api.cu -- host side of libmpcqp.so: the C ABI declared in include/mpcqp.h.
+// Owns device memory, the stream and the carried warm-start state of a batch of MPC instances and
+// launches the kernels of mpcqp_kernels.cu.  There is deliberately no CPU code path: without a
+// CUDA device mpcqp_create fails with MPCQP_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mpcqp.h"
+#include "mpcqp_kernels.cu"
+
+using namespace mpcqp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(MPCQP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+// invert an n x n SPD matrix in extended precision (Gauss-Jordan, no pivoting needed)
+void invert_spd(std::vector<long double>& a, int n) {
+    std::vector<long double> inv((size_t)n * n, 0.0L);
+    for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0L;
+    for (int p = 0; p < n; ++p) {
+        const long double d = 1.0L / a[(size_t)p * n + p];
+        for (int c = 0; c < n; ++c) { a[(size_t)p * n + c] *= d; inv[(size_t)p * n + c] *= d; }
+        for (int r = 0; r < n; ++r) {
+            if (r == p) continue;
+            const long double m = a[(size_t)r * n + p];
+            if (m == 0.0L) continue;
+            for (int c = 0; c < n; ++c) {
+                a[(size_t)r * n + c] -= m * a[(size_t)p * n + c];
+                inv[(size_t)r * n + c] -= m * inv[(size_t)p * n + c];
+            }
+        }
+    }
+    a.swap(inv);
+}
+
+}  // namespace
+
+struct mpcqp_handle {
+    mpcqp_params p;
+    DevParams dp;
+    DevState st;
+    cudaStream_t stream = nullptr;
+    double* d_xref = nullptr;
+    double* d_fsteps = nullptr;
+    double* d_Minv = nullptr;
+    double* d_M = nullptr;
+    void* d_block = nullptr;        // one allocation behind all DevState arrays
+    size_t block_bytes = 0;
+    int aw = 0, cw = 0;             // words per instance of the active / contact masks
+    bool ran = false;
+    int64_t launches = 0;
+    int sms = 0;
+};
+
+extern "C" {
+
+const char* mpcqp_last_error(void) { return g_err.c_str(); }
+const char* mpcqp_version(void) { return "mpcqp 0.1 (sm_100a)"; }
+
+void mpcqp_default_params(mpcqp_params* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->struct_size = (int32_t)sizeof(*p);
+    p->n_steps = 16;
+    p->batch = 1;
+    p->device = 0;
+    p->dt = 0.02;
+    p->T_gait = 0.32;
+    p->mass = 2.50000279;                                   // MPC.py:28
+    p->mu = 0.9;                                            // MPC.py:39
+    p->fz_max = 25.0;                                       // MPC.py:228
+    p->gravity = 9.81;                                      // MPC.py:201
+    const double gI[9] = {3.09249e-2, -8.00101e-7, 1.865287e-5,          // MPC.py:35-37
+                          -8.00101e-7, 5.106100e-2, 1.245813e-4,
+                          1.865287e-5, 1.245813e-4, 6.939757e-2};
+    std::memcpy(p->gI, gI, sizeof(gI));
+    const double fh[12] = {0.19, 0.19, -0.19, -0.19,                     // MPC.py:67-70
+                           0.15005, -0.15005, 0.15005, -0.15005,
+                           0.0, 0.0, 0.0, 0.0};
+    std::memcpy(p->footholds, fh, sizeof(fh));
+    // MPC.py:255-275
+    p->w_state[0] = 0.1; p->w_state[1] = 0.1; p->w_state[2] = 1.0;
+    p->w_state[3] = 0.11; p->w_state[4] = 0.11; p->w_state[5] = 0.11;
+    for (int i = 0; i < 3; ++i) p->w_state[6 + i] = 2.0 * std::sqrt(p->w_state[i]);
+    for (int i = 0; i < 3; ++i) p->w_state[9 + i] = 0.05 * std::sqrt(p->w_state[3 + i]);
+    p->w_force = 1e-5;                                      // MPC.py:282-284
+    p->mode = MPCQP_MODE_ACTIVE_SET | MPCQP_MODE_ADMM;
+    p->max_sweeps = 6;
+    p->max_iter = 1000;
+    p->min_iter = 10;
+    p->check_every = 5;
+    p->warm_start = 1;
+    p->rho = 2e-5;
+    p->sigma = 1e-6;
+    p->alpha = 1.6;
+    p->feas_tol = 1e-9;
+    p->dual_tol = 1e-12;
+}
+
+int mpcqp_destroy(mpcqp_handle* h) {
+    if (!h) return MPCQP_OK;
+    cudaSetDevice(h->p.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_xref);
+    cudaFree(h->d_fsteps);
+    cudaFree(h->d_Minv);
+    cudaFree(h->d_M);
+    cudaFree(h->d_block);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MPCQP_OK;
+}
+
+int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
+    if (!p || !out) return fail(MPCQP_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (p->struct_size != (int32_t)sizeof(mpcqp_params)) return fail(MPCQP_ERR_INVALID, "mpcqp_params.struct_size mismatch");
+    if (p->n_steps != 16) return fail(MPCQP_ERR_INVALID, "n_steps: this build supports a horizon of 16 steps");
+    if (p->batch < 1) return fail(MPCQP_ERR_INVALID, "batch must be >= 1");
+    if (!(p->dt > 0) || !(p->mass > 0) || !(p->mu > 0) || !(p->fz_max > 0) || !(p->w_force > 0))
+        return fail(MPCQP_ERR_INVALID, "dt, mass, mu, fz_max, w_force must be positive");
+    for (int i = 0; i < 12; ++i)
+        if (!(p->w_state[i] > 0)) return fail(MPCQP_ERR_INVALID, "state weights must be positive");
+    if (!(p->mode & (MPCQP_MODE_ACTIVE_SET | MPCQP_MODE_ADMM))) return fail(MPCQP_ERR_INVALID, "mode selects no solver stage");
+    if (!(p->rho > 0) || !(p->sigma >= 0) || !(p->alpha > 0 && p->alpha < 2)) return fail(MPCQP_ERR_INVALID, "bad ADMM settings");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MPCQP_ERR_NO_DEVICE, "no CUDA device visible: libmpcqp has no CPU fallback");
+    }
+    if (p->device < 0 || p->device >= ndev) return fail(MPCQP_ERR_INVALID, "device ordinal out of range");
+    CU(cudaSetDevice(p->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, p->device));
+    if (prop.major < 10) return fail(MPCQP_ERR_NO_DEVICE, "libmpcqp is built for sm_100a (B200) only");
+
+    mpcqp_handle* h = new (std::nothrow) mpcqp_handle();
+    if (!h) return fail(MPCQP_ERR_INVALID, "out of host memory");
+    h->p = *p;
+    h->sms = prop.multiProcessorCount;
+    const int N = p->n_steps, B = p->batch;
+    DevParams& d = h->dp;
+    std::memset(&d, 0, sizeof(d));
+    d.N = N; d.batch = B;
+    d.dt = p->dt; d.mass = p->mass; d.mu = p->mu; d.fz_max = p->fz_max; d.gravity = p->gravity; d.w_force = p->w_force;
+    {
+        std::vector<long double> g(9);
+        for (int i = 0; i < 9; ++i) g[i] = p->gI[i];
+        invert_spd(g, 3);
+        for (int i = 0; i < 9; ++i) d.gIinv[i] = (double)g[i];
+    }
+    std::memcpy(d.footholds, p->footholds, sizeof(d.footholds));
+    for (int c = 0; c < 6; ++c) { d.wp[c] = p->w_state[c]; d.wv[c] = p->w_state[6 + c]; }
+    d.rho = p->rho; d.sigma = p->sigma; d.alpha = p->alpha; d.feas_tol = p->feas_tol; d.dual_tol = p->dual_tol;
+    d.max_sweeps = p->max_sweeps; d.max_iter = p->max_iter; d.min_iter = p->min_iter > 0 ? p->min_iter : 1;
+    d.check_every = p->check_every > 0 ? p->check_every : 1;
+    d.warm_start = p->warm_start; d.mode = p->mode; d.refine = 1;
+
+    // Gram matrices of the double-integrator response and their inverses (constant per handle)
+    //   M_c[k,l] = sum_{i >= max(k,l)} ( dt^2 Qp_c (i-k)(i-l) + Qv_c ),  i = 0..N-1
+    const int n = 6 * N, NT = n / 8, NTILES = NT * (NT + 1) / 2;
+    std::vector<double> M((size_t)6 * N * N), Mt((size_t)NTILES * 64, 0.0);
+    for (int c = 0; c < 6; ++c) {
+        std::vector<long double> m((size_t)N * N);
+        for (int k = 0; k < N; ++k)
+            for (int l = 0; l < N; ++l) {
+                long double c0 = 0, c2 = 0;
+                for (int i = (k > l ? k : l); i < N; ++i) { c0 += 1; c2 += (long double)(i - k) * (i - l); }
+                m[(size_t)k * N + l] = (long double)p->dt * p->dt * p->w_state[c] * c2 + (long double)p->w_state[6 + c] * c0;
+                M[((size_t)c * N + k) * N + l] = (double)m[(size_t)k * N + l];
+            }
+        invert_spd(m, N);
+        for (int k = 0; k < N; ++k)
+            for (int l = 0; l < N; ++l) {
+                const int gi = 6 * k + c, gj = 6 * l + c;
+                if ((gi >> 3) < (gj >> 3)) continue;                 // lower block triangle (+ full diagonal tiles)
+                Mt[(size_t)tile_index(gi >> 3, gj >> 3) * 64 + elem_off(gi & 7, gj & 7)] = (double)m[(size_t)k * N + l];
+            }
+    }
+    auto bail = [&](int code) { mpcqp_destroy(h); return code; };
+#define CUH(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return bail(fail(MPCQP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
+    } while (0)
+    CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUH(cudaMalloc(&h->d_M, M.size() * sizeof(double)));
+    CUH(cudaMalloc(&h->d_Minv, Mt.size() * sizeof(double)));
+    CUH(cudaMemcpy(h->d_M, M.data(), M.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUH(cudaMemcpy(h->d_Minv, Mt.data(), Mt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    d.M = h->d_M; d.Minv_tiled = h->d_Minv;
+    CUH(cudaMalloc(&h->d_xref, (size_t)B * 12 * (N + 1) * sizeof(double)));
+    CUH(cudaMalloc(&h->d_fsteps, (size_t)B * 260 * sizeof(double)));
+
+    h->aw = (20 * N + 31) / 32; h->cw = (4 * N + 31) / 32;
+    // carve all per-instance arrays out of one block (doubles first: natural alignment)
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_f = take((size_t)B * 12 * N * 8), o_y = take((size_t)B * 20 * N * 8), o_xs = take((size_t)B * 12 * N * 8);
+    const size_t o_f0 = take((size_t)B * 12 * 8), o_obj = take((size_t)B * 8);
+    const size_t o_status = take((size_t)B * 4), o_sweeps = take((size_t)B * 4), o_iters = take((size_t)B * 4);
+    const size_t o_contact = take((size_t)B * h->cw * 4), o_active = take((size_t)B * h->aw * 4);
+    const size_t o_list = take((size_t)B * 4), o_count = take(256), o_sig = take((size_t)B * 4 * N);
+    h->block_bytes = off;
+    CUH(cudaMalloc(&h->d_block, off));
+    CUH(cudaMemset(h->d_block, 0, off));
+    char* base = (char*)h->d_block;
+    h->st.f = (double*)(base + o_f); h->st.y = (double*)(base + o_y); h->st.xs = (double*)(base + o_xs);
+    h->st.f0 = (double*)(base + o_f0); h->st.obj = (double*)(base + o_obj);
+    h->st.status = (int32_t*)(base + o_status); h->st.sweeps = (int32_t*)(base + o_sweeps); h->st.iters = (int32_t*)(base + o_iters);
+    h->st.contact = (uint32_t*)(base + o_contact); h->st.active = (uint32_t*)(base + o_active);
+    h->st.fb_list = (int32_t*)(base + o_list); h->st.fb_count = (int32_t*)(base + o_count);
+    h->st.sig = (uint8_t*)(base + o_sig);
+    CUH(cudaMemset(h->st.sig, SIG_FREE, (size_t)B * 4 * N));
+    CUH(cudaFuncSetAttribute(solve_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<16, false>)));
+    CUH(cudaFuncSetAttribute(solve_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<16, true>)));
+    CUH(cudaFuncSetAttribute(solve_kernel<16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUH(cudaFuncSetAttribute(solve_kernel<16, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#undef CUH
+    *out = h;
+    return MPCQP_OK;
+}
+
+static int stage_inputs(mpcqp_handle* h, const double* xref, const double* fsteps, int location,
+                        const double** dx, const double** df) {
+    const int N = h->p.n_steps, B = h->p.batch;
+    if (location == MPCQP_DEVICE) {
+        *dx = xref; *df = fsteps;
+    } else if (location == MPCQP_HOST) {
+        CU(cudaMemcpyAsync(h->d_xref, xref, (size_t)B * 12 * (N + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->d_fsteps, fsteps, (size_t)B * 260 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        *dx = h->d_xref; *df = h->d_fsteps;
+    } else {
+        return fail(MPCQP_ERR_INVALID, "location must be MPCQP_HOST or MPCQP_DEVICE");
+    }
+    return MPCQP_OK;
+}
+
+int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fsteps, int location) {
+    if (!h || !xref || !fsteps) return fail(MPCQP_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->p.device));
+    const double *dx, *df;
+    int rc = stage_inputs(h, xref, fsteps, location, &dx, &df);
+    if (rc) return rc;
+    const int B = h->p.batch;
+    const int first = (k == 0.0) ? 1 : 0;                       // MPC.py:491, 413: only k == 0 vs k > 0 matters
+    CU(cudaMemsetAsync(h->st.fb_count, 0, sizeof(int32_t), h->stream));
+    if (h->p.mode & MPCQP_MODE_ACTIVE_SET) {
+        solve_kernel<16, false><<<B, 128, sizeof(Smem<16, false>), h->stream>>>(h->dp, h->st, dx, df, first);
+        ++h->launches;
+    } else {
+        // ADMM only: queue every instance
+        std::vector<int32_t> all(B);
+        for (int i = 0; i < B; ++i) all[i] = i;
+        CU(cudaMemcpyAsync(h->st.fb_list, all.data(), (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->st.fb_count, &B, 4, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    if (h->p.mode & MPCQP_MODE_ADMM) {
+        const int grid = B < 2 * h->sms ? B : 2 * h->sms;
+        solve_kernel<16, true><<<grid, 128, sizeof(Smem<16, true>), h->stream>>>(h->dp, h->st, dx, df, first);
+        ++h->launches;
+    }
+    CU(cudaGetLastError());
+    h->ran = true;
+    return MPCQP_OK;
+}
+
+static int fetch(mpcqp_handle* h, void* dst, const void* src, size_t bytes, int location) {
+    if (!dst) return MPCQP_OK;
+    if (location == MPCQP_HOST) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else if (location == MPCQP_DEVICE) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+        return fail(MPCQP_ERR_INVALID, "location must be MPCQP_HOST or MPCQP_DEVICE");
+    }
+    return MPCQP_OK;
+}
+
+int mpcqp_get_latest_result(mpcqp_handle* h, double* forces, int location) {
+    if (!h || !forces) return fail(MPCQP_ERR_INVALID, "null argument");
+    if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
+    CU(cudaSetDevice(h->p.device));
+    int rc = fetch(h, forces, h->st.f0, (size_t)h->p.batch * 12 * sizeof(double), location);
+    if (rc) return rc;
+    if (location == MPCQP_HOST) CU(cudaStreamSynchronize(h->stream));
+    return MPCQP_OK;
+}
+
+int mpcqp_get_solution(mpcqp_handle* h, double* x, int location) {
+    if (!h || !x) return fail(MPCQP_ERR_INVALID, "null argument");
+    if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
+    CU(cudaSetDevice(h->p.device));
+    const int N = h->p.n_steps, B = h->p.batch;
+    const cudaMemcpyKind kind = location == MPCQP_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "bad location");
+    const size_t half = (size_t)12 * N * sizeof(double);
+    CU(cudaMemcpy2DAsync(x, 2 * half, h->st.xs, half, half, B, kind, h->stream));
+    CU(cudaMemcpy2DAsync((char*)x + half, 2 * half, h->st.f, half, half, B, kind, h->stream));
+    if (location == MPCQP_HOST) CU(cudaStreamSynchronize(h->stream));
+    return MPCQP_OK;
+}
+
+int mpcqp_get_info(mpcqp_handle* h, int32_t* status, int32_t* sweeps, int32_t* iters, double* obj,
+                   uint32_t* contact, uint32_t* active, double* y, int location) {
+    if (!h) return fail(MPCQP_ERR_INVALID, "null argument");
+    if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
+    CU(cudaSetDevice(h->p.device));
+    const size_t B = h->p.batch;
+    int rc;
+    if ((rc = fetch(h, status, h->st.status, B * 4, location))) return rc;
+    if ((rc = fetch(h, sweeps, h->st.sweeps, B * 4, location))) return rc;
+    if ((rc = fetch(h, iters, h->st.iters, B * 4, location))) return rc;
+    if ((rc = fetch(h, obj, h->st.obj, B * 8, location))) return rc;
+    if ((rc = fetch(h, contact, h->st.contact, B * h->cw * 4, location))) return rc;
+    if ((rc = fetch(h, active, h->st.active, B * h->aw * 4, location))) return rc;
+    if ((rc = fetch(h, y, h->st.y, B * 20 * h->p.n_steps * 8, location))) return rc;
+    if (location == MPCQP_HOST) CU(cudaStreamSynchronize(h->stream));
+    return MPCQP_OK;
+}
+
+int mpcqp_get_fallback_count(mpcqp_handle* h, int32_t* count) {
+    if (!h || !count) return fail(MPCQP_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->p.device));
+    CU(cudaMemcpyAsync(count, h->st.fb_count, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MPCQP_OK;
+}
+
+int mpcqp_reset_warm_start(mpcqp_handle* h) {
+    if (!h) return fail(MPCQP_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->p.device));
+    const size_t B = h->p.batch, N = h->p.n_steps;
+    CU(cudaMemsetAsync(h->st.f, 0, B * 12 * N * 8, h->stream));
+    CU(cudaMemsetAsync(h->st.y, 0, B * 20 * N * 8, h->stream));
+    CU(cudaMemsetAsync(h->st.sig, SIG_FREE, B * 4 * N, h->stream));
+    return MPCQP_OK;
+}
+
+int mpcqp_synchronize(mpcqp_handle* h) {
+    if (!h) return fail(MPCQP_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->p.device));
+    CU(cudaStreamSynchronize(h->stream));
+    return MPCQP_OK;
+}
+
+void* mpcqp_stream(mpcqp_handle* h) { return h ? (void*)h->stream : nullptr; }
+int64_t mpcqp_launch_count(mpcqp_handle* h) { return h ? h->launches : 0; }
+
+int mpcqp_export_build(mpcqp_handle* h, double k, const double* xref, const double* fsteps, int location,
+                       double* B_vals, double* S_vals, double* NK) {
+    if (!h || !xref || !fsteps || !B_vals || !S_vals || !NK) return fail(MPCQP_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->p.device));
+    const double *dx, *df;
+    int rc = stage_inputs(h, xref, fsteps, location, &dx, &df);
+    if (rc) return rc;
+    const size_t B = h->p.batch, N = h->p.n_steps;
+    double *dB, *dS, *dN;
+    const bool host = location == MPCQP_HOST;
+    if (host) {
+        CU(cudaMalloc(&dB, B * 48 * N * 8)); CU(cudaMalloc(&dS, B * 12 * N * 8)); CU(cudaMalloc(&dN, B * 12 * N * 8));
+    } else {
+        dB = B_vals; dS = S_vals; dN = NK;
+    }
+    export_build_kernel<16><<<(int)B, 128, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
+    ++h->launches;
+    CU(cudaGetLastError());
+    if (host) {
+        CU(cudaMemcpyAsync(B_vals, dB, B * 48 * N * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(S_vals, dS, B * 12 * N * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(NK, dN, B * 12 * N * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (host) { cudaFree(dB); cudaFree(dS); cudaFree(dN); }
+    return MPCQP_OK;
+}
+
+int mpcqp_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MPCQP_ERR_NO_DEVICE, "no CUDA device visible");
+    }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount, threads = 512, iters = 20000;
+    double* out;
+    CU(cudaMalloc(&out, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best[2] = {0, 0};
+    for (int which = 0; which < 2; ++which) {
+        for (int rep = 0; rep < 4; ++rep) {
+            CU(cudaEventRecord(e0));
+            if (which == 0) peak_dfma_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+            else peak_dmma_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+            CU(cudaEventRecord(e1));
+            CU(cudaEventSynchronize(e1));
+            float ms;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            const double flop = which == 0 ? 2.0 * 8 * iters * (double)threads * blocks
+                                           : 2.0 * 256 * 4 * iters * (double)(threads / 32) * blocks;
+            const double tf = flop / (ms * 1e-3) * 1e-12;
+            if (rep > 0 && tf > best[which]) best[which] = tf;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    if (dfma_tflops) *dfma_tflops = best[0];
+    if (dmma_tflops) *dmma_tflops = best[1];
+    return MPCQP_OK;
+}
+
+}  // extern "C"

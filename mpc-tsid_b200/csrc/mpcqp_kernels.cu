@@ -1,0 +1,722 @@
+// mpcqp_kernels.cu -- the hot path: per-tick QP build + solve for a batch of robots, one CTA each.
+//
+// Replaces, for a whole batch at once, what the reference does per tick on the CPU:
+//   MPC.construct_gait / construct_S      MPC.py:635-652, 611-633   -> decode_foot()
+//   MPC.update_ML  (lever-arm blocks)     MPC.py:316-360            -> decode_foot()
+//   MPC.update_NK  (right-hand side)      MPC.py:362-378            -> free_response()  (condensed form)
+//   MPC.call_solver -> osqp solve         MPC.py:380-430            -> sweep() / admm stage
+//   MPC.retrieve_result                   MPC.py:432-458            -> finish()
+// The QP is solved in condensed form (states and swing-foot forces eliminated);
+// the optimum is the same point the reference's sparse QP has (strictly convex, unique).
+#include "mpcqp_device.cuh"
+
+namespace mpcqp {
+
+// -------------------------------------------------------------------------------------------------
+// shared-memory plan of one CTA
+// -------------------------------------------------------------------------------------------------
+template <int N, bool ADMM>
+struct Smem {
+    static constexpr int NDIM = 6 * N;
+    static constexpr int NT = NDIM / 8;
+    static constexpr int NTILES = NT * (NT + 1) / 2;
+    double W[NTILES * 64];                  // factor of the sweep / polish system
+    double W2[ADMM ? NTILES * 64 : 8];      // factor of the ADMM system (ADMM stage only)
+    double xr[12 * (N + 1)];                // xref of this instance
+    double fs[20 * 13];                     // fsteps of this instance
+    double gam[NDIM];                       // gradient of the tracking cost w.r.t. the impulses at f = 0
+    double u[NDIM];                         // impulse-space work vector (rhs / solution of W v = s)
+    double ms[NDIM];                        // M u
+    double red[40];
+    unsigned long long hist[16];            // hashes of signatures already tried (cycle detection)
+    int flag;
+    int any;
+};
+
+// per-foot data that stays in the registers of its owner thread (tid < 4N: k = tid >> 2, j = tid & 3)
+struct Foot {
+    double A[9];        // dt inv(R gI) [r]x, row major (angular rows of Bv)
+    double g[3];        // gradient of the objective w.r.t. this force at f = 0
+    double f[3];        // current force
+    double y[5];        // multipliers of the five pyramid rows
+    double lin;         // dt / m
+    bool contact;
+};
+
+// per-foot description of the affine face f = pf + Z q for one signature
+struct Face {
+    double bx[6], by[6], bz[6];     // Bv Z columns (zero when the column is absent)
+    double dx, dy, dz;              // 1 / (w_f |z_col|^2) or 0
+    double pf[3];
+    double czx, czy;                // x, y components of the z column (sx mu, sy mu)
+    bool zx, zy, zz;
+};
+
+__device__ __forceinline__ void bv_apply(const Foot& ft, const double f[3], double out[6]) {
+    out[0] = ft.lin * f[0]; out[1] = ft.lin * f[1]; out[2] = ft.lin * f[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) out[3 + r] = ft.A[3 * r] * f[0] + ft.A[3 * r + 1] * f[1] + ft.A[3 * r + 2] * f[2];
+}
+__device__ __forceinline__ void bvT_apply(const Foot& ft, const double* v, double out[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] = ft.lin * v[c] + ft.A[c] * v[3] + ft.A[3 + c] * v[4] + ft.A[6 + c] * v[5];
+}
+
+// sum a 6-vector over the four feet of a step (lanes 4k..4k+3) and let lane j == 0 store it
+__device__ __forceinline__ void step_sum_store(double v[6], double* dst, int j) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        v[i] += shfl_xor_d(v[i], 1);
+        v[i] += shfl_xor_d(v[i], 2);
+    }
+    if (j == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dst[i] = v[i];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// decode: contact flag, foothold, lever arm block for (step k, foot j)      [MPC.py:316-360, 635-652]
+// -------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void decode_foot(const DevParams& P, const double* xr, const double* fs, int k, int j,
+                                            bool first_tick, Foot& ft, bool& bad) {
+    int row = -1;
+    double cum = 0.0;
+    for (int r = 0; r < 20; ++r) {
+        const double cnt = fs[r * 13];
+        if (cnt == 0.0) break;                       // MPC.py:646: first empty row ends the table
+        if (!(cnt > 0.0) || cnt != floor(cnt)) { bad = true; break; }
+        if ((double)k < cum + cnt) { row = r; break; }
+        cum += cnt;
+    }
+    double foot[3] = {0.0, 0.0, 0.0};
+    ft.contact = false;
+    if (row >= 0) {
+        const double x = fs[row * 13 + 1 + 3 * j];
+        ft.contact = !(isnan(x) || x == 0.0);        // MPC.py:650
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double v = fs[row * 13 + 1 + 3 * j + c];
+            foot[c] = isnan(v) ? 0.0 : v;            // MPC.py:327
+        }
+    }
+    if (first_tick) {                                 // MPC.py:176: tick 0 uses the default footholds
+#pragma unroll
+        for (int c = 0; c < 3; ++c) foot[c] = P.footholds[c * 4 + j];
+    }
+    double r[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[c] = foot[c] - xr[c * (N + 1) + k];      // MPC.py:343
+    double sn, cs;
+    sincos(xr[5 * (N + 1) + k], &sn, &cs);                                   // MPC.py:330
+    // inv(R gI) = gI^-1 R'   (MPC.py:339-340: the reference inverts R gI, not R gI R')
+    double Ii[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        Ii[3 * a + 0] = P.gIinv[3 * a + 0] * cs - P.gIinv[3 * a + 1] * sn;
+        Ii[3 * a + 1] = P.gIinv[3 * a + 0] * sn + P.gIinv[3 * a + 1] * cs;
+        Ii[3 * a + 2] = P.gIinv[3 * a + 2];
+    }
+    // dt * Ii * [r]x   (MPC.py:345-346, utils.py:179-185)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        ft.A[3 * a + 0] = P.dt * (Ii[3 * a + 1] * r[2] - Ii[3 * a + 2] * r[1]);
+        ft.A[3 * a + 1] = P.dt * (Ii[3 * a + 2] * r[0] - Ii[3 * a + 0] * r[2]);
+        ft.A[3 * a + 2] = P.dt * (Ii[3 * a + 0] * r[1] - Ii[3 * a + 1] * r[0]);
+    }
+    ft.lin = P.dt / P.mass;                                                  // MPC.py:119
+}
+
+// -------------------------------------------------------------------------------------------------
+// free response of the double integrators and its gradient                  [MPC.py:362-378, condensed]
+//   gam[6k + c] = sum_{s = k+1..N} ( (s-1-k) dt Qp_c ep_s,c + Qv_c ev_s,c )
+//   ep_s = p0 + s dt v0 + dt g_c s(s-1)/2 - xref_p[s],   ev_s = v0 + s g_c - xref_v[s]
+// -------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void free_response(const DevParams& P, const double* xr, double* gam) {
+    for (int idx = threadIdx.x; idx < 6 * N; idx += blockDim.x) {
+        const int k = idx / 6, c = idx - 6 * k;
+        const double p0 = xr[c * (N + 1)], v0 = xr[(6 + c) * (N + 1)];
+        const double gc = (c == 2) ? -P.gravity * P.dt : 0.0;                 // MPC.py:200-201
+        double acc = 0.0;
+        for (int s = k + 1; s <= N; ++s) {
+            const double ep = p0 + s * P.dt * v0 + P.dt * gc * (0.5 * s * (s - 1)) - xr[c * (N + 1) + s];
+            const double ev = v0 + s * gc - xr[(6 + c) * (N + 1) + s];
+            acc += (double)(s - 1 - k) * P.dt * P.wp[c] * ep + P.wv[c] * ev;
+        }
+        gam[idx] = acc;
+    }
+}
+
+// ms = M u   (six independent N x N Gram matrices, one per impulse component)
+template <int N>
+__device__ __forceinline__ void gram_apply(const DevParams& P, const double* u, double* ms) {
+    for (int idx = threadIdx.x; idx < 6 * N; idx += blockDim.x) {
+        const int k = idx / 6, c = idx - 6 * k;
+        const double* Mr = P.M + (c * N + k) * N;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+        for (int l = 0; l < N; l += 2) {
+            a0 = fma(__ldg(Mr + l), u[6 * l + c], a0);
+            a1 = fma(__ldg(Mr + l + 1), u[6 * (l + 1) + c], a1);
+        }
+        ms[idx] = a0 + a1;
+    }
+}
+
+__device__ __forceinline__ void make_face(const DevParams& P, const Foot& ft, uint8_t sig, Face& fc) {
+    int sx, sy, tz;
+    sig_unpack(sig, sx, sy, tz);
+    const bool live = ft.contact && tz != 1;
+    fc.zx = live && sx == 0;
+    fc.zy = live && sy == 0;
+    fc.zz = live && tz == 0;
+    fc.czx = sx * P.mu;
+    fc.czy = sy * P.mu;
+    const double w = P.w_force;
+    fc.dx = fc.zx ? 1.0 / w : 0.0;
+    fc.dy = fc.zy ? 1.0 / w : 0.0;
+    fc.dz = fc.zz ? 1.0 / (w * (1.0 + P.mu * P.mu * (double)(sx * sx + sy * sy))) : 0.0;
+    const bool top = live && tz == 2;
+    fc.pf[0] = top ? fc.czx * P.fz_max : 0.0;
+    fc.pf[1] = top ? fc.czy * P.fz_max : 0.0;
+    fc.pf[2] = top ? P.fz_max : 0.0;
+    const double e0[3] = {1.0, 0.0, 0.0}, e1[3] = {0.0, 1.0, 0.0}, cz[3] = {fc.czx, fc.czy, 1.0};
+    bv_apply(ft, e0, fc.bx);
+    bv_apply(ft, e1, fc.by);
+    bv_apply(ft, cz, fc.bz);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        fc.bx[i] = fc.zx ? fc.bx[i] : 0.0;
+        fc.by[i] = fc.zy ? fc.by[i] : 0.0;
+        fc.bz[i] = fc.zz ? fc.bz[i] : 0.0;
+    }
+}
+
+// W = M^-1 + blockdiag_k( sum_j sum_col d_col b_col b_col' )   written in tile layout
+template <int N, int NTILES>
+__device__ __forceinline__ void assemble_W(const DevParams& P, double* W, const Face& fc, int k, int j, bool foot_thread) {
+    // 1. copy the constant part (vectorised, coalesced; it lives in L2 after the first CTA touched it)
+    const double2* src = reinterpret_cast<const double2*>(P.Minv_tiled);
+    double2* dst = reinterpret_cast<double2*>(W);
+    for (int i = threadIdx.x; i < NTILES * 32; i += blockDim.x) dst[i] = __ldg(src + i);
+    // 2. the 6x6 block of step k: every foot computes its 21 entries, butterfly-sum over the 4 feet
+    double tkk[21];
+    if (foot_thread) {
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b)
+                tkk[e++] = fc.dx * fc.bx[a] * fc.bx[b] + fc.dy * fc.by[a] * fc.by[b] + fc.dz * fc.bz[a] * fc.bz[b];
+#pragma unroll
+        for (e = 0; e < 21; ++e) {
+            tkk[e] += shfl_xor_d(tkk[e], 1);
+            tkk[e] += shfl_xor_d(tkk[e], 2);
+        }
+    }
+    __syncthreads();
+    if (foot_thread) {
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b, ++e) {
+                if ((e & 3) != j) continue;                      // the four feet share the 21 stores
+                const int gi = 6 * k + a, gj = 6 * k + b;
+                const int I = gi >> 3, J = gj >> 3;
+                double* T = W + tile_index(I, J) * 64;
+                T[elem_off(gi & 7, gj & 7)] += tkk[e];
+                if (I == J && a != b) T[elem_off(gj & 7, gi & 7)] += tkk[e];
+            }
+    }
+    __syncthreads();
+}
+
+struct SweepOut {
+    bool ok;            // KKT guard passed for every foot (CTA uniform)
+    bool spd;
+};
+
+// One equality-constrained solve on the faces given by `sig`, then the KKT guard and the next
+// active-set guess.  Leaves ft.f / ft.y (this foot's force and multipliers) and nsig.
+template <int N, bool ADMM>
+__device__ SweepOut sweep(const DevParams& P, Smem<N, ADMM>& sm, Foot& ft, uint8_t sig, uint8_t& nsig,
+                          int k, int j, bool foot_thread) {
+    using S = Smem<N, ADMM>;
+    Face fc;
+    if (foot_thread) make_face(P, ft, sig, fc);
+    assemble_W<N, S::NTILES>(P, sm.W, fc, k, j, foot_thread);
+    SweepOut out;
+    out.spd = cholesky_tiles<S::NT, 4>(sm.W, &sm.flag);
+    out.ok = false;
+    if (!out.spd) return out;
+
+    // gradient at the particular point pf (non-zero only when some foot sits on the fz_max face)
+    double grad[3] = {0.0, 0.0, 0.0};
+    const bool have_pf = foot_thread && (fc.pf[2] != 0.0);
+    const int any_pf = __syncthreads_or(have_pf ? 1 : 0);
+    double f[3] = {0.0, 0.0, 0.0};
+    if (foot_thread) { f[0] = fc.pf[0]; f[1] = fc.pf[1]; f[2] = fc.pf[2]; }
+    // pass 0 solves from pf; passes 1..refine are iterative-refinement steps on the reduced system;
+    // the last pass only evaluates the gradient at the final point for the KKT guard.
+    for (int pass = 0;; ++pass) {
+        // grad = H f + g  (H f skipped on pass 0 when f = pf = 0 everywhere)
+        if (pass > 0 || any_pf) {
+            if (foot_thread) {
+                double v[6];
+                bv_apply(ft, f, v);
+                if (!ft.contact) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) v[i] = 0.0;
+                }
+                step_sum_store(v, sm.u + 6 * k, j);
+            }
+            __syncthreads();
+            gram_apply<N>(P, sm.u, sm.ms);
+            __syncthreads();
+            if (foot_thread) {
+                bvT_apply(ft, sm.ms + 6 * k, grad);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) grad[c] += P.w_force * f[c] + ft.g[c];
+            }
+        } else if (foot_thread) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) grad[c] = ft.g[c];
+        }
+        if (pass == 1 + P.refine) break;
+        // reduced rhs r = -Z' grad, t = D^-1 r, s_k = sum_j (Bv Z) t
+        double tx = 0.0, ty = 0.0, tz_ = 0.0;
+        if (foot_thread) {
+            tx = fc.zx ? -grad[0] * fc.dx : 0.0;
+            ty = fc.zy ? -grad[1] * fc.dy : 0.0;
+            tz_ = fc.zz ? -(fc.czx * grad[0] + fc.czy * grad[1] + grad[2]) * fc.dz : 0.0;
+            double v[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) v[i] = fc.bx[i] * tx + fc.by[i] * ty + fc.bz[i] * tz_;
+            step_sum_store(v, sm.u + 6 * k, j);
+        }
+        __syncthreads();
+        solve_tiles_warp0<S::NT>(sm.W, sm.u);
+        __syncthreads();
+        if (foot_thread) {
+            const double* v = sm.u + 6 * k;
+            double ax = 0.0, ay = 0.0, az = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { ax += fc.bx[i] * v[i]; ay += fc.by[i] * v[i]; az += fc.bz[i] * v[i]; }
+            const double qx = tx - fc.dx * ax, qy = ty - fc.dy * ay, qz = tz_ - fc.dz * az;
+            f[0] += qx + fc.czx * qz;
+            f[1] += qy + fc.czy * qz;
+            f[2] += qz;
+        }
+        __syncthreads();
+    }
+
+    // ---- multipliers, KKT guard, next signature (per foot)
+    bool ok = true;
+    nsig = sig;
+    if (foot_thread && ft.contact) {
+        int sx, sy, tz;
+        sig_unpack(sig, sx, sy, tz);
+        const double mu = P.mu, ytol = P.dual_tol, ftol = P.feas_tol;
+        double y[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        int nsx = sx, nsy = sy, ntz = tz;
+        if (tz == 1) {
+            // apex: need y >= 0 with C' y = -grad; the sign of the slack on the fz >= 0 row decides
+            const double qx = -grad[0], qy = -grad[1], qz = -grad[2];
+            y[0] = fmax(qx, 0.0); y[1] = fmax(-qx, 0.0);
+            y[2] = fmax(qy, 0.0); y[3] = fmax(-qy, 0.0);
+            y[4] = -qz - mu * (fabs(qx) + fabs(qy));
+            f[0] = f[1] = f[2] = 0.0;
+            if (y[4] < -ytol) { ok = false; nsx = 0; nsy = 0; ntz = 0; }
+        } else {
+            const double yx = (sx != 0) ? -sx * grad[0] : 0.0;
+            const double yy = (sy != 0) ? -sy * grad[1] : 0.0;
+            if (sx > 0) y[0] = yx; else if (sx < 0) y[1] = yx;
+            if (sy > 0) y[2] = yy; else if (sy < 0) y[3] = yy;
+            const double y4 = grad[2] - mu * (yx + yy);
+            if (tz == 2) {
+                y[4] = y4;
+                if (y4 > ytol) { ok = false; ntz = 0; }
+            }
+            if (sx != 0 && yx < -ytol) { ok = false; nsx = 0; }
+            if (sy != 0 && yy < -ytol) { ok = false; nsy = 0; }
+            if (sx == 0) {
+                if (f[0] - mu * f[2] > ftol) { ok = false; nsx = 1; }
+                else if (-f[0] - mu * f[2] > ftol) { ok = false; nsx = -1; }
+            }
+            if (sy == 0) {
+                if (f[1] - mu * f[2] > ftol) { ok = false; nsy = 1; }
+                else if (-f[1] - mu * f[2] > ftol) { ok = false; nsy = -1; }
+            }
+            if (tz == 0) {
+                if (f[2] > P.fz_max + ftol) { ok = false; ntz = 2; }
+                else if (f[2] < -ftol) { ok = false; ntz = 1; }
+            }
+        }
+        nsig = sig_pack(nsx, nsy, ntz);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ft.f[c] = f[c];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) ft.y[r] = y[r];
+    } else if (foot_thread) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ft.f[c] = 0.0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) ft.y[r] = 0.0;
+    }
+    out.ok = __syncthreads_and(ok ? 1 : 0) != 0;
+    return out;
+}
+
+// order-sensitive hash of the CTA's signature (cycle detection for the active-set sweeps)
+__device__ __forceinline__ unsigned long long sig_hash(uint8_t sig, bool foot_thread, unsigned long long* slot) {
+    if (threadIdx.x == 0) *slot = 0ull;
+    __syncthreads();
+    if (foot_thread) {
+        unsigned long long h = (unsigned long long)(sig + 1) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29; h *= (2ull * threadIdx.x + 0xBF58476D1CE4E5B9ull); h ^= h >> 32;
+        atomicAdd(slot, h);
+    }
+    __syncthreads();
+    return *slot;
+}
+
+// -------------------------------------------------------------------------------------------------
+// finish: states by forward simulation, objective, masks, outputs            [MPC.py:432-458]
+// -------------------------------------------------------------------------------------------------
+template <int N, bool ADMM>
+__device__ void finish(const DevParams& P, Smem<N, ADMM>& sm, const DevState& st, int inst, const Foot& ft,
+                       uint8_t sig, int k, int j, bool foot_thread, int status, int sweeps, int iters) {
+    // impulses of the final forces
+    if (foot_thread) {
+        double v[6];
+        bv_apply(ft, ft.f, v);
+        if (!ft.contact) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) v[i] = 0.0;
+        }
+        step_sum_store(v, sm.u + 6 * k, j);
+    }
+    __syncthreads();
+    double part = 0.0;
+    if (threadIdx.x < 6) {
+        // component c: p_{s+1} = p_s + dt v_s, v_{s+1} = v_s + u_s + g_c          (MPC.py:110-111, 200-205)
+        const int c = threadIdx.x;
+        double p = sm.xr[c * (N + 1)], v = sm.xr[(6 + c) * (N + 1)];
+        const double gc = (c == 2) ? -P.gravity * P.dt : 0.0;
+        double* xs = st.xs + (size_t)inst * 12 * N;
+        for (int s = 0; s < N; ++s) {
+            const double pn = p + P.dt * v;
+            const double vn = v + sm.u[6 * s + c] + gc;
+            p = pn; v = vn;
+            const double ep = p - sm.xr[c * (N + 1) + s + 1], ev = v - sm.xr[(6 + c) * (N + 1) + s + 1];
+            xs[12 * s + c] = ep;
+            xs[12 * s + 6 + c] = ev;
+            part += 0.5 * (P.wp[c] * ep * ep + P.wv[c] * ev * ev);
+        }
+    }
+    if (foot_thread) {
+        part += 0.5 * P.w_force * (ft.f[0] * ft.f[0] + ft.f[1] * ft.f[1] + ft.f[2] * ft.f[2]);
+        double* fo = st.f + (size_t)inst * 12 * N + 12 * k + 3 * j;
+        fo[0] = ft.f[0]; fo[1] = ft.f[1]; fo[2] = ft.f[2];
+        double* yo = st.y + (size_t)inst * 20 * N + 20 * k + 5 * j;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) yo[r] = ft.y[r];
+        st.sig[(size_t)inst * 4 * N + 4 * k + j] = sig;
+        if (k == 0) {
+            double* f0 = st.f0 + (size_t)inst * 12 + 3 * j;
+            f0[0] = ft.f[0]; f0[1] = ft.f[1]; f0[2] = ft.f[2];
+        }
+    }
+    // objective: block reduction
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = part;
+    // masks: contact (4N bits) and rows that hold with equality (20N bits)
+    constexpr int AW = (20 * N + 31) / 32, CW = (4 * N + 31) / 32;
+    unsigned int* amask = reinterpret_cast<unsigned int*>(sm.ms);
+    for (int i = threadIdx.x; i < AW + CW; i += blockDim.x) amask[i] = 0u;
+    __syncthreads();
+    if (foot_thread) {
+        // a swing foot is pinned to f = 0 (MPC.py:355-358), so all five of its rows sit on their bound
+        const double mu = P.mu, tol = 1e-9;
+        const double fx = ft.f[0], fy = ft.f[1], fz = ft.f[2];
+        const double row[5] = {fx - mu * fz, -fx - mu * fz, fy - mu * fz, -fy - mu * fz, -fz};
+        const int b0 = 20 * k + 5 * j;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const bool act = (fabs(row[r]) <= tol) || (r == 4 && fabs(row[4] + P.fz_max) <= tol);
+            if (act) atomicOr(&amask[(b0 + r) >> 5], 1u << ((b0 + r) & 31));
+        }
+        if (ft.contact) atomicOr(&amask[AW + ((4 * k + j) >> 5)], 1u << ((4 * k + j) & 31));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < AW; i += blockDim.x) st.active[(size_t)inst * AW + i] = amask[i];
+    for (int i = threadIdx.x; i < CW; i += blockDim.x) st.contact[(size_t)inst * CW + i] = amask[AW + i];
+    if (threadIdx.x == 0) {
+        double o = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) o += sm.red[w];
+        st.obj[inst] = o;
+        st.status[inst] = status;
+        st.sweeps[inst] = sweeps;
+        st.iters[inst] = iters;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// The solve kernel.  ADMM = false: active-set stage for every instance (grid = batch).
+//                    ADMM = true : fallback stage for the instances queued in st.fb_list.
+// -------------------------------------------------------------------------------------------------
+template <int N, bool ADMM>
+__global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g,
+                                                    const double* __restrict__ fsteps_g, int first_tick) {
+    using S = Smem<N, ADMM>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S& sm = *reinterpret_cast<S*>(smem_raw);
+    const int tid = threadIdx.x;
+    const bool foot_thread = tid < 4 * N;
+    const int k = tid >> 2, j = tid & 3;
+
+    int n_work = ADMM ? *st.fb_count : P.batch;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int inst = ADMM ? st.fb_list[w] : w;
+        __syncthreads();
+        // ---- stage inputs in shared memory (two contiguous, 16-byte aligned blocks per instance)
+        {
+            const double2* gx = reinterpret_cast<const double2*>(xref_g + (size_t)inst * 12 * (N + 1));
+            const double2* gf = reinterpret_cast<const double2*>(fsteps_g + (size_t)inst * 260);
+            double2* sx = reinterpret_cast<double2*>(sm.xr);
+            double2* sf = reinterpret_cast<double2*>(sm.fs);
+            for (int i = tid; i < 6 * (N + 1); i += blockDim.x) sx[i] = __ldg(gx + i);
+            for (int i = tid; i < 130; i += blockDim.x) sf[i] = __ldg(gf + i);
+        }
+        __syncthreads();
+        Foot ft;
+        bool bad = false;
+        uint8_t sig = SIG_FREE;
+        if (foot_thread) decode_foot<N>(P, sm.xr, sm.fs, k, j, first_tick != 0, ft, bad);
+        for (int i = tid; i < 12 * (N + 1); i += blockDim.x) bad = bad || !isfinite(sm.xr[i]);
+        free_response<N>(P, sm.xr, sm.gam);
+        const int any_bad = __syncthreads_or(bad ? 1 : 0);
+        const bool warm = P.warm_start && !first_tick;
+        if (foot_thread) {
+            bvT_apply(ft, sm.gam + 6 * k, ft.g);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ft.f[c] = 0.0;
+#pragma unroll
+            for (int r = 0; r < 5; ++r) ft.y[r] = 0.0;
+            // warm start: the previous tick's active set, advanced by one step (MPC.py:403-406)
+            if (warm && ft.contact) {
+                const int ks = (k + 1 < N) ? k + 1 : 0;
+                sig = st.sig[(size_t)inst * 4 * N + 4 * ks + j];
+                if (sig > 26) sig = SIG_FREE;
+            }
+        }
+        if (any_bad) {
+            if (foot_thread) { ft.contact = false; }
+            finish<N, ADMM>(P, sm, st, inst, ft, SIG_FREE, k, j, foot_thread, 3, 0, 0);
+            continue;
+        }
+
+        int sweeps = 0, iters = 0, status = 0;
+        bool done = false;
+        if (!ADMM) {
+            // ---------------- active-set stage
+            int nhist = 0;
+            for (int s = 0; s < P.max_sweeps && !done; ++s) {
+                const unsigned long long h = sig_hash(sig, foot_thread && ft.contact, &sm.hist[15]);
+                bool seen = false;
+                for (int i = 0; i < nhist; ++i) seen = seen || (sm.hist[i] == h);
+                if (seen) break;
+                __syncthreads();
+                if (tid == 0 && nhist < 15) sm.hist[nhist] = h;
+                nhist = (nhist < 15) ? nhist + 1 : nhist;
+                uint8_t nsig;
+                const SweepOut so = sweep<N, ADMM>(P, sm, ft, sig, nsig, k, j, foot_thread);
+                ++sweeps;
+                if (!so.spd) break;
+                if (so.ok) { done = true; status = 1; }
+                else sig = nsig;
+            }
+            if (!done) {
+                if (P.mode & 2) {
+                    if (tid == 0) {
+                        const int slot = atomicAdd(st.fb_count, 1);
+                        st.fb_list[slot] = inst;
+                        st.sweeps[inst] = sweeps;
+                    }
+                    continue;       // state of this instance is left untouched for the ADMM stage
+                }
+                status = 0;
+            }
+        } else {
+            // ---------------- ADMM stage (fixed rho, Woodbury-form linear solve, guarded polish)
+            sweeps = (P.mode & 1) ? st.sweeps[inst] : 0;
+            const double rho = P.rho, sigma = P.sigma, alpha = P.alpha, mu = P.mu;
+            double z[5] = {0, 0, 0, 0, 0}, f[3] = {0, 0, 0}, y[5] = {0, 0, 0, 0, 0};
+            if (foot_thread && ft.contact && warm) {
+                const int ks = (k + 1 < N) ? k + 1 : 0;
+                const double* fp = st.f + (size_t)inst * 12 * N + 12 * ks + 3 * j;
+                const double* yp = st.y + (size_t)inst * 20 * N + 20 * ks + 5 * j;
+                f[0] = fp[0]; f[1] = fp[1]; f[2] = fp[2];
+#pragma unroll
+                for (int r = 0; r < 5; ++r) y[r] = yp[r];
+                const double cf[5] = {f[0] - mu * f[2], -f[0] - mu * f[2], f[1] - mu * f[2], -f[1] - mu * f[2], -f[2]};
+#pragma unroll
+                for (int r = 0; r < 5; ++r) z[r] = fmin(cf[r], 0.0);
+                z[4] = fmax(z[4], -P.fz_max);
+            }
+            // factor W(rho) = M^-1 + Bv D^-1 Bv' into W2 (faces: everything free, D = (w + sigma) I + rho C'C)
+            Face fa;
+            double ddx = 0.0, ddz = 0.0;
+            if (foot_thread) {
+                make_face(P, ft, SIG_FREE, fa);
+                ddx = ft.contact ? 1.0 / (P.w_force + sigma + 2.0 * rho) : 0.0;
+                ddz = ft.contact ? 1.0 / (P.w_force + sigma + rho * (4.0 * mu * mu + 1.0)) : 0.0;
+                fa.dx = ddx; fa.dy = ddx; fa.dz = ddz;
+            }
+            assemble_W<N, S::NTILES>(P, sm.W2, fa, k, j, foot_thread);
+            const bool spd = cholesky_tiles<S::NT, 4>(sm.W2, &sm.flag);
+            uint8_t prev_sig = 255;
+            int stable = 0;
+            while (spd && !done && iters < P.max_iter) {
+                ++iters;
+                double tx = 0, ty = 0, tzz = 0;
+                if (foot_thread) {
+                    const double v0 = rho * z[0] - y[0], v1 = rho * z[1] - y[1], v2 = rho * z[2] - y[2],
+                                 v3 = rho * z[3] - y[3], v4 = rho * z[4] - y[4];
+                    tx = ddx * (sigma * f[0] - ft.g[0] + (v0 - v1));
+                    ty = ddx * (sigma * f[1] - ft.g[1] + (v2 - v3));
+                    tzz = ddz * (sigma * f[2] - ft.g[2] - mu * (v0 + v1 + v2 + v3) - v4);
+                    double v[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) v[i] = fa.bx[i] * tx + fa.by[i] * ty + fa.bz[i] * tzz;
+                    step_sum_store(v, sm.u + 6 * k, j);
+                }
+                __syncthreads();
+                solve_tiles_warp0<S::NT>(sm.W2, sm.u);
+                __syncthreads();
+                uint8_t cur = SIG_FREE;
+                if (foot_thread && ft.contact) {
+                    const double* v = sm.u + 6 * k;
+                    double ax = 0, ay = 0, az = 0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { ax += fa.bx[i] * v[i]; ay += fa.by[i] * v[i]; az += fa.bz[i] * v[i]; }
+                    const double ftx = tx - ddx * ax, fty = ty - ddx * ay, ftz = tzz - ddz * az;
+                    const double zt[5] = {ftx - mu * ftz, -ftx - mu * ftz, fty - mu * ftz, -fty - mu * ftz, -ftz};
+                    f[0] = alpha * ftx + (1.0 - alpha) * f[0];
+                    f[1] = alpha * fty + (1.0 - alpha) * f[1];
+                    f[2] = alpha * ftz + (1.0 - alpha) * f[2];
+                    bool upp[5], low4 = false;
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) {
+                        const double zr = alpha * zt[r] + (1.0 - alpha) * z[r];
+                        double zn = fmin(zr + y[r] / rho, 0.0);
+                        if (r == 4) zn = fmax(zn, -P.fz_max);
+                        y[r] += rho * (zr - zn);
+                        z[r] = zn;
+                        upp[r] = (0.0 - zn) < y[r];                    // OSQP's polish rule
+                        if (r == 4) low4 = (zn + P.fz_max) < -y[r];
+                    }
+                    const int sx = (upp[0] ? 1 : 0) - (upp[1] ? 1 : 0), sy = (upp[2] ? 1 : 0) - (upp[3] ? 1 : 0);
+                    const bool apex = upp[4] || (upp[0] && upp[1]) || (upp[2] && upp[3]);
+                    cur = sig_pack(sx, sy, apex ? 1 : (low4 ? 2 : 0));
+                }
+                __syncthreads();
+                if (iters >= P.min_iter && (iters % P.check_every) == 0) {
+                    const int same = __syncthreads_and((cur == prev_sig) ? 1 : 0);
+                    prev_sig = cur;
+                    stable = same ? stable + 1 : 0;
+                    if (stable >= 1) {
+                        stable = 0;
+                        uint8_t nsig;
+                        Foot trial = ft;
+                        const SweepOut so = sweep<N, ADMM>(P, sm, trial, cur, nsig, k, j, foot_thread);
+                        ++sweeps;
+                        if (so.spd && so.ok) { ft = trial; sig = cur; done = true; status = 1; }
+                    }
+                }
+            }
+            if (!done) {
+                status = 2;
+                sig = SIG_FREE;
+                if (foot_thread) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) ft.f[c] = ft.contact ? f[c] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) ft.y[r] = ft.contact ? y[r] : 0.0;
+                }
+            }
+        }
+        finish<N, ADMM>(P, sm, st, inst, ft, sig, k, j, foot_thread, status, sweeps, iters);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Build-half parity hook: the coefficients MPC.update_ML / update_NK write each tick, in the
+// reference's own order (MPC.py:154-166, 349, 355-358, 362-378).
+// -------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void export_build_kernel(DevParams P, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g,
+                                    int first_tick, double* __restrict__ Bv, double* __restrict__ Sv, double* __restrict__ NK) {
+    __shared__ double xr[12 * (N + 1)];
+    __shared__ double fs[260];
+    const int inst = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < 12 * (N + 1); i += blockDim.x) xr[i] = xref_g[(size_t)inst * 12 * (N + 1) + i];
+    for (int i = tid; i < 260; i += blockDim.x) fs[i] = fsteps_g[(size_t)inst * 260 + i];
+    __syncthreads();
+    if (tid < 4 * N) {
+        const int k = tid >> 2, j = tid & 3;
+        Foot ft;
+        bool bad = false;
+        decode_foot<N>(P, xr, fs, k, j, first_tick != 0, ft, bad);
+        double* b = Bv + (size_t)inst * 48 * N + 48 * k + 12 * j;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            b[4 * c + 0] = ft.lin;
+            b[4 * c + 1] = ft.A[0 + c];
+            b[4 * c + 2] = ft.A[3 + c];
+            b[4 * c + 3] = ft.A[6 + c];
+        }
+        double* s = Sv + (size_t)inst * 12 * N + 12 * k + 3 * j;
+        s[0] = s[1] = s[2] = ft.contact ? 0.0 : 1.0;                        // MPC.py:628-630
+    }
+    for (int idx = tid; idx < 12 * N; idx += blockDim.x) {
+        const int k = idx / 12, i = idx - 12 * k;
+        // row k of N: -g - [k == 0] A x0 + X*_{k+1} - [k > 0] A X*_k          (MPC.py:366-376)
+        double v = xr[i * (N + 1) + k + 1];
+        if (i == 8) v += P.gravity * P.dt;
+        double ax = xr[i * (N + 1) + k];
+        if (i < 6) ax += P.dt * xr[(i + 6) * (N + 1) + k];
+        NK[(size_t)inst * 12 * N + idx] = v - ax;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// FP64 peak probes (roofline denominators; MEASURED_PEAKS.json has no FP64 entry)
+// -------------------------------------------------------------------------------------------------
+__global__ void peak_dfma_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+__global__ void peak_dmma_kernel(double* out, int iters, double a, double b) {
+    double c[4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { c[q][0] = threadIdx.x + q; c[q][1] = q; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dmma884(c[q][0], c[q][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += c[q][0] + c[q][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace mpcqp

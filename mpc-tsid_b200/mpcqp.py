@@ -1,0 +1,207 @@
+"""ctypes binding of libmpcqp.so (include/mpcqp.h) -- the only door from Python into the engine.
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C mpc-tsid_b200/csrc`.  If it is
+missing, or no B200 is visible, everything here raises: there is no CPU fallback by design.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HOST, DEVICE = 0, 1
+MODE_ACTIVE_SET, MODE_ADMM = 1, 2
+STATUS = {0: "unsolved", 1: "solved", 2: "max_iter", 3: "bad_input"}
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmpcqp.so")
+
+# every symbol include/mpcqp.h declares (tests check that the built library exports all of them)
+EXPORTS = (
+    "mpcqp_default_params", "mpcqp_create", "mpcqp_destroy", "mpcqp_run", "mpcqp_get_latest_result",
+    "mpcqp_get_solution", "mpcqp_get_info", "mpcqp_get_fallback_count", "mpcqp_reset_warm_start",
+    "mpcqp_synchronize", "mpcqp_stream", "mpcqp_launch_count", "mpcqp_export_build",
+    "mpcqp_measure_fp64_peak", "mpcqp_last_error", "mpcqp_version",
+)
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("n_steps", C.c_int32), ("batch", C.c_int32), ("device", C.c_int32),
+        ("dt", C.c_double), ("T_gait", C.c_double), ("mass", C.c_double), ("mu", C.c_double),
+        ("fz_max", C.c_double), ("gravity", C.c_double),
+        ("gI", C.c_double * 9), ("footholds", C.c_double * 12), ("w_state", C.c_double * 12),
+        ("w_force", C.c_double),
+        ("mode", C.c_int32), ("max_sweeps", C.c_int32), ("max_iter", C.c_int32), ("min_iter", C.c_int32),
+        ("check_every", C.c_int32), ("warm_start", C.c_int32),
+        ("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
+        ("feas_tol", C.c_double), ("dual_tol", C.c_double),
+    ]
+
+
+class MpcqpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """dlopen libmpcqp.so and declare prototypes.  Raises if the extension was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise MpcqpError("libmpcqp.so not found at %s -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback)" % _LIB_PATH)
+    lib = C.CDLL(_LIB_PATH)
+    vp, dp, i32p, u32p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    lib.mpcqp_default_params.argtypes = [C.POINTER(Params)]
+    lib.mpcqp_default_params.restype = None
+    lib.mpcqp_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    lib.mpcqp_destroy.argtypes = [vp]
+    lib.mpcqp_run.argtypes = [vp, C.c_double, dp, dp, C.c_int]
+    lib.mpcqp_get_latest_result.argtypes = [vp, dp, C.c_int]
+    lib.mpcqp_get_solution.argtypes = [vp, dp, C.c_int]
+    lib.mpcqp_get_info.argtypes = [vp, i32p, i32p, i32p, dp, u32p, u32p, dp, C.c_int]
+    lib.mpcqp_get_fallback_count.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.mpcqp_reset_warm_start.argtypes = [vp]
+    lib.mpcqp_synchronize.argtypes = [vp]
+    lib.mpcqp_stream.argtypes = [vp]
+    lib.mpcqp_stream.restype = C.c_void_p
+    lib.mpcqp_launch_count.argtypes = [vp]
+    lib.mpcqp_launch_count.restype = C.c_int64
+    lib.mpcqp_export_build.argtypes = [vp, C.c_double, dp, dp, C.c_int, dp, dp, dp]
+    lib.mpcqp_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.mpcqp_last_error.restype = C.c_char_p
+    lib.mpcqp_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise MpcqpError("libmpcqp error %d: %s" % (rc, load().mpcqp_last_error().decode()))
+
+
+def default_params(**overrides):
+    p = Params()
+    load().mpcqp_default_params(C.byref(p))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError("mpcqp_params has no field %r" % k)
+        cur = getattr(p, k)
+        if hasattr(cur, "__len__"):
+            arr = np.asarray(v, dtype=np.float64).ravel()
+            if len(arr) != len(cur):
+                raise ValueError("%s needs %d values" % (k, len(cur)))
+            for i, x in enumerate(arr):
+                cur[i] = float(x)
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    """Host numpy array or a raw device pointer (int)."""
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return C.c_void_p(a.ctypes.data)
+
+
+def _host_f64(a, shape):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.shape != shape:
+        raise ValueError("expected shape %r, got %r" % (shape, a.shape))
+    return a
+
+
+class Engine:
+    """One libmpcqp handle: a batch of `batch` independent MPC instances on one GPU."""
+
+    def __init__(self, batch=1, n_steps=16, device=0, **overrides):
+        self.lib = load()
+        self.params = default_params(batch=int(batch), n_steps=int(n_steps), device=int(device), **overrides)
+        self.B, self.N = int(batch), int(n_steps)
+        h = C.c_void_p()
+        _check(self.lib.mpcqp_create(C.byref(self.params), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mpcqp_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # ---- run
+    def run(self, k, xref, fsteps):
+        """Host arrays: xref (B,12,N+1), fsteps (B,20,13).  Asynchronous."""
+        xref = _host_f64(xref, (self.B, 12, self.N + 1))
+        fsteps = _host_f64(fsteps, (self.B, 20, 13))
+        self._keep = (xref, fsteps)          # keep alive until the copy engine is done with them
+        _check(self.lib.mpcqp_run(self._h, float(k), _ptr(xref), _ptr(fsteps), HOST))
+
+    def run_device(self, k, xref_ptr, fsteps_ptr):
+        """Raw device pointers (e.g. torch.Tensor.data_ptr()) to arrays of the same layout."""
+        _check(self.lib.mpcqp_run(self._h, float(k), C.c_void_p(int(xref_ptr)), C.c_void_p(int(fsteps_ptr)), DEVICE))
+
+    # ---- results
+    def forces(self, out=None):
+        out = np.empty((self.B, 12)) if out is None else out
+        _check(self.lib.mpcqp_get_latest_result(self._h, _ptr(out), HOST))
+        return out
+
+    def forces_device(self, ptr):
+        _check(self.lib.mpcqp_get_latest_result(self._h, C.c_void_p(int(ptr)), DEVICE))
+
+    def solution(self, out=None):
+        out = np.empty((self.B, 24 * self.N)) if out is None else out
+        _check(self.lib.mpcqp_get_solution(self._h, _ptr(out), HOST))
+        return out
+
+    def solution_device(self, ptr):
+        _check(self.lib.mpcqp_get_solution(self._h, C.c_void_p(int(ptr)), DEVICE))
+
+    def info(self, with_y=True):
+        B, N = self.B, self.N
+        aw, cw = (20 * N + 31) // 32, (4 * N + 31) // 32
+        status, sweeps, iters = (np.empty(B, np.int32) for _ in range(3))
+        obj = np.empty(B)
+        contact, active = np.empty((B, cw), np.uint32), np.empty((B, aw), np.uint32)
+        y = np.empty((B, 20 * N)) if with_y else None
+        _check(self.lib.mpcqp_get_info(self._h, _ptr(status), _ptr(sweeps), _ptr(iters), _ptr(obj), _ptr(contact),
+                                       _ptr(active), _ptr(y) if with_y else None, HOST))
+        bits = lambda words, n: ((words[:, np.arange(n) // 32] >> (np.arange(n) % 32).astype(np.uint32)) & 1).astype(bool)
+        return dict(status=status, sweeps=sweeps, iters=iters, obj=obj, y=y,
+                    contact=bits(contact, 4 * N).reshape(B, N, 4), active=bits(active, 20 * N).reshape(B, N, 4, 5))
+
+    def fallback_count(self):
+        c = C.c_int32()
+        _check(self.lib.mpcqp_get_fallback_count(self._h, C.byref(c)))
+        return c.value
+
+    def export_build(self, k, xref, fsteps):
+        xref = _host_f64(xref, (self.B, 12, self.N + 1))
+        fsteps = _host_f64(fsteps, (self.B, 20, 13))
+        Bv, Sv, NK = np.empty((self.B, self.N, 48)), np.empty((self.B, 12 * self.N)), np.empty((self.B, 12 * self.N))
+        _check(self.lib.mpcqp_export_build(self._h, float(k), _ptr(xref), _ptr(fsteps), HOST, _ptr(Bv), _ptr(Sv), _ptr(NK)))
+        return Bv, Sv, NK
+
+    def reset_warm_start(self):
+        _check(self.lib.mpcqp_reset_warm_start(self._h))
+
+    def synchronize(self):
+        _check(self.lib.mpcqp_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return self.lib.mpcqp_stream(self._h)
+
+    @property
+    def launches(self):
+        return int(self.lib.mpcqp_launch_count(self._h))
+
+
+def measure_fp64_peak(device=0):
+    a, b = C.c_double(), C.c_double()
+    _check(load().mpcqp_measure_fp64_peak(int(device), C.byref(a), C.byref(b)))
+    return dict(dfma_tflops=a.value, dmma_tflops=b.value)
