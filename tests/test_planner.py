@@ -1,0 +1,53 @@
+"""mpc-tsid_b200/scenario.py (batched input generator) against the reference FootstepPlanner's
+outputs stored in tests/golden/planner_trot.npz."""
+import os
+
+import numpy as np
+import pytest
+
+from scenario import GAIT_KINDS, Scenario, gait_sequence, reference_ramp
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "planner_trot.npz"))
+
+
+@pytest.mark.parametrize("N", [16, 32])
+def test_trot_planner_matches_reference(N):
+    sc = Scenario(1, n_steps=N, gaits="trot", v_ref=G["v_ref"], phase=[0], random_commands=False)
+    xr_g, fs_g = G["xref_N%d" % N], G["fsteps_N%d" % N]
+    for k in range(xr_g.shape[0]):
+        xr, fs = sc.inputs()
+        np.testing.assert_allclose(sc.state[0], G["state_N%d" % N][k], rtol=0, atol=1e-15)
+        assert np.array_equal(np.isnan(fs[0]), np.isnan(fs_g[k]))
+        np.testing.assert_allclose(np.nan_to_num(fs[0]), np.nan_to_num(fs_g[k]), rtol=0, atol=1e-14)
+        np.testing.assert_allclose(xr[0], xr_g[k], rtol=0, atol=1e-14)
+        xn = xr_g[k][:, 1] + 0.01 * np.sin(np.arange(12) + k)
+        sc.advance(xn[None])
+
+
+def test_gait_tables():
+    for kind in GAIT_KINDS:
+        seq = gait_sequence(kind)
+        assert seq.shape == (16, 4) and set(np.unique(seq)) <= {0.0, 1.0}
+    assert gait_sequence("trot").sum() == 36            # 3 * 36 = 108 active force unknowns
+    assert gait_sequence("walk").sum() == 48 and gait_sequence("static").sum() == 64
+    sc = Scenario(3, gaits=["trot", "walk", "static"], phase=[0, 3, 7], random_commands=False)
+    for _ in range(20):
+        _, fs = sc.inputs()
+        assert np.all(fs[:, :, 0].sum(axis=1) == 16)   # phase lengths always cover the horizon
+        assert np.all(fs[2, 0, 1:] == fs[2, 0, 1:])    # static: no NaN in the only row
+        sc.advance(np.zeros((3, 12)))
+
+
+def test_batched_equals_single():
+    a = Scenario(4, gaits=["trot", "pace"], seed=5)
+    xr, fs = a.inputs()
+    for b in range(4):
+        s = Scenario(1, gaits=a.kinds[b], v_ref=a.v_ref[b], phase=[a.phase[b]], random_commands=False)
+        x1, f1 = s.inputs()
+        np.testing.assert_array_equal(x1[0], xr[b])
+        np.testing.assert_array_equal(np.nan_to_num(f1[0]), np.nan_to_num(fs[b]))
+
+
+def test_reference_ramp():
+    assert reference_ramp(0) == 0.0 and reference_ramp(48) == 0.0
+    assert abs(reference_ramp(100) - (2000 - 960) / 3500) < 1e-15 and reference_ramp(1000) == 1.0
