@@ -61,7 +61,7 @@ def polish(P, q, A, l, u, x, y, z=None, delta=1e-7, refine=60, tol=1e-14):
     return xp, yp, low, upp
 
 
-def sign_feasible_multipliers(P, q, A, l, u, x, y, low, upp):
+def sign_feasible_multipliers(P, q, A, l, u, x, y, low, upp, force=False):
     """When active rows are linearly dependent (a swing foot is pinned by three equalities AND sits on
     all five pyramid rows; a stance foot unloaded to the apex) the multipliers are not unique and the
     linear solve may return a sign-infeasible choice although a feasible one exists.  Re-derive them:
@@ -69,7 +69,7 @@ def sign_feasible_multipliers(P, q, A, l, u, x, y, low, upp):
     y <= 0 on lower-active ones and free sign on equalities (bounded-variable least squares)."""
     eq = (u - l) <= 0.0
     ok = np.all(y[upp & ~eq] >= 0.0) and np.all(y[low] <= 0.0)
-    if ok:
+    if ok and not force:
         return y
     from scipy.optimize import lsq_linear
     rows = np.flatnonzero(low | upp)

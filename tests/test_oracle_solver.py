@@ -83,7 +83,7 @@ def test_golden_solutions_are_optimal(path):
         Ax = A @ x
         tight_u = np.abs(Ax - u) <= 1e-9
         tight_l = np.abs(Ax - l) <= 1e-9
-        y = kkt.sign_feasible_multipliers(P, q, A, l, u, x, np.full(44 * N, -1.0), tight_l & ~tight_u, tight_u)
+        y = kkt.sign_feasible_multipliers(P, q, A, l, u, x, np.zeros(44 * N), tight_l & ~tight_u, tight_u, force=True)
         cert = kkt.certificate(P, q, A, l, u, x, y)
         assert cert["prim"] <= 1e-9 and cert["stat"] <= 1e-10 and cert["bad_sign"] <= 1e-15, (t, cert)
         assert g["cert_stat"][t] <= 1e-11 and g["cert_prim"][t] <= 1e-9
