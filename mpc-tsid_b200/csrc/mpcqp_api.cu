@@ -61,7 +61,7 @@ struct mpcqp_handle {
     double* d_xref = nullptr;
     double* d_fsteps = nullptr;
     double* d_Minv = nullptr;
-    double* d_M = nullptr;
+    double* d_C2 = nullptr;
     void* d_block = nullptr;        // one allocation behind all DevState arrays
     size_t block_bytes = 0;
     int aw = 0, cw = 0;             // words per instance of the active / contact masks
@@ -121,7 +121,7 @@ int mpcqp_destroy(mpcqp_handle* h) {
     cudaFree(h->d_xref);
     cudaFree(h->d_fsteps);
     cudaFree(h->d_Minv);
-    cudaFree(h->d_M);
+    cudaFree(h->d_C2);
     cudaFree(h->d_block);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -176,7 +176,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     // Gram matrices of the double-integrator response and their inverses (constant per handle)
     //   M_c[k,l] = sum_{i >= max(k,l)} ( dt^2 Qp_c (i-k)(i-l) + Qv_c ),  i = 0..N-1
     const int n = 6 * N, NT = n / 8, NTILES = NT * (NT + 1) / 2;
-    std::vector<double> M((size_t)6 * N * N), Mt((size_t)NTILES * 64, 0.0);
+    std::vector<double> C2((size_t)N * N), Mt((size_t)NTILES * 64, 0.0);
     for (int c = 0; c < 6; ++c) {
         std::vector<long double> m((size_t)N * N);
         for (int k = 0; k < N; ++k)
@@ -184,7 +184,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
                 long double c0 = 0, c2 = 0;
                 for (int i = (k > l ? k : l); i < N; ++i) { c0 += 1; c2 += (long double)(i - k) * (i - l); }
                 m[(size_t)k * N + l] = (long double)p->dt * p->dt * p->w_state[c] * c2 + (long double)p->w_state[6 + c] * c0;
-                M[((size_t)c * N + k) * N + l] = (double)m[(size_t)k * N + l];
+                C2[(size_t)k * N + l] = (double)c2;
             }
         invert_spd(m, N);
         for (int k = 0; k < N; ++k)
@@ -201,11 +201,11 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
         if (e_ != cudaSuccess) return bail(fail(MPCQP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
     } while (0)
     CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CUH(cudaMalloc(&h->d_M, M.size() * sizeof(double)));
+    CUH(cudaMalloc(&h->d_C2, C2.size() * sizeof(double)));
     CUH(cudaMalloc(&h->d_Minv, Mt.size() * sizeof(double)));
-    CUH(cudaMemcpy(h->d_M, M.data(), M.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUH(cudaMemcpy(h->d_C2, C2.data(), C2.size() * sizeof(double), cudaMemcpyHostToDevice));
     CUH(cudaMemcpy(h->d_Minv, Mt.data(), Mt.size() * sizeof(double), cudaMemcpyHostToDevice));
-    d.M = h->d_M; d.Minv_tiled = h->d_Minv;
+    d.C2 = h->d_C2; d.Minv_tiled = h->d_Minv;
     CUH(cudaMalloc(&h->d_xref, (size_t)B * 12 * (N + 1) * sizeof(double)));
     CUH(cudaMalloc(&h->d_fsteps, (size_t)B * 260 * sizeof(double)));
 
@@ -428,5 +428,16 @@ int mpcqp_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops
     if (dmma_tflops) *dmma_tflops = best[1];
     return MPCQP_OK;
 }
+
+#ifdef MPCQP_PROFILE
+// debug builds only: read (and clear) the per-phase cycle counters
+int mpcqp_debug_profile(unsigned long long* out16) {
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16));
+    unsigned long long z[16] = {0};
+    CU(cudaMemcpyToSymbol(g_prof, z, sizeof(z)));
+    return MPCQP_OK;
+}
+#endif
 
 }  // extern "C"

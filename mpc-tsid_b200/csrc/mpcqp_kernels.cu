@@ -10,6 +10,19 @@
 // the optimum is the same point the reference's sparse QP has (strictly convex, unique).
 #include "mpcqp_device.cuh"
 
+// Optional phase timing (-DMPCQP_PROFILE): per-phase clock64() deltas of thread 0, summed over CTAs
+// into g_prof; read back through mpcqp_debug_profile().  Off in the shipped build.
+#ifdef MPCQP_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_T0() long long prof_t_ = clock64()
+#define PROF(slot) do { if (threadIdx.x == 0) { long long n_ = clock64(); atomicAdd(&g_prof[slot], (unsigned long long)(n_ - prof_t_)); prof_t_ = n_; } } while (0)
+#define PROF_COUNT(slot) do { if (threadIdx.x == 0) atomicAdd(&g_prof[slot], 1ull); } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF(slot) do {} while (0)
+#define PROF_COUNT(slot) do {} while (0)
+#endif
+
 namespace mpcqp {
 
 // -------------------------------------------------------------------------------------------------
@@ -27,10 +40,13 @@ struct Smem {
     double gam[NDIM];                       // gradient of the tracking cost w.r.t. the impulses at f = 0
     double u[NDIM];                         // impulse-space work vector (rhs / solution of W v = s)
     double ms[NDIM];                        // M u
+    double tmp[NDIM];                       // scratch of tri_solve
+    double C2[N * N];                       // C2[k,l] = sum_{i >= max(k,l)} (i-k)(i-l), constant
     double red[40];
     unsigned long long hist[16];            // hashes of signatures already tried (cycle detection)
+    unsigned long long mbar;                // mbarrier of the bulk (TMA) staging copies
     int flag;
-    int any;
+    unsigned int phase;                     // its phase parity
 };
 
 // per-foot data that stays in the registers of its owner thread (tid < 4N: k = tid >> 2, j = tid & 3)
@@ -149,19 +165,23 @@ __device__ __forceinline__ void free_response(const DevParams& P, const double* 
     }
 }
 
-// ms = M u   (six independent N x N Gram matrices, one per impulse component)
+// ms = M u   (six independent N x N Gram matrices, one per impulse component):
+//   M_c[k,l] = dt^2 Qp_c C2[k,l] + Qv_c C0[k,l],  C0[k,l] = N - max(k,l),  C2 from shared memory
 template <int N>
-__device__ __forceinline__ void gram_apply(const DevParams& P, const double* u, double* ms) {
+__device__ __forceinline__ void gram_apply(const DevParams& P, const double* C2, const double* u, double* ms) {
     for (int idx = threadIdx.x; idx < 6 * N; idx += blockDim.x) {
         const int k = idx / 6, c = idx - 6 * k;
-        const double* Mr = P.M + (c * N + k) * N;
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll 4
+        const double* row = C2 + k * N;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
         for (int l = 0; l < N; l += 2) {
-            a0 = fma(__ldg(Mr + l), u[6 * l + c], a0);
-            a1 = fma(__ldg(Mr + l + 1), u[6 * (l + 1) + c], a1);
+            const double u0 = u[6 * l + c], u1 = u[6 * (l + 1) + c];
+            a0 = fma(row[l], u0, a0);
+            a1 = fma(row[l + 1], u1, a1);
+            b0 = fma((double)(N - (k > l ? k : l)), u0, b0);
+            b1 = fma((double)(N - (k > l + 1 ? k : l + 1)), u1, b1);
         }
-        ms[idx] = a0 + a1;
+        ms[idx] = P.dt * P.dt * P.wp[c] * (a0 + a1) + P.wv[c] * (b0 + b1);
     }
 }
 
@@ -194,14 +214,19 @@ __device__ __forceinline__ void make_face(const DevParams& P, const Foot& ft, ui
     }
 }
 
-// W = M^-1 + blockdiag_k( sum_j sum_col d_col b_col b_col' )   written in tile layout
+// W = M^-1 + blockdiag_k( sum_j sum_col d_col b_col b_col' )   written in tile layout.
+// The constant part (40 KB, L2 resident) is staged by one bulk async copy (TMA path) that overlaps
+// the per-foot arithmetic; its completion is observed on the CTA's mbarrier.
 template <int N, int NTILES>
-__device__ __forceinline__ void assemble_W(const DevParams& P, double* W, const Face& fc, int k, int j, bool foot_thread) {
-    // 1. copy the constant part (vectorised, coalesced; it lives in L2 after the first CTA touched it)
-    const double2* src = reinterpret_cast<const double2*>(P.Minv_tiled);
-    double2* dst = reinterpret_cast<double2*>(W);
-    for (int i = threadIdx.x; i < NTILES * 32; i += blockDim.x) dst[i] = __ldg(src + i);
-    // 2. the 6x6 block of step k: every foot computes its 21 entries, butterfly-sum over the 4 feet
+__device__ __forceinline__ void assemble_W(const DevParams& P, double* W, unsigned long long* mbar, unsigned int& phase,
+                                           const Face& fc, int k, int j, bool foot_thread) {
+    __syncthreads();                                    // nobody still reads the previous contents of W
+    if (threadIdx.x == 0) {
+        fence_async_smem();
+        mbar_expect_tx(mbar, NTILES * 64 * 8);
+        bulk_g2s(W, P.Minv_tiled, NTILES * 64 * 8, mbar);
+    }
+    // the 6x6 block of step k: every foot computes its 21 entries, butterfly-sum over the 4 feet
     double tkk[21];
     if (foot_thread) {
         int e = 0;
@@ -216,7 +241,8 @@ __device__ __forceinline__ void assemble_W(const DevParams& P, double* W, const 
             tkk[e] += shfl_xor_d(tkk[e], 2);
         }
     }
-    __syncthreads();
+    mbar_wait(mbar, phase);
+    phase ^= 1u;
     if (foot_thread) {
         int e = 0;
 #pragma unroll
@@ -242,14 +268,20 @@ struct SweepOut {
 // One equality-constrained solve on the faces given by `sig`, then the KKT guard and the next
 // active-set guess.  Leaves ft.f / ft.y (this foot's force and multipliers) and nsig.
 template <int N, bool ADMM>
-__device__ SweepOut sweep(const DevParams& P, Smem<N, ADMM>& sm, Foot& ft, uint8_t sig, uint8_t& nsig,
+__device__ SweepOut sweep(const DevParams& P, Smem<N, ADMM>& sm, unsigned int& phase, Foot& ft, uint8_t sig, uint8_t& nsig,
                           int k, int j, bool foot_thread) {
     using S = Smem<N, ADMM>;
     Face fc;
+    PROF_T0();
+    PROF_COUNT(15);
     if (foot_thread) make_face(P, ft, sig, fc);
-    assemble_W<N, S::NTILES>(P, sm.W, fc, k, j, foot_thread);
+    assemble_W<N, S::NTILES>(P, sm.W, &sm.mbar, phase, fc, k, j, foot_thread);
+    PROF(0);
     SweepOut out;
     out.spd = cholesky_tiles<S::NT, 4>(sm.W, &sm.flag);
+    PROF(1);
+    invert_tiles<S::NT, 4>(sm.W);
+    PROF(6);
     out.ok = false;
     if (!out.spd) return out;
 
@@ -274,13 +306,14 @@ __device__ SweepOut sweep(const DevParams& P, Smem<N, ADMM>& sm, Foot& ft, uint8
                 step_sum_store(v, sm.u + 6 * k, j);
             }
             __syncthreads();
-            gram_apply<N>(P, sm.u, sm.ms);
+            gram_apply<N>(P, sm.C2, sm.u, sm.ms);
             __syncthreads();
             if (foot_thread) {
                 bvT_apply(ft, sm.ms + 6 * k, grad);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) grad[c] += P.w_force * f[c] + ft.g[c];
             }
+            PROF(2);
         } else if (foot_thread) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) grad[c] = ft.g[c];
@@ -298,8 +331,9 @@ __device__ SweepOut sweep(const DevParams& P, Smem<N, ADMM>& sm, Foot& ft, uint8
             step_sum_store(v, sm.u + 6 * k, j);
         }
         __syncthreads();
-        solve_tiles_warp0<S::NT>(sm.W, sm.u);
-        __syncthreads();
+        PROF(3);
+        tri_solve<S::NT>(sm.W, sm.u, sm.tmp);
+        PROF(4);
         if (foot_thread) {
             const double* v = sm.u + 6 * k;
             double ax = 0.0, ay = 0.0, az = 0.0;
@@ -367,6 +401,7 @@ __device__ SweepOut sweep(const DevParams& P, Smem<N, ADMM>& sm, Foot& ft, uint8
         for (int r = 0; r < 5; ++r) ft.y[r] = 0.0;
     }
     out.ok = __syncthreads_and(ok ? 1 : 0) != 0;
+    PROF(5);
     return out;
 }
 
@@ -479,20 +514,27 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
     const bool foot_thread = tid < 4 * N;
     const int k = tid >> 2, j = tid & 3;
 
+    unsigned int phase = 0;
+    if (tid == 0) mbar_init(&sm.mbar, 1);
+    for (int i = tid; i < N * N; i += blockDim.x) sm.C2[i] = __ldg(P.C2 + i);
+    __syncthreads();
+
     int n_work = ADMM ? *st.fb_count : P.batch;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int inst = ADMM ? st.fb_list[w] : w;
         __syncthreads();
-        // ---- stage inputs in shared memory (two contiguous, 16-byte aligned blocks per instance)
-        {
-            const double2* gx = reinterpret_cast<const double2*>(xref_g + (size_t)inst * 12 * (N + 1));
-            const double2* gf = reinterpret_cast<const double2*>(fsteps_g + (size_t)inst * 260);
-            double2* sx = reinterpret_cast<double2*>(sm.xr);
-            double2* sf = reinterpret_cast<double2*>(sm.fs);
-            for (int i = tid; i < 6 * (N + 1); i += blockDim.x) sx[i] = __ldg(gx + i);
-            for (int i = tid; i < 130; i += blockDim.x) sf[i] = __ldg(gf + i);
+#ifdef MPCQP_PROFILE
+        const long long inst_t0 = clock64();
+#endif
+        // ---- stage inputs in shared memory: two bulk async copies (16-byte aligned blocks per instance)
+        if (tid == 0) {
+            fence_async_smem();
+            mbar_expect_tx(&sm.mbar, (12 * (N + 1) + 260) * 8);
+            bulk_g2s(sm.xr, xref_g + (size_t)inst * 12 * (N + 1), 12 * (N + 1) * 8, &sm.mbar);
+            bulk_g2s(sm.fs, fsteps_g + (size_t)inst * 260, 260 * 8, &sm.mbar);
         }
-        __syncthreads();
+        mbar_wait(&sm.mbar, phase);
+        phase ^= 1u;
         Foot ft;
         bool bad = false;
         uint8_t sig = SIG_FREE;
@@ -534,7 +576,7 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
                 if (tid == 0 && nhist < 15) sm.hist[nhist] = h;
                 nhist = (nhist < 15) ? nhist + 1 : nhist;
                 uint8_t nsig;
-                const SweepOut so = sweep<N, ADMM>(P, sm, ft, sig, nsig, k, j, foot_thread);
+                const SweepOut so = sweep<N, ADMM>(P, sm, phase, ft, sig, nsig, k, j, foot_thread);
                 ++sweeps;
                 if (!so.spd) break;
                 if (so.ok) { done = true; status = 1; }
@@ -577,8 +619,9 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
                 ddz = ft.contact ? 1.0 / (P.w_force + sigma + rho * (4.0 * mu * mu + 1.0)) : 0.0;
                 fa.dx = ddx; fa.dy = ddx; fa.dz = ddz;
             }
-            assemble_W<N, S::NTILES>(P, sm.W2, fa, k, j, foot_thread);
+            assemble_W<N, S::NTILES>(P, sm.W2, &sm.mbar, phase, fa, k, j, foot_thread);
             const bool spd = cholesky_tiles<S::NT, 4>(sm.W2, &sm.flag);
+            if (spd) invert_tiles<S::NT, 4>(sm.W2);
             uint8_t prev_sig = 255;
             int stable = 0;
             while (spd && !done && iters < P.max_iter) {
@@ -596,8 +639,7 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
                     step_sum_store(v, sm.u + 6 * k, j);
                 }
                 __syncthreads();
-                solve_tiles_warp0<S::NT>(sm.W2, sm.u);
-                __syncthreads();
+                tri_solve<S::NT>(sm.W2, sm.u, sm.tmp);
                 uint8_t cur = SIG_FREE;
                 if (foot_thread && ft.contact) {
                     const double* v = sm.u + 6 * k;
@@ -633,7 +675,7 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
                         stable = 0;
                         uint8_t nsig;
                         Foot trial = ft;
-                        const SweepOut so = sweep<N, ADMM>(P, sm, trial, cur, nsig, k, j, foot_thread);
+                        const SweepOut so = sweep<N, ADMM>(P, sm, phase, trial, cur, nsig, k, j, foot_thread);
                         ++sweeps;
                         if (so.spd && so.ok) { ft = trial; sig = cur; done = true; status = 1; }
                     }
@@ -651,6 +693,9 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
             }
         }
         finish<N, ADMM>(P, sm, st, inst, ft, sig, k, j, foot_thread, status, sweeps, iters);
+#ifdef MPCQP_PROFILE
+        if (threadIdx.x == 0) { atomicAdd(&g_prof[ADMM ? 13 : 12], (unsigned long long)(clock64() - inst_t0)); atomicAdd(&g_prof[ADMM ? 11 : 10], 1ull); }
+#endif
     }
 }
 
