@@ -79,6 +79,8 @@ typedef struct mpcqp_params {
     double alpha;               /* ADMM relaxation */
     double feas_tol;            /* primal feasibility tolerance of the KKT guard [N] */
     double dual_tol;            /* multiplier sign tolerance of the KKT guard */
+    int32_t refine;             /* iterative-refinement passes per equality-constrained solve (0 or 1) */
+    int32_t reserved;
 } mpcqp_params;
 
 /* Reference constants of MPC.py:22-82 for the Solo trot configuration (dt 0.02, N 16, T_gait 0.32). */

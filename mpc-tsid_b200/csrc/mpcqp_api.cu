@@ -112,6 +112,7 @@ void mpcqp_default_params(mpcqp_params* p) {
     p->alpha = 1.6;
     p->feas_tol = 1e-9;
     p->dual_tol = 1e-12;
+    p->refine = 0;
 }
 
 int mpcqp_destroy(mpcqp_handle* h) {
@@ -171,7 +172,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     d.rho = p->rho; d.sigma = p->sigma; d.alpha = p->alpha; d.feas_tol = p->feas_tol; d.dual_tol = p->dual_tol;
     d.max_sweeps = p->max_sweeps; d.max_iter = p->max_iter; d.min_iter = p->min_iter > 0 ? p->min_iter : 1;
     d.check_every = p->check_every > 0 ? p->check_every : 1;
-    d.warm_start = p->warm_start; d.mode = p->mode; d.refine = 1;
+    d.warm_start = p->warm_start; d.mode = p->mode; d.refine = p->refine > 0 ? 1 : 0;
 
     // Gram matrices of the double-integrator response and their inverses (constant per handle)
     //   M_c[k,l] = sum_{i >= max(k,l)} ( dt^2 Qp_c (i-k)(i-l) + Qv_c ),  i = 0..N-1

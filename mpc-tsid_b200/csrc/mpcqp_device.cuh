@@ -102,89 +102,181 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 // On exit: off-diagonal tiles hold L_IJ, diagonal tiles hold inv(L_JJ) (lower triangular).
 // Returns false (CTA-uniform) if a pivot is not positive.
 // ---------------------------------------------------------------------------------------------
+// sum_{K in [K0, K1)} L_IK L_JK'  accumulated into (c0, c1) with two independent DMMA chains
+__device__ __forceinline__ void syrk_accumulate(const double* __restrict__ rowI, const double* __restrict__ rowJ,
+                                                int K0, int K1, int fo, double& c0, double& c1) {
+    double e0 = 0.0, e1 = 0.0;
+    int K = K0;
+#pragma unroll 2
+    for (; K + 1 < K1; K += 2) {
+        const double a0 = rowI[K * 64 + fo], a1 = rowI[K * 64 + 32 + fo];
+        const double b0 = rowJ[K * 64 + fo], b1 = rowJ[K * 64 + 32 + fo];
+        const double a2 = rowI[K * 64 + 64 + fo], a3 = rowI[K * 64 + 96 + fo];
+        const double b2 = rowJ[K * 64 + 64 + fo], b3 = rowJ[K * 64 + 96 + fo];
+        dmma884(c0, c1, a0, b0);
+        dmma884(e0, e1, a2, b2);
+        dmma884(c0, c1, a1, b1);
+        dmma884(e0, e1, a3, b3);
+    }
+    if (K < K1) {
+        const double a0 = rowI[K * 64 + fo], a1 = rowI[K * 64 + 32 + fo];
+        const double b0 = rowJ[K * 64 + fo], b1 = rowJ[K * 64 + 32 + fo];
+        dmma884(c0, c1, a0, b0);
+        dmma884(e0, e1, a1, b1);
+    }
+    c0 += e0; c1 += e1;
+}
+
+// 8x8 diagonal tile in shared memory (both triangles valid) -> inv(chol(tile)), lower triangular,
+// written back in place.  Every lane of the calling warp runs the same pivot chain in registers
+// (rsqrt, scale, rank-1 update: no shuffle or memory hop between dependent steps); lane c < 8 then
+// builds column c of the inverse by forward substitution.  Kept out of line so that its 36-double
+// working set does not inflate the register allocation of the tile loop around it.
+__device__ __noinline__ void diag_factor_invert(double* __restrict__ D, int lane, int* __restrict__ flag) {
+    double L[36];                                       // packed lower triangle
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) L[r * (r + 1) / 2 + c] = D[elem_off(r, c)];
+    __syncwarp();
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double d = L[j * (j + 1) / 2 + j];
+        ok = ok && (d > 0.0);
+        const double inv = rsqrt(d);
+        L[j * (j + 1) / 2 + j] = inv;                   // keep 1 / l_jj on the diagonal
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) L[i * (i + 1) / 2 + j] *= inv;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+            for (int c = j + 1; c <= i; ++c)
+                L[i * (i + 1) / 2 + c] = fma(-L[i * (i + 1) / 2 + j], L[c * (c + 1) / 2 + j], L[i * (i + 1) / 2 + c]);
+    }
+    const int cc = lane & 7;
+    double x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < r; ++k) sum = (k >= cc) ? fma(L[r * (r + 1) / 2 + k], x[k], sum) : sum;
+        const double dr = L[r * (r + 1) / 2 + r];
+        x[r] = (r == cc) ? dr : ((r > cc) ? -sum * dr : 0.0);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) D[elem_off(r, lane)] = x[r];
+        if (!ok) *flag = 0;
+    }
+}
+
+// One tile of X = inv(L):  X_RJ = -inv(L_RR) * sum_{K=J..R-1} L_RK X_KJ   (C fragment in o0, o1).
+// Needs rows < R of X and row R of L in shared memory.
+__device__ __forceinline__ void xinv_tile(const double* __restrict__ Wt, int R, int Jc, int lane, double& o0, double& o1) {
+    const int g = lane >> 2, t = lane & 3;
+    const int fo = g * 4 + t;                                        // A operand: element (g, t + 4kk)
+    const int bo = (g >> 2) * 32 + t * 4 + (g & 3);                  // B operand: element (t + 4kk, g) -> + 16 kk
+    const double* rowR = Wt + tile_index(R, 0) * 64;
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+    int K = Jc;
+#pragma unroll 2
+    for (; K + 1 < R; K += 2) {
+        const double* XA = Wt + tile_index(K, Jc) * 64;
+        const double* XB = Wt + tile_index(K + 1, Jc) * 64;
+        const double a0 = rowR[K * 64 + fo], a1 = rowR[K * 64 + 32 + fo];
+        const double a2 = rowR[K * 64 + 64 + fo], a3 = rowR[K * 64 + 96 + fo];
+        const double b0 = XA[bo], b1 = XA[bo + 16], b2 = XB[bo], b3 = XB[bo + 16];
+        dmma884(c0, c1, a0, b0);
+        dmma884(e0, e1, a2, b2);
+        dmma884(c0, c1, a1, b1);
+        dmma884(e0, e1, a3, b3);
+    }
+    if (K < R) {
+        const double* XA = Wt + tile_index(K, Jc) * 64;
+        dmma884(c0, c1, rowR[K * 64 + fo], XA[bo]);
+        dmma884(e0, e1, rowR[K * 64 + 32 + fo], XA[bo + 16]);
+    }
+    c0 += e0; c1 += e1;
+    // B operand of the last product is the accumulator itself, re-laid by shuffles (rows t, t + 4)
+    const double* Drr = Wt + tile_index(R, R) * 64;
+    const int s0 = t * 4 + (g >> 1), s1 = s0 + 16;
+    const double v00 = shfl_d(c0, s0), v01 = shfl_d(c1, s0);
+    const double v10 = shfl_d(c0, s1), v11 = shfl_d(c1, s1);
+    const double bb0 = (g & 1) ? v01 : v00;
+    const double bb1 = (g & 1) ? v11 : v10;
+    double d0 = 0.0, d1 = 0.0;
+    dmma884(d0, d1, Drr[fo], bb0);
+    dmma884(d0, d1, Drr[32 + fo], bb1);
+    o0 = -d0; o1 = -d1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cholesky W = L L' of the (8 NT x 8 NT) SPD matrix held as lower 8x8 tiles in shared memory,
+// fused with the in-place inversion of the factor: on exit every tile holds X = inv(L), so that
+// every later solve W v = s is two fully parallel mat-vecs, v = X'(X s)  (tri_solve).
+//
+//   * left-looking over tile columns; trailing updates, panel solves and the inversion run on the
+//     FP64 tensor pipe (DMMA m8n8k4);
+//   * the 8x8 diagonal tile is factorised redundantly in the registers of every lane of its owner
+//     warp (the pivot chain -- rsqrt, scale, update -- has no shuffle or memory hop in it) and
+//     inverted column-per-lane; tile I of a column belongs to warp I % NWARPS so this serial part
+//     rotates over the warps / the SM's four schedulers;
+//   * the pivot chain is the critical path, so everything else is scheduled into its shadow:
+//     while the owner factorises diagonal tile J, the other warps (a) pre-accumulate the update of
+//     column J + 1 over the columns that are already final and (b) compute row J - 1 of X, which
+//     overwrites row J - 1 of L (dead for the factorisation by then) one barrier later.
+// Returns false (CTA-uniform) if a pivot is not positive.
+// ---------------------------------------------------------------------------------------------
 template <int NT, int NWARPS>
-__device__ bool cholesky_tiles(double* __restrict__ Wt, int* __restrict__ flag) {
+__device__ bool factor_invert_tiles(double* __restrict__ Wt, int* __restrict__ flag) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int fo = g * 4 + t;                                   // operand fragment offset inside a panel
     const int co = (t >> 1) * 32 + g * 4 + (t & 1) * 2;         // C fragment offset (cols 2t, 2t+1 of row g)
     constexpr int MAXT = (NT + NWARPS - 1) / NWARPS;
+    constexpr int XT = (NT - 1 + NWARPS - 2) / (NWARPS - 1);    // X-row tiles per non-owner warp
     if (threadIdx.x == 0) *flag = 1;
-    for (int J = 0; J < NT; ++J) {
-        double c0[MAXT], c1[MAXT];
-        const int I0 = J + ((warp - J) & (NWARPS - 1));         // first tile row >= J owned by this warp
-        const double* rowJ = Wt + tile_index(J, 0) * 64;
-        // ---- trailing update of tile column J (two accumulator pairs per tile: even / odd K)
+    double cur0[MAXT], cur1[MAXT], nxt0[MAXT], nxt1[MAXT], xr0[XT], xr1[XT];
 #pragma unroll
-        for (int m = 0; m < MAXT; ++m) {
-            const int I = I0 + m * NWARPS;
-            c0[m] = 0.0; c1[m] = 0.0;
-            if (I < NT) {
-                const double* rowI = Wt + tile_index(I, 0) * 64;
-                double e0 = 0.0, e1 = 0.0;
-                int K = 0;
-                for (; K + 1 < J; K += 2) {
-                    const double a0 = rowI[K * 64 + fo], a1 = rowI[K * 64 + 32 + fo];
-                    const double b0 = rowJ[K * 64 + fo], b1 = rowJ[K * 64 + 32 + fo];
-                    const double a2 = rowI[K * 64 + 64 + fo], a3 = rowI[K * 64 + 96 + fo];
-                    const double b2 = rowJ[K * 64 + 64 + fo], b3 = rowJ[K * 64 + 96 + fo];
-                    dmma884(c0[m], c1[m], a0, b0);
-                    dmma884(e0, e1, a2, b2);
-                    dmma884(c0[m], c1[m], a1, b1);
-                    dmma884(e0, e1, a3, b3);
-                }
-                if (K < J) {
-                    const double a0 = rowI[K * 64 + fo], a1 = rowI[K * 64 + 32 + fo];
-                    const double b0 = rowJ[K * 64 + fo], b1 = rowJ[K * 64 + 32 + fo];
-                    dmma884(c0[m], c1[m], a0, b0);
-                    dmma884(e0, e1, a1, b1);
-                }
-                const double2 w = *reinterpret_cast<const double2*>(Wt + tile_index(I, J) * 64 + co);
-                c0[m] = w.x - (c0[m] + e0);
-                c1[m] = w.y - (c1[m] + e1);
-            }
+    for (int m = 0; m < MAXT; ++m) {
+        const int I = warp + m * NWARPS;
+        cur0[m] = 0.0; cur1[m] = 0.0;
+        if (I < NT) {
+            const double2 w = *reinterpret_cast<const double2*>(Wt + tile_index(I, 0) * 64 + co);
+            cur0[m] = w.x; cur1[m] = w.y;
         }
-        // ---- diagonal tile: owner warp J % NWARPS holds it in slot 0
+    }
+    for (int J = 0; J < NT; ++J) {
+        const int I0 = J + ((warp - J) & (NWARPS - 1));         // first tile row >= J owned by this warp
+        const int I1 = J + 1 + ((warp - J - 1) & (NWARPS - 1)); // same for column J + 1
+        const bool owner = warp == (J & (NWARPS - 1));
+        const int rank = (warp - J - 1) & (NWARPS - 1);         // 0 .. NWARPS-2 among the non-owners
+        const double* rowN = Wt + tile_index(J + 1 < NT ? J + 1 : J, 0) * 64;
         double* D = Wt + tile_index(J, J) * 64;
-        if (warp == (J & (NWARPS - 1))) {
-            *reinterpret_cast<double2*>(D + co) = make_double2(c0[0], c1[0]);
+#pragma unroll
+        for (int m = 0; m < MAXT; ++m) { nxt0[m] = 0.0; nxt1[m] = 0.0; }
+        if (owner) {
+            // ---- diagonal tile, factorised redundantly by every lane of the owner warp
+            *reinterpret_cast<double2*>(D + co) = make_double2(cur0[0], cur1[0]);
             __syncwarp();
-            double L[36];                                       // packed lower triangle, every lane the same
+            diag_factor_invert(D, lane, flag);
+        } else {
+            // ---- in the shadow of the pivot chain: (a) look-ahead of column J + 1 over K < J
+            if (J + 1 < NT) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c <= r; ++c) L[r * (r + 1) / 2 + c] = D[elem_off(r, c)];
-            __syncwarp();
-            bool ok = true;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const double d = L[j * (j + 1) / 2 + j];
-                ok = ok && (d > 0.0);
-                const double inv = rsqrt(d);
-                L[j * (j + 1) / 2 + j] = inv;                   // keep 1 / l_jj on the diagonal
-#pragma unroll
-                for (int i = j + 1; i < 8; ++i) L[i * (i + 1) / 2 + j] *= inv;
-#pragma unroll
-                for (int i = j + 1; i < 8; ++i)
-#pragma unroll
-                    for (int c = j + 1; c <= i; ++c)
-                        L[i * (i + 1) / 2 + c] = fma(-L[i * (i + 1) / 2 + j], L[c * (c + 1) / 2 + j], L[i * (i + 1) / 2 + c]);
+                for (int m = 0; m < MAXT; ++m) {
+                    const int I = I1 + m * NWARPS;
+                    if (I < NT) syrk_accumulate(Wt + tile_index(I, 0) * 64, rowN, 0, J, fo, nxt0[m], nxt1[m]);
+                }
             }
-            // X = inv(L): lane c (< 8) builds column c by forward substitution, all in registers
-            const int cc = lane & 7;
-            double x[8];
+            // (b) row J - 1 of X (kept in registers until the barrier below)
+            if (J >= 2) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                double sum = 0.0;
-#pragma unroll
-                for (int k = 0; k < r; ++k) sum = (k >= cc) ? fma(L[r * (r + 1) / 2 + k], x[k], sum) : sum;
-                const double dr = L[r * (r + 1) / 2 + r];
-                x[r] = (r == cc) ? dr : ((r > cc) ? -sum * dr : 0.0);
-            }
-            if (lane < 8) {
-#pragma unroll
-                for (int r = 0; r < 8; ++r) D[elem_off(r, lane)] = x[r];
-                if (!ok) *flag = 0;
+                for (int m = 0; m < XT; ++m) {
+                    const int Jc = rank + m * (NWARPS - 1);
+                    if (Jc < J - 1) xinv_tile(Wt, J - 1, Jc, lane, xr0[m], xr1[m]);
+                }
             }
         }
         __syncthreads();
@@ -195,8 +287,8 @@ __device__ bool cholesky_tiles(double* __restrict__ Wt, int* __restrict__ flag) 
             const int I = I0 + m * NWARPS;
             if (I < NT && I > J) {
                 const int s0 = g * 4 + (t >> 1), s1 = s0 + 2;
-                const double v00 = shfl_d(c0[m], s0), v01 = shfl_d(c1[m], s0);
-                const double v10 = shfl_d(c0[m], s1), v11 = shfl_d(c1[m], s1);
+                const double v00 = shfl_d(cur0[m], s0), v01 = shfl_d(cur1[m], s0);
+                const double v10 = shfl_d(cur0[m], s1), v11 = shfl_d(cur1[m], s1);
                 const double a0 = (t & 1) ? v01 : v00;
                 const double a1 = (t & 1) ? v11 : v10;
                 double d0 = 0.0, d1 = 0.0;
@@ -205,112 +297,113 @@ __device__ bool cholesky_tiles(double* __restrict__ Wt, int* __restrict__ flag) 
                 *reinterpret_cast<double2*>(Wt + tile_index(I, J) * 64 + co) = make_double2(d0, d1);
             }
         }
+        if (!owner && J >= 2) {
+#pragma unroll
+            for (int m = 0; m < XT; ++m) {
+                const int Jc = rank + m * (NWARPS - 1);
+                if (Jc < J - 1) *reinterpret_cast<double2*>(Wt + tile_index(J - 1, Jc) * 64 + co) = make_double2(xr0[m], xr1[m]);
+            }
+        }
+        __syncthreads();
+        // ---- finish column J + 1: add the K = J term (the owner of J also its K < J part), C = W - sum
+        if (J + 1 < NT) {
+#pragma unroll
+            for (int m = 0; m < MAXT; ++m) {
+                const int I = I1 + m * NWARPS;
+                cur0[m] = 0.0; cur1[m] = 0.0;
+                if (I < NT) {
+                    const double* rowI = Wt + tile_index(I, 0) * 64;
+                    syrk_accumulate(rowI, rowN, owner ? 0 : J, J + 1, fo, nxt0[m], nxt1[m]);
+                    const double2 w = *reinterpret_cast<const double2*>(Wt + tile_index(I, J + 1) * 64 + co);
+                    cur0[m] = w.x - nxt0[m];
+                    cur1[m] = w.y - nxt1[m];
+                }
+            }
+        }
+    }
+    // ---- last row of X, all warps
+    {
+        double l0[MAXT], l1[MAXT];
+#pragma unroll
+        for (int m = 0; m < MAXT; ++m) {
+            const int Jc = warp + m * NWARPS;
+            if (Jc < NT - 1) xinv_tile(Wt, NT - 1, Jc, lane, l0[m], l1[m]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < MAXT; ++m) {
+            const int Jc = warp + m * NWARPS;
+            if (Jc < NT - 1) *reinterpret_cast<double2*>(Wt + tile_index(NT - 1, Jc) * 64 + co) = make_double2(l0[m], l1[m]);
+        }
         __syncthreads();
     }
     return *flag != 0;
 }
 
-// ---------------------------------------------------------------------------------------------
-// In-place inverse of the block lower-triangular factor: on entry off-diagonal tiles hold L_IJ and
-// diagonal tiles inv(L_JJ); on exit every tile holds X = inv(L).  Row by row,
-//     X_IJ = -inv(L_II) * sum_{K=J..I-1} L_IK X_KJ,
-// all tiles of a row in parallel on the FP64 tensor pipe (tile J of the row -> warp J % NWARPS).
-// With X explicit the two triangular solves of every later linear solve become two fully parallel
-// mat-vecs (tri_solve) instead of 2 * NT dependent block steps.
-// ---------------------------------------------------------------------------------------------
+// v = X' (X s) = inv(L L') s, in place in shared memory (s has 8 NT entries, tmp is scratch of the
+// same size).  Every warp reads whole 8x8 tiles with the C-fragment access pattern (one conflict-
+// free 16-byte load per lane): lane (g, t) holds X[g][2t], X[g][2t+1].  Warp w owns tile rows
+// (pass 1) / tile columns (pass 2) w, w + NWARPS, ...   Ends with a __syncthreads().
 template <int NT, int NWARPS>
-__device__ void invert_tiles(double* __restrict__ Wt) {
+__device__ void tri_solve(const double* __restrict__ Wt, double* __restrict__ s, double* __restrict__ tmp) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int fo = g * 4 + t;                                        // A operand: element (g, t + 4kk)
-    const int bo = (g >> 2) * 32 + t * 4 + (g & 3);                  // B operand: element (t + 4kk, g) -> + 16 kk
     const int co = (t >> 1) * 32 + g * 4 + (t & 1) * 2;
     constexpr int MAXT = (NT + NWARPS - 1) / NWARPS;
-    for (int I = 1; I < NT; ++I) {
-        double c0[MAXT], c1[MAXT];
-        const double* rowI = Wt + tile_index(I, 0) * 64;
+    // ---- y = X s : row 8I + g, partial over columns (2t, 2t+1) of every tile, reduced over t
+    {
+        double a0[MAXT], a1[MAXT];
 #pragma unroll
         for (int m = 0; m < MAXT; ++m) {
-            const int J = warp + m * NWARPS;
-            c0[m] = 0.0; c1[m] = 0.0;
-            if (J < I) {
-                double e0 = 0.0, e1 = 0.0;
-                int K = J;
-                for (; K + 1 < I; K += 2) {
-                    const double* XA = Wt + tile_index(K, J) * 64;
-                    const double* XB = Wt + tile_index(K + 1, J) * 64;
-                    const double a0 = rowI[K * 64 + fo], a1 = rowI[K * 64 + 32 + fo];
-                    const double a2 = rowI[K * 64 + 64 + fo], a3 = rowI[K * 64 + 96 + fo];
-                    const double b0 = XA[bo], b1 = XA[bo + 16], b2 = XB[bo], b3 = XB[bo + 16];
-                    dmma884(c0[m], c1[m], a0, b0);
-                    dmma884(e0, e1, a2, b2);
-                    dmma884(c0[m], c1[m], a1, b1);
-                    dmma884(e0, e1, a3, b3);
+            const int I = warp + m * NWARPS;
+            a0[m] = 0.0; a1[m] = 0.0;
+            if (I < NT) {
+                const double* T = Wt + tile_index(I, 0) * 64 + co;
+#pragma unroll 4
+                for (int J = 0; J <= I; ++J) {
+                    const double2 x = *reinterpret_cast<const double2*>(T + J * 64);
+                    const double2 sv = *reinterpret_cast<const double2*>(s + 8 * J + 2 * t);
+                    a0[m] = fma(x.x, sv.x, a0[m]);
+                    a1[m] = fma(x.y, sv.y, a1[m]);
                 }
-                if (K < I) {
-                    const double* XA = Wt + tile_index(K, J) * 64;
-                    const double a0 = rowI[K * 64 + fo], a1 = rowI[K * 64 + 32 + fo];
-                    dmma884(c0[m], c1[m], a0, XA[bo]);
-                    dmma884(e0, e1, a1, XA[bo + 16]);
-                }
-                c0[m] += e0; c1[m] += e1;
-                // X_IJ = -inv(L_II) * acc : A = inv(L_II) from smem, B = acc re-laid by shuffles
-                const double* Dii = Wt + tile_index(I, I) * 64;
-                const int s0 = t * 4 + (g >> 1), s1 = s0 + 16;       // lanes holding rows t, t + 4 of acc
-                const double v00 = shfl_d(c0[m], s0), v01 = shfl_d(c1[m], s0);
-                const double v10 = shfl_d(c0[m], s1), v11 = shfl_d(c1[m], s1);
-                const double bb0 = (g & 1) ? v01 : v00;
-                const double bb1 = (g & 1) ? v11 : v10;
-                double d0 = 0.0, d1 = 0.0;
-                dmma884(d0, d1, Dii[fo], bb0);
-                dmma884(d0, d1, Dii[32 + fo], bb1);
-                c0[m] = -d0; c1[m] = -d1;
             }
         }
-        __syncthreads();                                             // every read of row I's L tiles is done
+#pragma unroll
+        for (int m = 0; m < MAXT; ++m) {
+            double v = a0[m] + a1[m];
+            v += shfl_xor_d(v, 1);
+            v += shfl_xor_d(v, 2);
+            const int I = warp + m * NWARPS;
+            if (I < NT && t == 0) tmp[8 * I + g] = v;
+        }
+    }
+    __syncthreads();
+    // ---- v = X' y : columns 8J + 2t, 8J + 2t + 1, partial over row g of every tile, reduced over g
+    {
+        double a0[MAXT], a1[MAXT];
 #pragma unroll
         for (int m = 0; m < MAXT; ++m) {
             const int J = warp + m * NWARPS;
-            if (J < I) *reinterpret_cast<double2*>(Wt + tile_index(I, J) * 64 + co) = make_double2(c0[m], c1[m]);
+            a0[m] = 0.0; a1[m] = 0.0;
+            if (J < NT) {
+#pragma unroll 4
+                for (int I = J; I < NT; ++I) {
+                    const double2 x = *reinterpret_cast<const double2*>(Wt + tile_index(I, J) * 64 + co);
+                    const double yv = tmp[8 * I + g];
+                    a0[m] = fma(x.x, yv, a0[m]);
+                    a1[m] = fma(x.y, yv, a1[m]);
+                }
+            }
         }
-        __syncthreads();
-    }
-}
-
-// v = X' (X s) = inv(L L') s, in place in shared memory (s has 8 NT entries).  All threads take
-// part; `tmp` is 8 NT doubles of scratch.  Ends with a __syncthreads().
-template <int NT>
-__device__ void tri_solve(const double* __restrict__ Wt, double* __restrict__ s, double* __restrict__ tmp) {
-    const int n = 8 * NT;
-    // y = X s : one row per thread, long rows first (thread 0 takes the last row)
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        const int i = n - 1 - idx, I = i >> 3, r = i & 7;
-        const double* T = Wt + tile_index(I, 0) * 64 + r * 4;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        for (int J = 0; J <= I; ++J) {
-            const double2 p0 = *reinterpret_cast<const double2*>(T + J * 64);
-            const double2 p1 = *reinterpret_cast<const double2*>(T + J * 64 + 2);
-            const double2 p2 = *reinterpret_cast<const double2*>(T + J * 64 + 32);
-            const double2 p3 = *reinterpret_cast<const double2*>(T + J * 64 + 34);
-            const double* sv = s + 8 * J;
-            a0 = fma(p0.x, sv[0], a0); a1 = fma(p0.y, sv[1], a1); a2 = fma(p1.x, sv[2], a2); a3 = fma(p1.y, sv[3], a3);
-            a0 = fma(p2.x, sv[4], a0); a1 = fma(p2.y, sv[5], a1); a2 = fma(p3.x, sv[6], a2); a3 = fma(p3.y, sv[7], a3);
+#pragma unroll
+        for (int m = 0; m < MAXT; ++m) {
+            double v0 = a0[m], v1 = a1[m];
+            v0 += shfl_xor_d(v0, 4);  v1 += shfl_xor_d(v1, 4);
+            v0 += shfl_xor_d(v0, 8);  v1 += shfl_xor_d(v1, 8);
+            v0 += shfl_xor_d(v0, 16); v1 += shfl_xor_d(v1, 16);
+            const int J = warp + m * NWARPS;
+            if (J < NT && g == 0) *reinterpret_cast<double2*>(s + 8 * J + 2 * t) = make_double2(v0, v1);
         }
-        tmp[i] = (a0 + a1) + (a2 + a3);
-    }
-    __syncthreads();
-    // v = X' y : one column per thread, long columns first
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const int J = j >> 3, c = j & 7;
-        const int off = (c >> 2) * 32 + (c & 3);
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        for (int I = J; I < NT; ++I) {
-            const double* T = Wt + tile_index(I, J) * 64 + off;
-            const double* yv = tmp + 8 * I;
-            a0 = fma(T[0], yv[0], a0); a1 = fma(T[4], yv[1], a1); a2 = fma(T[8], yv[2], a2); a3 = fma(T[12], yv[3], a3);
-            a0 = fma(T[16], yv[4], a0); a1 = fma(T[20], yv[5], a1); a2 = fma(T[24], yv[6], a2); a3 = fma(T[28], yv[7], a3);
-        }
-        s[j] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
 }

@@ -25,6 +25,8 @@ __device__ unsigned long long g_prof[16];
 
 namespace mpcqp {
 
+constexpr int NWARPS = 4;           // warps per CTA (one CTA = one QP instance)
+
 // -------------------------------------------------------------------------------------------------
 // shared-memory plan of one CTA
 // -------------------------------------------------------------------------------------------------
@@ -33,10 +35,14 @@ struct Smem {
     static constexpr int NDIM = 6 * N;
     static constexpr int NT = NDIM / 8;
     static constexpr int NTILES = NT * (NT + 1) / 2;
-    double W[NTILES * 64];                  // factor of the sweep / polish system
-    double W2[ADMM ? NTILES * 64 : 8];      // factor of the ADMM system (ADMM stage only)
+    static constexpr int NF = 4 * N;        // foot-steps
+    double W[NTILES * 64];                  // sweep / polish system: W, then inv(L) in place
+    double W2[ADMM ? NTILES * 64 : 2];      // ADMM system (ADMM stage only)
     double xr[12 * (N + 1)];                // xref of this instance
-    double fs[20 * 13];                     // fsteps of this instance
+    union {
+        double fs[20 * 13];                 // fsteps of this instance (dead after decode)
+        double fa[12 * NF];                 // per foot-step, struct of arrays: A[9] = dt inv(R gI)[r]x, g[3]
+    };
     double gam[NDIM];                       // gradient of the tracking cost w.r.t. the impulses at f = 0
     double u[NDIM];                         // impulse-space work vector (rhs / solution of W v = s)
     double ms[NDIM];                        // M u
@@ -46,36 +52,52 @@ struct Smem {
     unsigned long long hist[16];            // hashes of signatures already tried (cycle detection)
     unsigned long long mbar;                // mbarrier of the bulk (TMA) staging copies
     int flag;
-    unsigned int phase;                     // its phase parity
+    int pad;
 };
 
-// per-foot data that stays in the registers of its owner thread (tid < 4N: k = tid >> 2, j = tid & 3)
-struct Foot {
-    double A[9];        // dt inv(R gI) [r]x, row major (angular rows of Bv)
-    double g[3];        // gradient of the objective w.r.t. this force at f = 0
-    double f[3];        // current force
-    double y[5];        // multipliers of the five pyramid rows
-    double lin;         // dt / m
-    bool contact;
-};
-
-// per-foot description of the affine face f = pf + Z q for one signature
+// per-foot description of the affine face f = pf + Z q selected by one signature:
+// Z has the columns ex (if zx), ey (if zy), (czx, czy, 1) (if zz); D = w_f Z'Z is diagonal.
 struct Face {
-    double bx[6], by[6], bz[6];     // Bv Z columns (zero when the column is absent)
-    double dx, dy, dz;              // 1 / (w_f |z_col|^2) or 0
+    double dx, dy, dz;              // 1 / (w_f |z_col|^2), or 0 when the column is absent
     double pf[3];
-    double czx, czy;                // x, y components of the z column (sx mu, sy mu)
+    double czx, czy;                // sx mu, sy mu
     bool zx, zy, zz;
 };
 
-__device__ __forceinline__ void bv_apply(const Foot& ft, const double f[3], double out[6]) {
-    out[0] = ft.lin * f[0]; out[1] = ft.lin * f[1]; out[2] = ft.lin * f[2];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) out[3 + r] = ft.A[3 * r] * f[0] + ft.A[3 * r + 1] * f[1] + ft.A[3 * r + 2] * f[2];
+__device__ __forceinline__ void make_face(const DevParams& P, bool contact, uint8_t sig, Face& fc) {
+    int sx, sy, tz;
+    sig_unpack(sig, sx, sy, tz);
+    const bool live = contact && tz != 1;
+    fc.zx = live && sx == 0;
+    fc.zy = live && sy == 0;
+    fc.zz = live && tz == 0;
+    fc.czx = sx * P.mu;
+    fc.czy = sy * P.mu;
+    const double w = P.w_force;
+    fc.dx = fc.zx ? 1.0 / w : 0.0;
+    fc.dy = fc.zy ? 1.0 / w : 0.0;
+    fc.dz = fc.zz ? 1.0 / (w * (1.0 + P.mu * P.mu * (double)(sx * sx + sy * sy))) : 0.0;
+    const bool top = live && tz == 2;
+    fc.pf[0] = top ? fc.czx * P.fz_max : 0.0;
+    fc.pf[1] = top ? fc.czy * P.fz_max : 0.0;
+    fc.pf[2] = top ? P.fz_max : 0.0;
 }
-__device__ __forceinline__ void bvT_apply(const Foot& ft, const double* v, double out[3]) {
+
+template <int NF>
+__device__ __forceinline__ void load_A(const double* fa, int t, double A[9]) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) out[c] = ft.lin * v[c] + ft.A[c] * v[3] + ft.A[3 + c] * v[4] + ft.A[6 + c] * v[5];
+    for (int i = 0; i < 9; ++i) A[i] = fa[i * NF + t];
+}
+
+// Bv f: rows 0..2 = (dt/m) f, rows 3..5 = A f
+__device__ __forceinline__ void bv_apply(const double A[9], double lin, const double f[3], double out[6]) {
+    out[0] = lin * f[0]; out[1] = lin * f[1]; out[2] = lin * f[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) out[3 + r] = A[3 * r] * f[0] + A[3 * r + 1] * f[1] + A[3 * r + 2] * f[2];
+}
+__device__ __forceinline__ void bvT_apply(const double A[9], double lin, const double* v, double out[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] = lin * v[c] + A[c] * v[3] + A[3 + c] * v[4] + A[6 + c] * v[5];
 }
 
 // sum a 6-vector over the four feet of a step (lanes 4k..4k+3) and let lane j == 0 store it
@@ -96,7 +118,7 @@ __device__ __forceinline__ void step_sum_store(double v[6], double* dst, int j) 
 // -------------------------------------------------------------------------------------------------
 template <int N>
 __device__ __forceinline__ void decode_foot(const DevParams& P, const double* xr, const double* fs, int k, int j,
-                                            bool first_tick, Foot& ft, bool& bad) {
+                                            bool first_tick, double A[9], bool& contact, bool& bad) {
     int row = -1;
     double cum = 0.0;
     for (int r = 0; r < 20; ++r) {
@@ -107,10 +129,10 @@ __device__ __forceinline__ void decode_foot(const DevParams& P, const double* xr
         cum += cnt;
     }
     double foot[3] = {0.0, 0.0, 0.0};
-    ft.contact = false;
+    contact = false;
     if (row >= 0) {
         const double x = fs[row * 13 + 1 + 3 * j];
-        ft.contact = !(isnan(x) || x == 0.0);        // MPC.py:650
+        contact = !(isnan(x) || x == 0.0);           // MPC.py:650
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const double v = fs[row * 13 + 1 + 3 * j + c];
@@ -137,11 +159,10 @@ __device__ __forceinline__ void decode_foot(const DevParams& P, const double* xr
     // dt * Ii * [r]x   (MPC.py:345-346, utils.py:179-185)
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        ft.A[3 * a + 0] = P.dt * (Ii[3 * a + 1] * r[2] - Ii[3 * a + 2] * r[1]);
-        ft.A[3 * a + 1] = P.dt * (Ii[3 * a + 2] * r[0] - Ii[3 * a + 0] * r[2]);
-        ft.A[3 * a + 2] = P.dt * (Ii[3 * a + 0] * r[1] - Ii[3 * a + 1] * r[0]);
+        A[3 * a + 0] = P.dt * (Ii[3 * a + 1] * r[2] - Ii[3 * a + 2] * r[1]);
+        A[3 * a + 1] = P.dt * (Ii[3 * a + 2] * r[0] - Ii[3 * a + 0] * r[2]);
+        A[3 * a + 2] = P.dt * (Ii[3 * a + 0] * r[1] - Ii[3 * a + 1] * r[0]);
     }
-    ft.lin = P.dt / P.mass;                                                  // MPC.py:119
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -155,13 +176,14 @@ __device__ __forceinline__ void free_response(const DevParams& P, const double* 
         const int k = idx / 6, c = idx - 6 * k;
         const double p0 = xr[c * (N + 1)], v0 = xr[(6 + c) * (N + 1)];
         const double gc = (c == 2) ? -P.gravity * P.dt : 0.0;                 // MPC.py:200-201
-        double acc = 0.0;
+        double acc0 = 0.0, acc1 = 0.0;
         for (int s = k + 1; s <= N; ++s) {
             const double ep = p0 + s * P.dt * v0 + P.dt * gc * (0.5 * s * (s - 1)) - xr[c * (N + 1) + s];
             const double ev = v0 + s * gc - xr[(6 + c) * (N + 1) + s];
-            acc += (double)(s - 1 - k) * P.dt * P.wp[c] * ep + P.wv[c] * ev;
+            acc0 = fma((double)(s - 1 - k) * P.dt * P.wp[c], ep, acc0);
+            acc1 = fma(P.wv[c], ev, acc1);
         }
-        gam[idx] = acc;
+        gam[idx] = acc0 + acc1;
     }
 }
 
@@ -172,74 +194,53 @@ __device__ __forceinline__ void gram_apply(const DevParams& P, const double* C2,
     for (int idx = threadIdx.x; idx < 6 * N; idx += blockDim.x) {
         const int k = idx / 6, c = idx - 6 * k;
         const double* row = C2 + k * N;
-        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
 #pragma unroll
-        for (int l = 0; l < N; l += 2) {
-            const double u0 = u[6 * l + c], u1 = u[6 * (l + 1) + c];
+        for (int l = 0; l < N; l += 4) {
+            const double u0 = u[6 * l + c], u1 = u[6 * (l + 1) + c], u2 = u[6 * (l + 2) + c], u3 = u[6 * (l + 3) + c];
             a0 = fma(row[l], u0, a0);
             a1 = fma(row[l + 1], u1, a1);
+            a2 = fma(row[l + 2], u2, a2);
+            a3 = fma(row[l + 3], u3, a3);
             b0 = fma((double)(N - (k > l ? k : l)), u0, b0);
             b1 = fma((double)(N - (k > l + 1 ? k : l + 1)), u1, b1);
+            b2 = fma((double)(N - (k > l + 2 ? k : l + 2)), u2, b2);
+            b3 = fma((double)(N - (k > l + 3 ? k : l + 3)), u3, b3);
         }
-        ms[idx] = P.dt * P.dt * P.wp[c] * (a0 + a1) + P.wv[c] * (b0 + b1);
+        ms[idx] = P.dt * P.dt * P.wp[c] * ((a0 + a1) + (a2 + a3)) + P.wv[c] * ((b0 + b1) + (b2 + b3));
     }
 }
 
-__device__ __forceinline__ void make_face(const DevParams& P, const Foot& ft, uint8_t sig, Face& fc) {
-    int sx, sy, tz;
-    sig_unpack(sig, sx, sy, tz);
-    const bool live = ft.contact && tz != 1;
-    fc.zx = live && sx == 0;
-    fc.zy = live && sy == 0;
-    fc.zz = live && tz == 0;
-    fc.czx = sx * P.mu;
-    fc.czy = sy * P.mu;
-    const double w = P.w_force;
-    fc.dx = fc.zx ? 1.0 / w : 0.0;
-    fc.dy = fc.zy ? 1.0 / w : 0.0;
-    fc.dz = fc.zz ? 1.0 / (w * (1.0 + P.mu * P.mu * (double)(sx * sx + sy * sy))) : 0.0;
-    const bool top = live && tz == 2;
-    fc.pf[0] = top ? fc.czx * P.fz_max : 0.0;
-    fc.pf[1] = top ? fc.czy * P.fz_max : 0.0;
-    fc.pf[2] = top ? P.fz_max : 0.0;
-    const double e0[3] = {1.0, 0.0, 0.0}, e1[3] = {0.0, 1.0, 0.0}, cz[3] = {fc.czx, fc.czy, 1.0};
-    bv_apply(ft, e0, fc.bx);
-    bv_apply(ft, e1, fc.by);
-    bv_apply(ft, cz, fc.bz);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        fc.bx[i] = fc.zx ? fc.bx[i] : 0.0;
-        fc.by[i] = fc.zy ? fc.by[i] : 0.0;
-        fc.bz[i] = fc.zz ? fc.bz[i] : 0.0;
-    }
-}
-
-// W = M^-1 + blockdiag_k( sum_j sum_col d_col b_col b_col' )   written in tile layout.
-// The constant part (40 KB, L2 resident) is staged by one bulk async copy (TMA path) that overlaps
-// the per-foot arithmetic; its completion is observed on the CTA's mbarrier.
+// W = M^-1 + blockdiag_k( sum_j Bv Z D^-1 Z' Bv' )   written in tile layout.
+// The constant part (40 KB, L2 resident) is staged by one bulk async copy (TMA path); the per-foot
+// arithmetic overlaps it and the 6x6 blocks are added once the copy has landed.
 template <int N, int NTILES>
-__device__ __forceinline__ void assemble_W(const DevParams& P, double* W, unsigned long long* mbar, unsigned int& phase,
-                                           const Face& fc, int k, int j, bool foot_thread) {
+__device__ __forceinline__ void assemble_W(const DevParams& P, double* W, const double* fa, unsigned long long* mbar,
+                                           unsigned int& phase, const Face& fc, double ddx, double ddz, bool admm,
+                                           int k, int j, bool foot_thread) {
     __syncthreads();                                    // nobody still reads the previous contents of W
     if (threadIdx.x == 0) {
         fence_async_smem();
         mbar_expect_tx(mbar, NTILES * 64 * 8);
         bulk_g2s(W, P.Minv_tiled, NTILES * 64 * 8, mbar);
     }
-    // the 6x6 block of step k: every foot computes its 21 entries, butterfly-sum over the 4 feet
-    double tkk[21];
+    // b[col][0..5]: the three columns of Bv Z
+    double b[3][6], d[3];
     if (foot_thread) {
-        int e = 0;
+        double A[9];
+        load_A<4 * N>(fa, threadIdx.x, A);
+        const double lin = P.dt / P.mass;
+        const double zx = fc.zx ? 1.0 : 0.0, zy = fc.zy ? 1.0 : 0.0, zz = fc.zz ? 1.0 : 0.0;
+        b[0][0] = lin * zx; b[0][1] = 0.0; b[0][2] = 0.0;
+        b[1][0] = 0.0; b[1][1] = lin * zy; b[1][2] = 0.0;
+        b[2][0] = lin * fc.czx * zz; b[2][1] = lin * fc.czy * zz; b[2][2] = lin * zz;
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = 0; b <= a; ++b)
-                tkk[e++] = fc.dx * fc.bx[a] * fc.bx[b] + fc.dy * fc.by[a] * fc.by[b] + fc.dz * fc.bz[a] * fc.bz[b];
-#pragma unroll
-        for (e = 0; e < 21; ++e) {
-            tkk[e] += shfl_xor_d(tkk[e], 1);
-            tkk[e] += shfl_xor_d(tkk[e], 2);
+        for (int r = 0; r < 3; ++r) {
+            b[0][3 + r] = A[3 * r] * zx;
+            b[1][3 + r] = A[3 * r + 1] * zy;
+            b[2][3 + r] = (A[3 * r] * fc.czx + A[3 * r + 1] * fc.czy + A[3 * r + 2]) * zz;
         }
+        d[0] = admm ? ddx * zx : fc.dx; d[1] = admm ? ddx * zy : fc.dy; d[2] = admm ? ddz * zz : fc.dz;
     }
     mbar_wait(mbar, phase);
     phase ^= 1u;
@@ -248,98 +249,102 @@ __device__ __forceinline__ void assemble_W(const DevParams& P, double* W, unsign
 #pragma unroll
         for (int a = 0; a < 6; ++a)
 #pragma unroll
-            for (int b = 0; b <= a; ++b, ++e) {
-                if ((e & 3) != j) continue;                      // the four feet share the 21 stores
-                const int gi = 6 * k + a, gj = 6 * k + b;
-                const int I = gi >> 3, J = gj >> 3;
-                double* T = W + tile_index(I, J) * 64;
-                T[elem_off(gi & 7, gj & 7)] += tkk[e];
-                if (I == J && a != b) T[elem_off(gj & 7, gi & 7)] += tkk[e];
+            for (int c = 0; c <= a; ++c, ++e) {
+                double v = d[0] * b[0][a] * b[0][c] + d[1] * b[1][a] * b[1][c] + d[2] * b[2][a] * b[2][c];
+                v += shfl_xor_d(v, 1);
+                v += shfl_xor_d(v, 2);
+                if ((e & 3) == j) {                              // the four feet share the 21 updates
+                    const int gi = 6 * k + a, gj = 6 * k + c;
+                    const int I = gi >> 3, J = gj >> 3;
+                    double* T = W + tile_index(I, J) * 64;
+                    T[elem_off(gi & 7, gj & 7)] += v;
+                    if (I == J && a != c) T[elem_off(gj & 7, gi & 7)] += v;
+                }
             }
     }
     __syncthreads();
 }
 
-struct SweepOut {
-    bool ok;            // KKT guard passed for every foot (CTA uniform)
-    bool spd;
+// per-foot results of one sweep
+struct FootSol {
+    double f[3];
+    double y[5];
 };
 
 // One equality-constrained solve on the faces given by `sig`, then the KKT guard and the next
-// active-set guess.  Leaves ft.f / ft.y (this foot's force and multipliers) and nsig.
+// active-set guess.  Returns (CTA-uniform) 1 if the guard passed for every foot, 0 if not, -1 if W
+// was not positive definite.
 template <int N, bool ADMM>
-__device__ SweepOut sweep(const DevParams& P, Smem<N, ADMM>& sm, unsigned int& phase, Foot& ft, uint8_t sig, uint8_t& nsig,
-                          int k, int j, bool foot_thread) {
+__device__ int sweep(const DevParams& P, Smem<N, ADMM>& sm, unsigned int& phase, bool contact, uint8_t sig,
+                     uint8_t& nsig, FootSol& sol, int k, int j, bool foot_thread) {
     using S = Smem<N, ADMM>;
+    constexpr int NF = 4 * N;
+    const int tid = threadIdx.x;
+    const double lin = P.dt / P.mass;
     Face fc;
     PROF_T0();
     PROF_COUNT(15);
-    if (foot_thread) make_face(P, ft, sig, fc);
-    assemble_W<N, S::NTILES>(P, sm.W, &sm.mbar, phase, fc, k, j, foot_thread);
+    make_face(P, foot_thread && contact, sig, fc);
+    assemble_W<N, S::NTILES>(P, sm.W, sm.fa, &sm.mbar, phase, fc, 0.0, 0.0, false, k, j, foot_thread);
     PROF(0);
-    SweepOut out;
-    out.spd = cholesky_tiles<S::NT, 4>(sm.W, &sm.flag);
+    const bool spd = factor_invert_tiles<S::NT, NWARPS>(sm.W, &sm.flag);
     PROF(1);
-    invert_tiles<S::NT, 4>(sm.W);
-    PROF(6);
-    out.ok = false;
-    if (!out.spd) return out;
+    if (!spd) return -1;
 
-    // gradient at the particular point pf (non-zero only when some foot sits on the fz_max face)
-    double grad[3] = {0.0, 0.0, 0.0};
+    // f = pf + Z q.  Pass 0 solves from pf; passes 1..refine are iterative-refinement steps on the
+    // reduced system; the last pass only evaluates the gradient at the final point for the guard.
     const bool have_pf = foot_thread && (fc.pf[2] != 0.0);
     const int any_pf = __syncthreads_or(have_pf ? 1 : 0);
-    double f[3] = {0.0, 0.0, 0.0};
-    if (foot_thread) { f[0] = fc.pf[0]; f[1] = fc.pf[1]; f[2] = fc.pf[2]; }
-    // pass 0 solves from pf; passes 1..refine are iterative-refinement steps on the reduced system;
-    // the last pass only evaluates the gradient at the final point for the KKT guard.
+    double f[3] = {fc.pf[0], fc.pf[1], fc.pf[2]};
+    double grad[3] = {0.0, 0.0, 0.0};
     for (int pass = 0;; ++pass) {
         // grad = H f + g  (H f skipped on pass 0 when f = pf = 0 everywhere)
         if (pass > 0 || any_pf) {
             if (foot_thread) {
-                double v[6];
-                bv_apply(ft, f, v);
-                if (!ft.contact) {
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) v[i] = 0.0;
-                }
+                double A[9], v[6];
+                load_A<NF>(sm.fa, tid, A);
+                bv_apply(A, lin, f, v);
                 step_sum_store(v, sm.u + 6 * k, j);
             }
             __syncthreads();
             gram_apply<N>(P, sm.C2, sm.u, sm.ms);
             __syncthreads();
             if (foot_thread) {
-                bvT_apply(ft, sm.ms + 6 * k, grad);
+                double A[9];
+                load_A<NF>(sm.fa, tid, A);
+                bvT_apply(A, lin, sm.ms + 6 * k, grad);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) grad[c] += P.w_force * f[c] + ft.g[c];
+                for (int c = 0; c < 3; ++c) grad[c] += P.w_force * f[c] + sm.fa[(9 + c) * NF + tid];
             }
             PROF(2);
         } else if (foot_thread) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) grad[c] = ft.g[c];
+            for (int c = 0; c < 3; ++c) grad[c] = sm.fa[(9 + c) * NF + tid];
         }
         if (pass == 1 + P.refine) break;
-        // reduced rhs r = -Z' grad, t = D^-1 r, s_k = sum_j (Bv Z) t
+        // reduced rhs r = -Z' grad, t = D^-1 r, s_k = sum_j Bv (Z t)
         double tx = 0.0, ty = 0.0, tz_ = 0.0;
         if (foot_thread) {
             tx = fc.zx ? -grad[0] * fc.dx : 0.0;
             ty = fc.zy ? -grad[1] * fc.dy : 0.0;
             tz_ = fc.zz ? -(fc.czx * grad[0] + fc.czy * grad[1] + grad[2]) * fc.dz : 0.0;
-            double v[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) v[i] = fc.bx[i] * tx + fc.by[i] * ty + fc.bz[i] * tz_;
+            const double zt[3] = {tx + fc.czx * tz_, ty + fc.czy * tz_, tz_};
+            double A[9], v[6];
+            load_A<NF>(sm.fa, tid, A);
+            bv_apply(A, lin, zt, v);
             step_sum_store(v, sm.u + 6 * k, j);
         }
         __syncthreads();
         PROF(3);
-        tri_solve<S::NT>(sm.W, sm.u, sm.tmp);
+        tri_solve<S::NT, NWARPS>(sm.W, sm.u, sm.tmp);
         PROF(4);
         if (foot_thread) {
-            const double* v = sm.u + 6 * k;
-            double ax = 0.0, ay = 0.0, az = 0.0;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) { ax += fc.bx[i] * v[i]; ay += fc.by[i] * v[i]; az += fc.bz[i] * v[i]; }
-            const double qx = tx - fc.dx * ax, qy = ty - fc.dy * ay, qz = tz_ - fc.dz * az;
+            double A[9], h[3];
+            load_A<NF>(sm.fa, tid, A);
+            bvT_apply(A, lin, sm.u + 6 * k, h);                 // Bv' v
+            const double qx = tx - fc.dx * (fc.zx ? h[0] : 0.0);
+            const double qy = ty - fc.dy * (fc.zy ? h[1] : 0.0);
+            const double qz = tz_ - fc.dz * (fc.zz ? (fc.czx * h[0] + fc.czy * h[1] + h[2]) : 0.0);
             f[0] += qx + fc.czx * qz;
             f[1] += qy + fc.czy * qz;
             f[2] += qz;
@@ -350,28 +355,31 @@ __device__ SweepOut sweep(const DevParams& P, Smem<N, ADMM>& sm, unsigned int& p
     // ---- multipliers, KKT guard, next signature (per foot)
     bool ok = true;
     nsig = sig;
-    if (foot_thread && ft.contact) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sol.f[c] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) sol.y[r] = 0.0;
+    if (foot_thread && contact) {
         int sx, sy, tz;
         sig_unpack(sig, sx, sy, tz);
         const double mu = P.mu, ytol = P.dual_tol, ftol = P.feas_tol;
-        double y[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
         int nsx = sx, nsy = sy, ntz = tz;
         if (tz == 1) {
             // apex: need y >= 0 with C' y = -grad; the sign of the slack on the fz >= 0 row decides
             const double qx = -grad[0], qy = -grad[1], qz = -grad[2];
-            y[0] = fmax(qx, 0.0); y[1] = fmax(-qx, 0.0);
-            y[2] = fmax(qy, 0.0); y[3] = fmax(-qy, 0.0);
-            y[4] = -qz - mu * (fabs(qx) + fabs(qy));
+            sol.y[0] = fmax(qx, 0.0); sol.y[1] = fmax(-qx, 0.0);
+            sol.y[2] = fmax(qy, 0.0); sol.y[3] = fmax(-qy, 0.0);
+            sol.y[4] = -qz - mu * (fabs(qx) + fabs(qy));
             f[0] = f[1] = f[2] = 0.0;
-            if (y[4] < -ytol) { ok = false; nsx = 0; nsy = 0; ntz = 0; }
+            if (sol.y[4] < -ytol) { ok = false; nsx = 0; nsy = 0; ntz = 0; }
         } else {
             const double yx = (sx != 0) ? -sx * grad[0] : 0.0;
             const double yy = (sy != 0) ? -sy * grad[1] : 0.0;
-            if (sx > 0) y[0] = yx; else if (sx < 0) y[1] = yx;
-            if (sy > 0) y[2] = yy; else if (sy < 0) y[3] = yy;
+            if (sx > 0) sol.y[0] = yx; else if (sx < 0) sol.y[1] = yx;
+            if (sy > 0) sol.y[2] = yy; else if (sy < 0) sol.y[3] = yy;
             const double y4 = grad[2] - mu * (yx + yy);
             if (tz == 2) {
-                y[4] = y4;
+                sol.y[4] = y4;
                 if (y4 > ytol) { ok = false; ntz = 0; }
             }
             if (sx != 0 && yx < -ytol) { ok = false; nsx = 0; }
@@ -391,25 +399,18 @@ __device__ SweepOut sweep(const DevParams& P, Smem<N, ADMM>& sm, unsigned int& p
         }
         nsig = sig_pack(nsx, nsy, ntz);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) ft.f[c] = f[c];
-#pragma unroll
-        for (int r = 0; r < 5; ++r) ft.y[r] = y[r];
-    } else if (foot_thread) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) ft.f[c] = 0.0;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) ft.y[r] = 0.0;
+        for (int c = 0; c < 3; ++c) sol.f[c] = f[c];
     }
-    out.ok = __syncthreads_and(ok ? 1 : 0) != 0;
+    const int all_ok = __syncthreads_and(ok ? 1 : 0);
     PROF(5);
-    return out;
+    return all_ok ? 1 : 0;
 }
 
 // order-sensitive hash of the CTA's signature (cycle detection for the active-set sweeps)
-__device__ __forceinline__ unsigned long long sig_hash(uint8_t sig, bool foot_thread, unsigned long long* slot) {
+__device__ __forceinline__ unsigned long long sig_hash(uint8_t sig, bool hashed, unsigned long long* slot) {
     if (threadIdx.x == 0) *slot = 0ull;
     __syncthreads();
-    if (foot_thread) {
+    if (hashed) {
         unsigned long long h = (unsigned long long)(sig + 1) * 0x9E3779B97F4A7C15ull;
         h ^= h >> 29; h *= (2ull * threadIdx.x + 0xBF58476D1CE4E5B9ull); h ^= h >> 32;
         atomicAdd(slot, h);
@@ -422,15 +423,18 @@ __device__ __forceinline__ unsigned long long sig_hash(uint8_t sig, bool foot_th
 // finish: states by forward simulation, objective, masks, outputs            [MPC.py:432-458]
 // -------------------------------------------------------------------------------------------------
 template <int N, bool ADMM>
-__device__ void finish(const DevParams& P, Smem<N, ADMM>& sm, const DevState& st, int inst, const Foot& ft,
-                       uint8_t sig, int k, int j, bool foot_thread, int status, int sweeps, int iters) {
+__device__ void finish(const DevParams& P, Smem<N, ADMM>& sm, const DevState& st, int inst, bool contact,
+                       const FootSol& sol, uint8_t sig, int k, int j, bool foot_thread, bool valid_A,
+                       int status, int sweeps, int iters) {
+    constexpr int NF = 4 * N;
+    const double lin = P.dt / P.mass;
     // impulses of the final forces
     if (foot_thread) {
-        double v[6];
-        bv_apply(ft, ft.f, v);
-        if (!ft.contact) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) v[i] = 0.0;
+        double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (contact && valid_A) {
+            double A[9];
+            load_A<NF>(sm.fa, threadIdx.x, A);
+            bv_apply(A, lin, sol.f, v);
         }
         step_sum_store(v, sm.u + 6 * k, j);
     }
@@ -453,16 +457,16 @@ __device__ void finish(const DevParams& P, Smem<N, ADMM>& sm, const DevState& st
         }
     }
     if (foot_thread) {
-        part += 0.5 * P.w_force * (ft.f[0] * ft.f[0] + ft.f[1] * ft.f[1] + ft.f[2] * ft.f[2]);
+        part += 0.5 * P.w_force * (sol.f[0] * sol.f[0] + sol.f[1] * sol.f[1] + sol.f[2] * sol.f[2]);
         double* fo = st.f + (size_t)inst * 12 * N + 12 * k + 3 * j;
-        fo[0] = ft.f[0]; fo[1] = ft.f[1]; fo[2] = ft.f[2];
+        fo[0] = sol.f[0]; fo[1] = sol.f[1]; fo[2] = sol.f[2];
         double* yo = st.y + (size_t)inst * 20 * N + 20 * k + 5 * j;
 #pragma unroll
-        for (int r = 0; r < 5; ++r) yo[r] = ft.y[r];
+        for (int r = 0; r < 5; ++r) yo[r] = sol.y[r];
         st.sig[(size_t)inst * 4 * N + 4 * k + j] = sig;
         if (k == 0) {
             double* f0 = st.f0 + (size_t)inst * 12 + 3 * j;
-            f0[0] = ft.f[0]; f0[1] = ft.f[1]; f0[2] = ft.f[2];
+            f0[0] = sol.f[0]; f0[1] = sol.f[1]; f0[2] = sol.f[2];
         }
     }
     // objective: block reduction
@@ -477,7 +481,7 @@ __device__ void finish(const DevParams& P, Smem<N, ADMM>& sm, const DevState& st
     if (foot_thread) {
         // a swing foot is pinned to f = 0 (MPC.py:355-358), so all five of its rows sit on their bound
         const double mu = P.mu, tol = 1e-9;
-        const double fx = ft.f[0], fy = ft.f[1], fz = ft.f[2];
+        const double fx = sol.f[0], fy = sol.f[1], fz = sol.f[2];
         const double row[5] = {fx - mu * fz, -fx - mu * fz, fy - mu * fz, -fy - mu * fz, -fz};
         const int b0 = 20 * k + 5 * j;
 #pragma unroll
@@ -485,7 +489,7 @@ __device__ void finish(const DevParams& P, Smem<N, ADMM>& sm, const DevState& st
             const bool act = (fabs(row[r]) <= tol) || (r == 4 && fabs(row[4] + P.fz_max) <= tol);
             if (act) atomicOr(&amask[(b0 + r) >> 5], 1u << ((b0 + r) & 31));
         }
-        if (ft.contact) atomicOr(&amask[AW + ((4 * k + j) >> 5)], 1u << ((4 * k + j) & 31));
+        if (contact) atomicOr(&amask[AW + ((4 * k + j) >> 5)], 1u << ((4 * k + j) & 31));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < AW; i += blockDim.x) st.active[(size_t)inst * AW + i] = amask[i];
@@ -505,14 +509,16 @@ __device__ void finish(const DevParams& P, Smem<N, ADMM>& sm, const DevState& st
 //                    ADMM = true : fallback stage for the instances queued in st.fb_list.
 // -------------------------------------------------------------------------------------------------
 template <int N, bool ADMM>
-__global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g,
-                                                    const double* __restrict__ fsteps_g, int first_tick) {
+__global__ void __launch_bounds__(32 * NWARPS, ADMM ? 2 : 4)
+solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g, int first_tick) {
     using S = Smem<N, ADMM>;
+    constexpr int NF = 4 * N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S& sm = *reinterpret_cast<S*>(smem_raw);
     const int tid = threadIdx.x;
-    const bool foot_thread = tid < 4 * N;
+    const bool foot_thread = tid < NF;
     const int k = tid >> 2, j = tid & 3;
+    const double lin = P.dt / P.mass;
 
     unsigned int phase = 0;
     if (tid == 0) mbar_init(&sm.mbar, 1);
@@ -526,6 +532,7 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
 #ifdef MPCQP_PROFILE
         const long long inst_t0 = clock64();
 #endif
+        PROF_T0();
         // ---- stage inputs in shared memory: two bulk async copies (16-byte aligned blocks per instance)
         if (tid == 0) {
             fence_async_smem();
@@ -535,32 +542,40 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
         }
         mbar_wait(&sm.mbar, phase);
         phase ^= 1u;
-        Foot ft;
-        bool bad = false;
+        bool bad = false, contact = false;
         uint8_t sig = SIG_FREE;
-        if (foot_thread) decode_foot<N>(P, sm.xr, sm.fs, k, j, first_tick != 0, ft, bad);
+        double A0[9];
+        if (foot_thread) decode_foot<N>(P, sm.xr, sm.fs, k, j, first_tick != 0, A0, contact, bad);
         for (int i = tid; i < 12 * (N + 1); i += blockDim.x) bad = bad || !isfinite(sm.xr[i]);
         free_response<N>(P, sm.xr, sm.gam);
-        const int any_bad = __syncthreads_or(bad ? 1 : 0);
+        const int any_bad = __syncthreads_or(bad ? 1 : 0);       // also: every thread is done reading fs
         const bool warm = P.warm_start && !first_tick;
         if (foot_thread) {
-            bvT_apply(ft, sm.gam + 6 * k, ft.g);
+            // per-foot constants move to shared memory (struct of arrays) so that nothing per-foot is
+            // live in registers across the factorisation
 #pragma unroll
-            for (int c = 0; c < 3; ++c) ft.f[c] = 0.0;
+            for (int i = 0; i < 9; ++i) sm.fa[i * NF + tid] = A0[i];
+            double g[3];
+            bvT_apply(A0, lin, sm.gam + 6 * k, g);
 #pragma unroll
-            for (int r = 0; r < 5; ++r) ft.y[r] = 0.0;
+            for (int c = 0; c < 3; ++c) sm.fa[(9 + c) * NF + tid] = g[c];
             // warm start: the previous tick's active set, advanced by one step (MPC.py:403-406)
-            if (warm && ft.contact) {
+            if (warm && contact) {
                 const int ks = (k + 1 < N) ? k + 1 : 0;
                 sig = st.sig[(size_t)inst * 4 * N + 4 * ks + j];
                 if (sig > 26) sig = SIG_FREE;
             }
         }
+        FootSol sol;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sol.f[c] = 0.0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) sol.y[r] = 0.0;
         if (any_bad) {
-            if (foot_thread) { ft.contact = false; }
-            finish<N, ADMM>(P, sm, st, inst, ft, SIG_FREE, k, j, foot_thread, 3, 0, 0);
+            finish<N, ADMM>(P, sm, st, inst, false, sol, SIG_FREE, k, j, foot_thread, false, 3, 0, 0);
             continue;
         }
+        PROF(7);
 
         int sweeps = 0, iters = 0, status = 0;
         bool done = false;
@@ -568,7 +583,7 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
             // ---------------- active-set stage
             int nhist = 0;
             for (int s = 0; s < P.max_sweeps && !done; ++s) {
-                const unsigned long long h = sig_hash(sig, foot_thread && ft.contact, &sm.hist[15]);
+                const unsigned long long h = sig_hash(sig, foot_thread && contact, &sm.hist[15]);
                 bool seen = false;
                 for (int i = 0; i < nhist; ++i) seen = seen || (sm.hist[i] == h);
                 if (seen) break;
@@ -576,10 +591,10 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
                 if (tid == 0 && nhist < 15) sm.hist[nhist] = h;
                 nhist = (nhist < 15) ? nhist + 1 : nhist;
                 uint8_t nsig;
-                const SweepOut so = sweep<N, ADMM>(P, sm, phase, ft, sig, nsig, k, j, foot_thread);
+                const int r = sweep<N, ADMM>(P, sm, phase, contact, sig, nsig, sol, k, j, foot_thread);
                 ++sweeps;
-                if (!so.spd) break;
-                if (so.ok) { done = true; status = 1; }
+                if (r < 0) break;
+                if (r > 0) { done = true; status = 1; }
                 else sig = nsig;
             }
             if (!done) {
@@ -592,13 +607,17 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
                     continue;       // state of this instance is left untouched for the ADMM stage
                 }
                 status = 0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sol.f[c] = 0.0;
+#pragma unroll
+                for (int r = 0; r < 5; ++r) sol.y[r] = 0.0;
             }
         } else {
             // ---------------- ADMM stage (fixed rho, Woodbury-form linear solve, guarded polish)
             sweeps = (P.mode & 1) ? st.sweeps[inst] : 0;
             const double rho = P.rho, sigma = P.sigma, alpha = P.alpha, mu = P.mu;
             double z[5] = {0, 0, 0, 0, 0}, f[3] = {0, 0, 0}, y[5] = {0, 0, 0, 0, 0};
-            if (foot_thread && ft.contact && warm) {
+            if (foot_thread && contact && warm) {
                 const int ks = (k + 1 < N) ? k + 1 : 0;
                 const double* fp = st.f + (size_t)inst * 12 * N + 12 * ks + 3 * j;
                 const double* yp = st.y + (size_t)inst * 20 * N + 20 * ks + 5 * j;
@@ -610,18 +629,14 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
                 for (int r = 0; r < 5; ++r) z[r] = fmin(cf[r], 0.0);
                 z[4] = fmax(z[4], -P.fz_max);
             }
-            // factor W(rho) = M^-1 + Bv D^-1 Bv' into W2 (faces: everything free, D = (w + sigma) I + rho C'C)
+            // W(rho) = M^-1 + Bv D^-1 Bv' with every force free and D = (w + sigma) I + rho C'C (diagonal)
+            const bool live = foot_thread && contact;
+            const double ddx = live ? 1.0 / (P.w_force + sigma + 2.0 * rho) : 0.0;
+            const double ddz = live ? 1.0 / (P.w_force + sigma + rho * (4.0 * mu * mu + 1.0)) : 0.0;
             Face fa;
-            double ddx = 0.0, ddz = 0.0;
-            if (foot_thread) {
-                make_face(P, ft, SIG_FREE, fa);
-                ddx = ft.contact ? 1.0 / (P.w_force + sigma + 2.0 * rho) : 0.0;
-                ddz = ft.contact ? 1.0 / (P.w_force + sigma + rho * (4.0 * mu * mu + 1.0)) : 0.0;
-                fa.dx = ddx; fa.dy = ddx; fa.dz = ddz;
-            }
-            assemble_W<N, S::NTILES>(P, sm.W2, &sm.mbar, phase, fa, k, j, foot_thread);
-            const bool spd = cholesky_tiles<S::NT, 4>(sm.W2, &sm.flag);
-            if (spd) invert_tiles<S::NT, 4>(sm.W2);
+            make_face(P, live, SIG_FREE, fa);
+            assemble_W<N, S::NTILES>(P, sm.W2, sm.fa, &sm.mbar, phase, fa, ddx, ddz, true, k, j, foot_thread);
+            const bool spd = factor_invert_tiles<S::NT, NWARPS>(sm.W2, &sm.flag);
             uint8_t prev_sig = 255;
             int stable = 0;
             while (spd && !done && iters < P.max_iter) {
@@ -630,23 +645,23 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
                 if (foot_thread) {
                     const double v0 = rho * z[0] - y[0], v1 = rho * z[1] - y[1], v2 = rho * z[2] - y[2],
                                  v3 = rho * z[3] - y[3], v4 = rho * z[4] - y[4];
-                    tx = ddx * (sigma * f[0] - ft.g[0] + (v0 - v1));
-                    ty = ddx * (sigma * f[1] - ft.g[1] + (v2 - v3));
-                    tzz = ddz * (sigma * f[2] - ft.g[2] - mu * (v0 + v1 + v2 + v3) - v4);
-                    double v[6];
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) v[i] = fa.bx[i] * tx + fa.by[i] * ty + fa.bz[i] * tzz;
+                    tx = ddx * (sigma * f[0] - sm.fa[9 * NF + tid] + (v0 - v1));
+                    ty = ddx * (sigma * f[1] - sm.fa[10 * NF + tid] + (v2 - v3));
+                    tzz = ddz * (sigma * f[2] - sm.fa[11 * NF + tid] - mu * (v0 + v1 + v2 + v3) - v4);
+                    const double tt[3] = {tx, ty, tzz};
+                    double A[9], v[6];
+                    load_A<NF>(sm.fa, tid, A);
+                    bv_apply(A, lin, tt, v);
                     step_sum_store(v, sm.u + 6 * k, j);
                 }
                 __syncthreads();
-                tri_solve<S::NT>(sm.W2, sm.u, sm.tmp);
+                tri_solve<S::NT, NWARPS>(sm.W2, sm.u, sm.tmp);
                 uint8_t cur = SIG_FREE;
-                if (foot_thread && ft.contact) {
-                    const double* v = sm.u + 6 * k;
-                    double ax = 0, ay = 0, az = 0;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) { ax += fa.bx[i] * v[i]; ay += fa.by[i] * v[i]; az += fa.bz[i] * v[i]; }
-                    const double ftx = tx - ddx * ax, fty = ty - ddx * ay, ftz = tzz - ddz * az;
+                if (live) {
+                    double A[9], h[3];
+                    load_A<NF>(sm.fa, tid, A);
+                    bvT_apply(A, lin, sm.u + 6 * k, h);
+                    const double ftx = tx - ddx * h[0], fty = ty - ddx * h[1], ftz = tzz - ddz * h[2];
                     const double zt[5] = {ftx - mu * ftz, -ftx - mu * ftz, fty - mu * ftz, -fty - mu * ftz, -ftz};
                     f[0] = alpha * ftx + (1.0 - alpha) * f[0];
                     f[1] = alpha * fty + (1.0 - alpha) * f[1];
@@ -674,25 +689,25 @@ __global__ void __launch_bounds__(128, 4) solve_kernel(DevParams P, DevState st,
                     if (stable >= 1) {
                         stable = 0;
                         uint8_t nsig;
-                        Foot trial = ft;
-                        const SweepOut so = sweep<N, ADMM>(P, sm, phase, trial, cur, nsig, k, j, foot_thread);
+                        FootSol trial;
+                        const int r = sweep<N, ADMM>(P, sm, phase, contact, cur, nsig, trial, k, j, foot_thread);
                         ++sweeps;
-                        if (so.spd && so.ok) { ft = trial; sig = cur; done = true; status = 1; }
+                        if (r > 0) { sol = trial; sig = cur; done = true; status = 1; }
                     }
                 }
             }
             if (!done) {
                 status = 2;
                 sig = SIG_FREE;
-                if (foot_thread) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) ft.f[c] = ft.contact ? f[c] : 0.0;
+                for (int c = 0; c < 3; ++c) sol.f[c] = live ? f[c] : 0.0;
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) ft.y[r] = ft.contact ? y[r] : 0.0;
-                }
+                for (int r = 0; r < 5; ++r) sol.y[r] = live ? y[r] : 0.0;
             }
         }
-        finish<N, ADMM>(P, sm, st, inst, ft, sig, k, j, foot_thread, status, sweeps, iters);
+        PROF(8);
+        finish<N, ADMM>(P, sm, st, inst, contact, sol, sig, k, j, foot_thread, true, status, sweeps, iters);
+        PROF(9);
 #ifdef MPCQP_PROFILE
         if (threadIdx.x == 0) { atomicAdd(&g_prof[ADMM ? 13 : 12], (unsigned long long)(clock64() - inst_t0)); atomicAdd(&g_prof[ADMM ? 11 : 10], 1ull); }
 #endif
@@ -714,19 +729,19 @@ __global__ void export_build_kernel(DevParams P, const double* __restrict__ xref
     __syncthreads();
     if (tid < 4 * N) {
         const int k = tid >> 2, j = tid & 3;
-        Foot ft;
-        bool bad = false;
-        decode_foot<N>(P, xr, fs, k, j, first_tick != 0, ft, bad);
+        double A[9];
+        bool bad = false, contact = false;
+        decode_foot<N>(P, xr, fs, k, j, first_tick != 0, A, contact, bad);
         double* b = Bv + (size_t)inst * 48 * N + 48 * k + 12 * j;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            b[4 * c + 0] = ft.lin;
-            b[4 * c + 1] = ft.A[0 + c];
-            b[4 * c + 2] = ft.A[3 + c];
-            b[4 * c + 3] = ft.A[6 + c];
+            b[4 * c + 0] = P.dt / P.mass;                                    // MPC.py:119
+            b[4 * c + 1] = A[0 + c];
+            b[4 * c + 2] = A[3 + c];
+            b[4 * c + 3] = A[6 + c];
         }
         double* s = Sv + (size_t)inst * 12 * N + 12 * k + 3 * j;
-        s[0] = s[1] = s[2] = ft.contact ? 0.0 : 1.0;                        // MPC.py:628-630
+        s[0] = s[1] = s[2] = contact ? 0.0 : 1.0;                            // MPC.py:628-630
     }
     for (int idx = tid; idx < 12 * N; idx += blockDim.x) {
         const int k = idx / 12, i = idx - 12 * k;

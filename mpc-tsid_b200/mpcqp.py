@@ -34,6 +34,7 @@ class Params(C.Structure):
         ("check_every", C.c_int32), ("warm_start", C.c_int32),
         ("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
         ("feas_tol", C.c_double), ("dual_tol", C.c_double),
+        ("refine", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

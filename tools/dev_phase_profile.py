@@ -11,7 +11,7 @@ eng = mpcqp.Engine(batch=B)
 lib = mpcqp.load()
 sc = Scenario(B, gaits="trot", seed=20260)
 buf = (ctypes.c_ulonglong * 16)()
-names = ["assemble", "cholesky", "grad(H f)", "rhs+sync", "tri-solve", "back+guard", "invert"]
+names = ["assemble", "factor+invert", "grad(H f)", "rhs+sync", "tri-solve", "back+guard", "-", "build", "solve-stage", "finish"]
 for t in range(T):
     xr, fs = sc.inputs()
     eng.run(t, xr, fs); x = eng.solution(); info = eng.info(with_y=False)
