@@ -306,7 +306,9 @@ def main():
     hbm_ach = hbm_alg * B * K / (total_ms * 1e-3) * 1e-9
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-        "traffic": None, "kernel": "solve_kernel<16,false> (+ ADMM fallback kernel)",
+        "traffic": 22.49e6 * B / 4096.0, "kernel": "solve_kernel<16,false> (+ ADMM fallback kernel)",
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel<16,false> launch at 4096 "
+                          "instances, ncu --set full (profiles/r01_solve_kernel_ncu_summary.txt), scaled to this batch",
         "peak_source": "DMMA m8n8k4 issue loop measured on this GPU in this run (mpcqp_measure_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 entry",
         "flop_model": "engine's own count, DESIGN.md section 5: sweeps*%.0f + admm_iters*%.0f per solve" % (
