@@ -33,6 +33,8 @@ for p in (ROOT, os.path.join(ROOT, "mpc-tsid_b200")):
         sys.path.insert(0, p)
 
 METRIC = "MPC QP solves/sec (Solo trot, N=16)"
+WORKLOAD = ("BASELINE.json configs[1]: batched Solo trot N=16 dt=0.02, %d instances per GPU, closed loop with warm start "
+            "across ticks, random commands/gait phases, seeded state noise")
 UNIT = "solves/s"
 N_STEPS = 16
 
@@ -88,8 +90,8 @@ def reference_main(args):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Solo trot N=16 dt=0.02, closed loop on the centroidal model; one robot per host core, "
-                               "one QP per tick on CPU (BASELINE.json configs[0] shape, bounded sample)"},
+        "config": {"workload": WORKLOAD % 4096,
+                   "sample": "one closed-loop trot robot per host core, one QP per tick (same generator, same tick shape)"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "osqp is not installable offline and /root/reference is absent on the GPU box: this is the oracle port "
@@ -330,8 +332,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[1]: batched Solo trot N=16 dt=0.02, %d instances per GPU, closed "
-                                   "loop with warm start across ticks, random commands/gait phases, seeded state noise" % B,
+            "config": {"workload": WORKLOAD % B,
                        "instances_per_gpu": B, "parallelism": "instances sharded by index, no collective",
                        "settle_ticks": max(args.settle, 0),
                        "tick_window": "ticks %d..%d of the closed loop are timed (steady operation; the first %d ticks after "

@@ -58,6 +58,8 @@ struct mpcqp_handle {
     DevParams dp;
     DevState st;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};      // host-input runs: copy + solve of alternate chunks overlap
+    cudaEvent_t ev_main = nullptr, ev_side[2] = {nullptr, nullptr};
     double* d_xref = nullptr;
     double* d_fsteps = nullptr;
     double* d_Minv = nullptr;
@@ -124,6 +126,11 @@ int mpcqp_destroy(mpcqp_handle* h) {
     cudaFree(h->d_Minv);
     cudaFree(h->d_C2);
     cudaFree(h->d_block);
+    for (int i = 0; i < 2; ++i) {
+        if (h->side[i]) cudaStreamDestroy(h->side[i]);
+        if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
+    }
+    if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MPCQP_OK;
@@ -202,6 +209,11 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
         if (e_ != cudaSuccess) return bail(fail(MPCQP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
     } while (0)
     CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUH(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+        CUH(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming));
+    }
+    CUH(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
     CUH(cudaMalloc(&h->d_C2, C2.size() * sizeof(double)));
     CUH(cudaMalloc(&h->d_Minv, Mt.size() * sizeof(double)));
     CUH(cudaMemcpy(h->d_C2, C2.data(), C2.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -256,17 +268,49 @@ static int stage_inputs(mpcqp_handle* h, const double* xref, const double* fstep
 
 int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fsteps, int location) {
     if (!h || !xref || !fsteps) return fail(MPCQP_ERR_INVALID, "null argument");
+    if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "location must be MPCQP_HOST or MPCQP_DEVICE");
     CU(cudaSetDevice(h->p.device));
-    const double *dx, *df;
-    int rc = stage_inputs(h, xref, fsteps, location, &dx, &df);
-    if (rc) return rc;
-    const int B = h->p.batch;
+    const int B = h->p.batch, N = h->p.n_steps;
     const int first = (k == 0.0) ? 1 : 0;                       // MPC.py:491, 413: only k == 0 vs k > 0 matters
+    const size_t xs = (size_t)12 * (N + 1), fs = 260;
     CU(cudaMemsetAsync(h->st.fb_count, 0, sizeof(int32_t), h->stream));
-    if (h->p.mode & MPCQP_MODE_ACTIVE_SET) {
-        solve_kernel<16, false><<<B, 128, sizeof(Smem<16, false>), h->stream>>>(h->dp, h->st, dx, df, first);
+    const bool stageA = (h->p.mode & MPCQP_MODE_ACTIVE_SET) != 0;
+    const double *dx = xref, *df = fsteps;
+    // Host inputs: the batch is cut into chunks of two full waves (2 x 4 CTAs x #SM instances); chunk
+    // c is copied and solved on side stream c & 1, so the H2D copy of one chunk overlaps the solve of
+    // the previous one and the two solve kernels fill each other's tails.
+    const int chunk = 2 * 4 * h->sms;
+    if (location == MPCQP_HOST) {
+        dx = h->d_xref; df = h->d_fsteps;
+        if (stageA && B > chunk) {
+            CU(cudaEventRecord(h->ev_main, h->stream));          // everything issued so far (incl. the last tick)
+            for (int i = 0; i < 2; ++i) CU(cudaStreamWaitEvent(h->side[i], h->ev_main, 0));
+            int c = 0;
+            for (int off = 0; off < B; off += chunk, ++c) {
+                const int n = B - off < chunk ? B - off : chunk;
+                cudaStream_t s = h->side[c & 1];
+                CU(cudaMemcpyAsync(h->d_xref + off * xs, xref + off * xs, n * xs * sizeof(double), cudaMemcpyHostToDevice, s));
+                CU(cudaMemcpyAsync(h->d_fsteps + off * fs, fsteps + off * fs, n * fs * sizeof(double), cudaMemcpyHostToDevice, s));
+                solve_kernel<16, false><<<n, 128, sizeof(Smem<16, false>), s>>>(h->dp, h->st, dx, df, first, off, n);
+                ++h->launches;
+            }
+            for (int i = 0; i < 2; ++i) {
+                CU(cudaEventRecord(h->ev_side[i], h->side[i]));
+                CU(cudaStreamWaitEvent(h->stream, h->ev_side[i], 0));
+            }
+        } else {
+            CU(cudaMemcpyAsync(h->d_xref, xref, B * xs * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(h->d_fsteps, fsteps, B * fs * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            if (stageA) {
+                solve_kernel<16, false><<<B, 128, sizeof(Smem<16, false>), h->stream>>>(h->dp, h->st, dx, df, first, 0, B);
+                ++h->launches;
+            }
+        }
+    } else if (stageA) {
+        solve_kernel<16, false><<<B, 128, sizeof(Smem<16, false>), h->stream>>>(h->dp, h->st, dx, df, first, 0, B);
         ++h->launches;
-    } else {
+    }
+    if (!stageA) {
         // ADMM only: queue every instance
         std::vector<int32_t> all(B);
         for (int i = 0; i < B; ++i) all[i] = i;
@@ -276,7 +320,7 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
     }
     if (h->p.mode & MPCQP_MODE_ADMM) {
         const int grid = B < 2 * h->sms ? B : 2 * h->sms;
-        solve_kernel<16, true><<<grid, 128, sizeof(Smem<16, true>), h->stream>>>(h->dp, h->st, dx, df, first);
+        solve_kernel<16, true><<<grid, 128, sizeof(Smem<16, true>), h->stream>>>(h->dp, h->st, dx, df, first, 0, B);
         ++h->launches;
     }
     CU(cudaGetLastError());

@@ -510,7 +510,8 @@ __device__ void finish(const DevParams& P, Smem<N, ADMM>& sm, const DevState& st
 // -------------------------------------------------------------------------------------------------
 template <int N, bool ADMM>
 __global__ void __launch_bounds__(32 * NWARPS, ADMM ? 2 : 4)
-solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g, int first_tick) {
+solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g, int first_tick,
+             int inst_offset, int inst_count) {
     using S = Smem<N, ADMM>;
     constexpr int NF = 4 * N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -525,9 +526,9 @@ solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const 
     for (int i = tid; i < N * N; i += blockDim.x) sm.C2[i] = __ldg(P.C2 + i);
     __syncthreads();
 
-    int n_work = ADMM ? *st.fb_count : P.batch;
+    int n_work = ADMM ? *st.fb_count : inst_count;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int inst = ADMM ? st.fb_list[w] : w;
+        const int inst = ADMM ? st.fb_list[w] : w + inst_offset;
         __syncthreads();
 #ifdef MPCQP_PROFILE
         const long long inst_t0 = clock64();
