@@ -15,6 +15,22 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// tile helpers out of line (small code, call overhead) or inlined (large code, no calls)
+#ifdef MPCQP_OUTLINE_TILES
+#define MPCQP_TILE_FN __noinline__
+#else
+#define MPCQP_TILE_FN __forceinline__
+#endif
+// optional per-phase cycle counters of the factorisation (tools/piece_bench.cu)
+#ifdef MPCQP_TILE_PROF
+__device__ unsigned long long g_tile_prof[8];
+#define TPROF(slot) do { if ((threadIdx.x & 31) == 0) { long long n_ = clock64(); atomicAdd(&g_tile_prof[(slot) + 8 * 0], (unsigned long long)(n_ - tp_)); tp_ = n_; } } while (0)
+#define TPROF_T0() long long tp_ = clock64()
+#else
+#define TPROF(slot) do {} while (0)
+#define TPROF_T0() do {} while (0)
+#endif
+
 namespace mpcqp {
 
 struct DevParams {
@@ -102,12 +118,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 // On exit: off-diagonal tiles hold L_IJ, diagonal tiles hold inv(L_JJ) (lower triangular).
 // Returns false (CTA-uniform) if a pivot is not positive.
 // ---------------------------------------------------------------------------------------------
-// sum_{K in [K0, K1)} L_IK L_JK'  accumulated into (c0, c1) with two independent DMMA chains
-__device__ __forceinline__ void syrk_accumulate(const double* __restrict__ rowI, const double* __restrict__ rowJ,
-                                                int K0, int K1, int fo, double& c0, double& c1) {
-    double e0 = 0.0, e1 = 0.0;
+// sum_{K in [K0, K1)} L_IK L_JK'  as a C fragment, two independent DMMA chains.  Out of line on purpose:
+// the tile loop calls it from six places and the kernel's hot loop has to stay inside the
+// instruction cache (four CTAs per SM sit in different phases).
+__device__ MPCQP_TILE_FN double2 syrk_sum(const double* __restrict__ rowI, const double* __restrict__ rowJ,
+                                         int K0, int K1, int fo) {
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
     int K = K0;
-#pragma unroll 2
     for (; K + 1 < K1; K += 2) {
         const double a0 = rowI[K * 64 + fo], a1 = rowI[K * 64 + 32 + fo];
         const double b0 = rowJ[K * 64 + fo], b1 = rowJ[K * 64 + 32 + fo];
@@ -124,7 +141,7 @@ __device__ __forceinline__ void syrk_accumulate(const double* __restrict__ rowI,
         dmma884(c0, c1, a0, b0);
         dmma884(e0, e1, a1, b1);
     }
-    c0 += e0; c1 += e1;
+    return make_double2(c0 + e0, c1 + e1);
 }
 
 // 8x8 diagonal tile in shared memory (both triangles valid) -> inv(chol(tile)), lower triangular,
@@ -173,14 +190,13 @@ __device__ __noinline__ void diag_factor_invert(double* __restrict__ D, int lane
 
 // One tile of X = inv(L):  X_RJ = -inv(L_RR) * sum_{K=J..R-1} L_RK X_KJ   (C fragment in o0, o1).
 // Needs rows < R of X and row R of L in shared memory.
-__device__ __forceinline__ void xinv_tile(const double* __restrict__ Wt, int R, int Jc, int lane, double& o0, double& o1) {
+__device__ MPCQP_TILE_FN double2 xinv_tile(const double* __restrict__ Wt, int R, int Jc, int lane) {
     const int g = lane >> 2, t = lane & 3;
     const int fo = g * 4 + t;                                        // A operand: element (g, t + 4kk)
     const int bo = (g >> 2) * 32 + t * 4 + (g & 3);                  // B operand: element (t + 4kk, g) -> + 16 kk
     const double* rowR = Wt + tile_index(R, 0) * 64;
     double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
     int K = Jc;
-#pragma unroll 2
     for (; K + 1 < R; K += 2) {
         const double* XA = Wt + tile_index(K, Jc) * 64;
         const double* XB = Wt + tile_index(K + 1, Jc) * 64;
@@ -208,7 +224,7 @@ __device__ __forceinline__ void xinv_tile(const double* __restrict__ Wt, int R, 
     double d0 = 0.0, d1 = 0.0;
     dmma884(d0, d1, Drr[fo], bb0);
     dmma884(d0, d1, Drr[32 + fo], bb1);
-    o0 = -d0; o1 = -d1;
+    return make_double2(-d0, -d1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -247,6 +263,7 @@ __device__ bool factor_invert_tiles(double* __restrict__ Wt, int* __restrict__ f
             cur0[m] = w.x; cur1[m] = w.y;
         }
     }
+    TPROF_T0();
     for (int J = 0; J < NT; ++J) {
         const int I0 = J + ((warp - J) & (NWARPS - 1));         // first tile row >= J owned by this warp
         const int I1 = J + 1 + ((warp - J - 1) & (NWARPS - 1)); // same for column J + 1
@@ -261,13 +278,14 @@ __device__ bool factor_invert_tiles(double* __restrict__ Wt, int* __restrict__ f
             *reinterpret_cast<double2*>(D + co) = make_double2(cur0[0], cur1[0]);
             __syncwarp();
             diag_factor_invert(D, lane, flag);
+            TPROF(0);
         } else {
             // ---- in the shadow of the pivot chain: (a) look-ahead of column J + 1 over K < J
             if (J + 1 < NT) {
 #pragma unroll
                 for (int m = 0; m < MAXT; ++m) {
                     const int I = I1 + m * NWARPS;
-                    if (I < NT) syrk_accumulate(Wt + tile_index(I, 0) * 64, rowN, 0, J, fo, nxt0[m], nxt1[m]);
+                    if (I < NT) { const double2 r = syrk_sum(Wt + tile_index(I, 0) * 64, rowN, 0, J, fo); nxt0[m] = r.x; nxt1[m] = r.y; }
                 }
             }
             // (b) row J - 1 of X (kept in registers until the barrier below)
@@ -275,11 +293,13 @@ __device__ bool factor_invert_tiles(double* __restrict__ Wt, int* __restrict__ f
 #pragma unroll
                 for (int m = 0; m < XT; ++m) {
                     const int Jc = rank + m * (NWARPS - 1);
-                    if (Jc < J - 1) xinv_tile(Wt, J - 1, Jc, lane, xr0[m], xr1[m]);
+                    if (Jc < J - 1) { const double2 r = xinv_tile(Wt, J - 1, Jc, lane); xr0[m] = r.x; xr1[m] = r.y; }
                 }
             }
+            TPROF(1);
         }
         __syncthreads();
+        TPROF(2);
         // ---- panel: L_IJ = C_IJ * inv(L_JJ)'   (A = C fragment re-laid by shuffles, B[k][n] = Linv[n][k])
         const double b0 = D[fo], b1 = D[32 + fo];
 #pragma unroll
@@ -304,7 +324,9 @@ __device__ bool factor_invert_tiles(double* __restrict__ Wt, int* __restrict__ f
                 if (Jc < J - 1) *reinterpret_cast<double2*>(Wt + tile_index(J - 1, Jc) * 64 + co) = make_double2(xr0[m], xr1[m]);
             }
         }
+        TPROF(3);
         __syncthreads();
+        TPROF(4);
         // ---- finish column J + 1: add the K = J term (the owner of J also its K < J part), C = W - sum
         if (J + 1 < NT) {
 #pragma unroll
@@ -313,13 +335,14 @@ __device__ bool factor_invert_tiles(double* __restrict__ Wt, int* __restrict__ f
                 cur0[m] = 0.0; cur1[m] = 0.0;
                 if (I < NT) {
                     const double* rowI = Wt + tile_index(I, 0) * 64;
-                    syrk_accumulate(rowI, rowN, owner ? 0 : J, J + 1, fo, nxt0[m], nxt1[m]);
+                    const double2 r = syrk_sum(rowI, rowN, owner ? 0 : J, J + 1, fo);
                     const double2 w = *reinterpret_cast<const double2*>(Wt + tile_index(I, J + 1) * 64 + co);
-                    cur0[m] = w.x - nxt0[m];
-                    cur1[m] = w.y - nxt1[m];
+                    cur0[m] = w.x - (nxt0[m] + r.x);
+                    cur1[m] = w.y - (nxt1[m] + r.y);
                 }
             }
         }
+        TPROF(5);
     }
     // ---- last row of X, all warps
     {
@@ -327,7 +350,7 @@ __device__ bool factor_invert_tiles(double* __restrict__ Wt, int* __restrict__ f
 #pragma unroll
         for (int m = 0; m < MAXT; ++m) {
             const int Jc = warp + m * NWARPS;
-            if (Jc < NT - 1) xinv_tile(Wt, NT - 1, Jc, lane, l0[m], l1[m]);
+            if (Jc < NT - 1) { const double2 r = xinv_tile(Wt, NT - 1, Jc, lane); l0[m] = r.x; l1[m] = r.y; }
         }
         __syncthreads();
 #pragma unroll
@@ -359,7 +382,7 @@ __device__ void tri_solve(const double* __restrict__ Wt, double* __restrict__ s,
             a0[m] = 0.0; a1[m] = 0.0;
             if (I < NT) {
                 const double* T = Wt + tile_index(I, 0) * 64 + co;
-#pragma unroll 4
+#pragma unroll 2
                 for (int J = 0; J <= I; ++J) {
                     const double2 x = *reinterpret_cast<const double2*>(T + J * 64);
                     const double2 sv = *reinterpret_cast<const double2*>(s + 8 * J + 2 * t);
@@ -386,7 +409,7 @@ __device__ void tri_solve(const double* __restrict__ Wt, double* __restrict__ s,
             const int J = warp + m * NWARPS;
             a0[m] = 0.0; a1[m] = 0.0;
             if (J < NT) {
-#pragma unroll 4
+#pragma unroll 2
                 for (int I = J; I < NT; ++I) {
                     const double2 x = *reinterpret_cast<const double2*>(Wt + tile_index(I, J) * 64 + co);
                     const double yv = tmp[8 * I + g];

@@ -100,17 +100,17 @@ __device__ __forceinline__ void bvT_apply(const double A[9], double lin, const d
     for (int c = 0; c < 3; ++c) out[c] = lin * v[c] + A[c] * v[3] + A[3 + c] * v[4] + A[6 + c] * v[5];
 }
 
-// sum a 6-vector over the four feet of a step (lanes 4k..4k+3) and let lane j == 0 store it
+// sum a 6-vector over the four feet of a step (lanes 4k..4k+3) and let lane j == 0 store it.
+// Out of line (code size): called from every per-foot phase.
+__device__ __noinline__ void step_sum_store6(double v0, double v1, double v2, double v3, double v4, double v5, double* dst, int j) {
+    v0 += shfl_xor_d(v0, 1); v1 += shfl_xor_d(v1, 1); v2 += shfl_xor_d(v2, 1);
+    v3 += shfl_xor_d(v3, 1); v4 += shfl_xor_d(v4, 1); v5 += shfl_xor_d(v5, 1);
+    v0 += shfl_xor_d(v0, 2); v1 += shfl_xor_d(v1, 2); v2 += shfl_xor_d(v2, 2);
+    v3 += shfl_xor_d(v3, 2); v4 += shfl_xor_d(v4, 2); v5 += shfl_xor_d(v5, 2);
+    if (j == 0) { dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3; dst[4] = v4; dst[5] = v5; }
+}
 __device__ __forceinline__ void step_sum_store(double v[6], double* dst, int j) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        v[i] += shfl_xor_d(v[i], 1);
-        v[i] += shfl_xor_d(v[i], 2);
-    }
-    if (j == 0) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) dst[i] = v[i];
-    }
+    step_sum_store6(v[0], v[1], v[2], v[3], v[4], v[5], dst, j);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -195,7 +195,7 @@ __device__ __forceinline__ void gram_apply(const DevParams& P, const double* C2,
         const int k = idx / 6, c = idx - 6 * k;
         const double* row = C2 + k * N;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-#pragma unroll
+#pragma unroll 2
         for (int l = 0; l < N; l += 4) {
             const double u0 = u[6 * l + c], u1 = u[6 * (l + 1) + c], u2 = u[6 * (l + 2) + c], u3 = u[6 * (l + 3) + c];
             a0 = fma(row[l], u0, a0);
@@ -423,7 +423,7 @@ __device__ __forceinline__ unsigned long long sig_hash(uint8_t sig, bool hashed,
 // finish: states by forward simulation, objective, masks, outputs            [MPC.py:432-458]
 // -------------------------------------------------------------------------------------------------
 template <int N, bool ADMM>
-__device__ void finish(const DevParams& P, Smem<N, ADMM>& sm, const DevState& st, int inst, bool contact,
+__device__ __forceinline__ void finish(const DevParams& P, Smem<N, ADMM>& sm, const DevState& st, int inst, bool contact,
                        const FootSol& sol, uint8_t sig, int k, int j, bool foot_thread, bool valid_A,
                        int status, int sweeps, int iters) {
     constexpr int NF = 4 * N;
@@ -572,15 +572,16 @@ solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const 
         for (int c = 0; c < 3; ++c) sol.f[c] = 0.0;
 #pragma unroll
         for (int r = 0; r < 5; ++r) sol.y[r] = 0.0;
-        if (any_bad) {
-            finish<N, ADMM>(P, sm, st, inst, false, sol, SIG_FREE, k, j, foot_thread, false, 3, 0, 0);
-            continue;
-        }
         PROF(7);
 
         int sweeps = 0, iters = 0, status = 0;
         bool done = false;
-        if (!ADMM) {
+        if (any_bad) {
+            // malformed input: report it, emit zero forces (never NaN), skip both solver stages
+            status = 3;
+            contact = false;
+            sig = SIG_FREE;
+        } else if (!ADMM) {
             // ---------------- active-set stage
             int nhist = 0;
             for (int s = 0; s < P.max_sweeps && !done; ++s) {
@@ -707,7 +708,7 @@ solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const 
             }
         }
         PROF(8);
-        finish<N, ADMM>(P, sm, st, inst, contact, sol, sig, k, j, foot_thread, true, status, sweeps, iters);
+        finish<N, ADMM>(P, sm, st, inst, contact, sol, sig, k, j, foot_thread, !any_bad, status, sweeps, iters);
         PROF(9);
 #ifdef MPCQP_PROFILE
         if (threadIdx.x == 0) { atomicAdd(&g_prof[ADMM ? 13 : 12], (unsigned long long)(clock64() - inst_t0)); atomicAdd(&g_prof[ADMM ? 11 : 10], 1ull); }

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <vector>
 #include <cmath>
+#define MPCQP_TILE_PROF
 #include "mpcqp_device.cuh"
 using namespace mpcqp;
 constexpr int NT = 12, NTILES = 78;
@@ -63,12 +64,17 @@ int main() {
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sm));
     const char* names[] = {"bulk 40KB", "factor+invert", "-", "tri_solve", "64 dep DFMA", "16 dep rsqrt", "16 syncthreads"};
     for (int blocks : {1, 148 * 4}) {
-        bench<<<blocks, 128, sizeof(Sm)>>>(dW, dout, 20);
+        bench<<<blocks, 128, sizeof(Sm)>>>(dW, dout, 21);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[16]; cudaMemcpy(h, dout, sizeof(h), cudaMemcpyDeviceToHost);
         printf("blocks=%d (%s):", blocks, cudaGetErrorString(e));
         for (int i = 0; i < 7; ++i) printf("  %s %lld", names[i], h[i]);
         printf("\n");
+        unsigned long long tp[8], z[8] = {0};
+        cudaMemcpyFromSymbol(tp, g_tile_prof, sizeof(tp)); cudaMemcpyToSymbol(g_tile_prof, z, sizeof(z));
+        const double per = 1.0 / (4.0 * blocks * 21);   // summed over 4 warps, blocks CTAs, 21 reps (1 warm-up launch counted)
+        printf("   per-warp avg cycles per factorisation: diag(owner) %.0f  shadow(non-owner) %.0f  wait1 %.0f  panel %.0f  wait2 %.0f  finish-col %.0f\n",
+               tp[0] * per, tp[1] * per, tp[2] * per, tp[3] * per, tp[4] * per, tp[5] * per);
     }
     return 0;
 }
