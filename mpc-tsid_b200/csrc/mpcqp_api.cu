@@ -53,6 +53,22 @@ void invert_spd(std::vector<long double>& a, int n) {
 
 }  // namespace
 
+template <int N>
+cudaError_t configure_kernels() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(solve_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<N, false>)))) return e;
+    if ((e = cudaFuncSetAttribute(solve_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<N, true>)))) return e;
+    if ((e = cudaFuncSetAttribute(solve_kernel<N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
+    return cudaFuncSetAttribute(solve_kernel<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+template <int N>
+void launch_solve(bool admm, int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const double* dx,
+                  const double* df, int first, int off, int n) {
+    if (admm) solve_kernel<N, true><<<grid, 32 * Cfg<N>::NW, sizeof(Smem<N, true>), s>>>(dp, st, dx, df, first, off, n);
+    else solve_kernel<N, false><<<grid, 32 * Cfg<N>::NW, sizeof(Smem<N, false>), s>>>(dp, st, dx, df, first, off, n);
+}
+
 struct mpcqp_handle {
     mpcqp_params p;
     DevParams dp;
@@ -70,6 +86,13 @@ struct mpcqp_handle {
     bool ran = false;
     int64_t launches = 0;
     int sms = 0;
+
+    void solve(bool admm, int grid, cudaStream_t s, const double* dx, const double* df, int first, int off, int n) {
+        if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, dx, df, first, off, n);
+        else launch_solve<32>(admm, grid, s, dp, st, dx, df, first, off, n);
+        ++launches;
+    }
+    int ctas_per_sm(bool admm) const { return p.n_steps == 16 ? (admm ? 2 : 4) : 1; }
 };
 
 extern "C" {
@@ -140,7 +163,8 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     if (!p || !out) return fail(MPCQP_ERR_INVALID, "null argument");
     *out = nullptr;
     if (p->struct_size != (int32_t)sizeof(mpcqp_params)) return fail(MPCQP_ERR_INVALID, "mpcqp_params.struct_size mismatch");
-    if (p->n_steps != 16) return fail(MPCQP_ERR_INVALID, "n_steps: this build supports a horizon of 16 steps");
+    if (p->n_steps != 16 && p->n_steps != 32)
+        return fail(MPCQP_ERR_INVALID, "n_steps: this build supports horizons of 16 and 32 steps");
     if (p->batch < 1) return fail(MPCQP_ERR_INVALID, "batch must be >= 1");
     if (!(p->dt > 0) || !(p->mass > 0) || !(p->mu > 0) || !(p->fz_max > 0) || !(p->w_force > 0))
         return fail(MPCQP_ERR_INVALID, "dt, mass, mu, fz_max, w_force must be positive");
@@ -242,10 +266,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     h->st.fb_list = (int32_t*)(base + o_list); h->st.fb_count = (int32_t*)(base + o_count);
     h->st.sig = (uint8_t*)(base + o_sig);
     CUH(cudaMemset(h->st.sig, SIG_FREE, (size_t)B * 4 * N));
-    CUH(cudaFuncSetAttribute(solve_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<16, false>)));
-    CUH(cudaFuncSetAttribute(solve_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<16, true>)));
-    CUH(cudaFuncSetAttribute(solve_kernel<16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUH(cudaFuncSetAttribute(solve_kernel<16, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (N == 16) { CUH(configure_kernels<16>()); } else { CUH(configure_kernels<32>()); }
 #undef CUH
     *out = h;
     return MPCQP_OK;
@@ -279,7 +300,7 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
     // Host inputs: the batch is cut into chunks of two full waves (2 x 4 CTAs x #SM instances); chunk
     // c is copied and solved on side stream c & 1, so the H2D copy of one chunk overlaps the solve of
     // the previous one and the two solve kernels fill each other's tails.
-    const int chunk = 2 * 4 * h->sms;
+    const int chunk = 2 * h->ctas_per_sm(false) * h->sms;
     if (location == MPCQP_HOST) {
         dx = h->d_xref; df = h->d_fsteps;
         if (stageA && B > chunk) {
@@ -291,8 +312,7 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
                 cudaStream_t s = h->side[c & 1];
                 CU(cudaMemcpyAsync(h->d_xref + off * xs, xref + off * xs, n * xs * sizeof(double), cudaMemcpyHostToDevice, s));
                 CU(cudaMemcpyAsync(h->d_fsteps + off * fs, fsteps + off * fs, n * fs * sizeof(double), cudaMemcpyHostToDevice, s));
-                solve_kernel<16, false><<<n, 128, sizeof(Smem<16, false>), s>>>(h->dp, h->st, dx, df, first, off, n);
-                ++h->launches;
+                h->solve(false, n, s, dx, df, first, off, n);
             }
             for (int i = 0; i < 2; ++i) {
                 CU(cudaEventRecord(h->ev_side[i], h->side[i]));
@@ -301,14 +321,10 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
         } else {
             CU(cudaMemcpyAsync(h->d_xref, xref, B * xs * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             CU(cudaMemcpyAsync(h->d_fsteps, fsteps, B * fs * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-            if (stageA) {
-                solve_kernel<16, false><<<B, 128, sizeof(Smem<16, false>), h->stream>>>(h->dp, h->st, dx, df, first, 0, B);
-                ++h->launches;
-            }
+            if (stageA) h->solve(false, B, h->stream, dx, df, first, 0, B);
         }
     } else if (stageA) {
-        solve_kernel<16, false><<<B, 128, sizeof(Smem<16, false>), h->stream>>>(h->dp, h->st, dx, df, first, 0, B);
-        ++h->launches;
+        h->solve(false, B, h->stream, dx, df, first, 0, B);
     }
     if (!stageA) {
         // ADMM only: queue every instance
@@ -319,9 +335,8 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
         CU(cudaStreamSynchronize(h->stream));
     }
     if (h->p.mode & MPCQP_MODE_ADMM) {
-        const int grid = B < 2 * h->sms ? B : 2 * h->sms;
-        solve_kernel<16, true><<<grid, 128, sizeof(Smem<16, true>), h->stream>>>(h->dp, h->st, dx, df, first, 0, B);
-        ++h->launches;
+        const int slots = h->ctas_per_sm(true) * h->sms;
+        h->solve(true, B < slots ? B : slots, h->stream, dx, df, first, 0, B);
     }
     CU(cudaGetLastError());
     h->ran = true;
@@ -425,7 +440,8 @@ int mpcqp_export_build(mpcqp_handle* h, double k, const double* xref, const doub
     } else {
         dB = B_vals; dS = S_vals; dN = NK;
     }
-    export_build_kernel<16><<<(int)B, 128, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
+    if (N == 16) export_build_kernel<16><<<(int)B, 128, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
+    else export_build_kernel<32><<<(int)B, 128, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
     ++h->launches;
     CU(cudaGetLastError());
     if (host) {

@@ -25,7 +25,16 @@ __device__ unsigned long long g_prof[16];
 
 namespace mpcqp {
 
-constexpr int NWARPS = 4;           // warps per CTA (one CTA = one QP instance)
+// Launch shape per horizon.  N = 16: W is 39 KB, four CTAs of four warps share an SM.  N = 32: W is
+// 154 KB, one CTA of eight warps per SM, and the ADMM stage cannot hold a second factor, so its
+// polish attempts borrow the ADMM buffer and the ADMM system is refactored if the polish fails.
+template <int N>
+struct Cfg {
+    static constexpr int NW = (N <= 16) ? 4 : 8;                // warps per CTA (one CTA = one QP instance)
+    static constexpr int MIN_CTAS = (N <= 16) ? 4 : 1;          // CTAs per SM the active-set kernel is built for
+    static constexpr int MIN_CTAS_ADMM = (N <= 16) ? 2 : 1;
+    static constexpr bool TWO_BUF = (N <= 16);                  // ADMM kernel keeps W (polish) and W2 (ADMM) at once
+};
 
 // -------------------------------------------------------------------------------------------------
 // shared-memory plan of one CTA
@@ -37,7 +46,7 @@ struct Smem {
     static constexpr int NTILES = NT * (NT + 1) / 2;
     static constexpr int NF = 4 * N;        // foot-steps
     double W[NTILES * 64];                  // sweep / polish system: W, then inv(L) in place
-    double W2[ADMM ? NTILES * 64 : 2];      // ADMM system (ADMM stage only)
+    double W2[(ADMM && Cfg<N>::TWO_BUF) ? NTILES * 64 : 2];   // ADMM system (ADMM stage, when two factors fit)
     double xr[12 * (N + 1)];                // xref of this instance
     union {
         double fs[20 * 13];                 // fsteps of this instance (dead after decode)
@@ -287,7 +296,7 @@ __device__ int sweep(const DevParams& P, Smem<N, ADMM>& sm, unsigned int& phase,
     make_face(P, foot_thread && contact, sig, fc);
     assemble_W<N, S::NTILES>(P, sm.W, sm.fa, &sm.mbar, phase, fc, 0.0, 0.0, false, k, j, foot_thread);
     PROF(0);
-    const bool spd = factor_invert_tiles<S::NT, NWARPS>(sm.W, &sm.flag);
+    const bool spd = factor_invert_tiles<S::NT, Cfg<N>::NW>(sm.W, &sm.flag);
     PROF(1);
     if (!spd) return -1;
 
@@ -336,7 +345,7 @@ __device__ int sweep(const DevParams& P, Smem<N, ADMM>& sm, unsigned int& phase,
         }
         __syncthreads();
         PROF(3);
-        tri_solve<S::NT, NWARPS>(sm.W, sm.u, sm.tmp);
+        tri_solve<S::NT, Cfg<N>::NW>(sm.W, sm.u, sm.tmp);
         PROF(4);
         if (foot_thread) {
             double A[9], h[3];
@@ -509,7 +518,7 @@ __device__ __forceinline__ void finish(const DevParams& P, Smem<N, ADMM>& sm, co
 //                    ADMM = true : fallback stage for the instances queued in st.fb_list.
 // -------------------------------------------------------------------------------------------------
 template <int N, bool ADMM>
-__global__ void __launch_bounds__(32 * NWARPS, ADMM ? 2 : 4)
+__global__ void __launch_bounds__(32 * Cfg<N>::NW, ADMM ? Cfg<N>::MIN_CTAS_ADMM : Cfg<N>::MIN_CTAS)
 solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g, int first_tick,
              int inst_offset, int inst_count) {
     using S = Smem<N, ADMM>;
@@ -637,8 +646,9 @@ solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const 
             const double ddz = live ? 1.0 / (P.w_force + sigma + rho * (4.0 * mu * mu + 1.0)) : 0.0;
             Face fa;
             make_face(P, live, SIG_FREE, fa);
-            assemble_W<N, S::NTILES>(P, sm.W2, sm.fa, &sm.mbar, phase, fa, ddx, ddz, true, k, j, foot_thread);
-            const bool spd = factor_invert_tiles<S::NT, NWARPS>(sm.W2, &sm.flag);
+            double* const Wadmm = Cfg<N>::TWO_BUF ? sm.W2 : sm.W;
+            assemble_W<N, S::NTILES>(P, Wadmm, sm.fa, &sm.mbar, phase, fa, ddx, ddz, true, k, j, foot_thread);
+            bool spd = factor_invert_tiles<S::NT, Cfg<N>::NW>(Wadmm, &sm.flag);
             uint8_t prev_sig = 255;
             int stable = 0;
             while (spd && !done && iters < P.max_iter) {
@@ -657,7 +667,7 @@ solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const 
                     step_sum_store(v, sm.u + 6 * k, j);
                 }
                 __syncthreads();
-                tri_solve<S::NT, NWARPS>(sm.W2, sm.u, sm.tmp);
+                tri_solve<S::NT, Cfg<N>::NW>(Wadmm, sm.u, sm.tmp);
                 uint8_t cur = SIG_FREE;
                 if (live) {
                     double A[9], h[3];
@@ -695,6 +705,11 @@ solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const 
                         const int r = sweep<N, ADMM>(P, sm, phase, contact, cur, nsig, trial, k, j, foot_thread);
                         ++sweeps;
                         if (r > 0) { sol = trial; sig = cur; done = true; status = 1; }
+                        else if (!Cfg<N>::TWO_BUF) {
+                            // the polish borrowed the ADMM buffer: rebuild the ADMM factor and carry on
+                            assemble_W<N, S::NTILES>(P, Wadmm, sm.fa, &sm.mbar, phase, fa, ddx, ddz, true, k, j, foot_thread);
+                            spd = factor_invert_tiles<S::NT, Cfg<N>::NW>(Wadmm, &sm.flag);
+                        }
                     }
                 }
             }

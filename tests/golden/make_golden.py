@@ -71,6 +71,9 @@ def run_case(name, scen, ticks, first_state=None):
     out["ML_indptr"] = mpc.ML.indptr.copy()
     out["i_update_B"] = np.asarray(mpc.i_update_B)
     out["i_update_S"] = np.asarray(mpc.i_update_S)
+    if scen.N != 16:
+        for key in ("ML_data", "NK", "NK_inf", "x_admm", "warm_x"):     # keep the long-horizon fixture small
+            out[key] = out[key][:2]
     np.savez_compressed(os.path.join(HERE, "solve_%s.npz" % name), **out)
     nact = int(((np.abs(out["x"][:, 12 * scen.N:].reshape(ticks, -1, 3)[:, :, 2] - 25.0) < 1e-9)).sum())
     print("wrote solve_%s.npz  (%d ticks, %d foot-steps at fz_max)" % (name, ticks, nact))
@@ -122,5 +125,15 @@ def main():
     run_case("motionless", s, 4, first_state=np.array([0, 0, .2, 0, 0, 0, 0, 0, .1, 0, 0, 0]))
 
 
+def long_horizon():
+    # 6. long horizon (BASELINE configs[3]): n_periods = 2 -> N = 32, same T_gait
+    s = Scenario(1, n_steps=32, gaits="trot", v_ref=[0.5, 0.1, 0, 0, 0, 0.3], phase=[3], random_commands=False, seed=16)
+    run_case("trot_N32", s, 5)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "long":
+        long_horizon()
+    else:
+        main()
+        long_horizon()

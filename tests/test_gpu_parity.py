@@ -22,13 +22,14 @@ GOLD = sorted(glob.glob(os.path.join(HERE, "golden", "solve_*.npz")))
 N = 16
 
 
-def _active_from_x(g, t):
-    """Rows of the reference's inequality block that hold with equality at the golden optimum."""
-    import scipy.sparse as sp
-    A = sp.csc_matrix((g["ML_data"][t], g["ML_indices"], g["ML_indptr"]), shape=(44 * N, 24 * N))
-    Ax = (A @ g["x"][t])[24 * N:]
-    l, u = g["NK_inf"][t][24 * N:], g["NK"][t][24 * N:]
-    return ((np.abs(Ax - u) <= 1e-9) | (np.abs(Ax - l) <= 1e-9)).reshape(N, 4, 5)
+def _active_from_x(g, t, n):
+    """Rows of the reference's inequality block that hold with equality at the golden optimum (matrices
+    from oracle.mpc_build, which tests/test_oracle_build.py pins to the reference's own ML.data)."""
+    from oracle import mpc_build
+    _, A, l, u, _ = mpc_build.build_qp(g["xref"][t], g["fsteps"][t], mpc_build.Params(n_steps=n), first_tick=(g["k"][t] == 0))
+    Ax = (A @ g["x"][t])[24 * n:]
+    l, u = l[24 * n:], u[24 * n:]
+    return ((np.abs(Ax - u) <= 1e-9) | (np.abs(Ax - l) <= 1e-9)).reshape(n, 4, 5)
 
 
 @pytest.mark.parametrize("mode", [3, 2], ids=["activeset+admm", "admm-only"])
@@ -36,18 +37,17 @@ def _active_from_x(g, t):
 def test_golden_sequences(path, mode):
     """Replay each golden closed-loop sequence tick by tick (warm start carried like the reference)."""
     g = np.load(path)
-    eng = mpcqp.Engine(batch=1, mode=mode)
+    n = g["x"].shape[1] // 24                       # horizon of this fixture (16, or 32 for the long-horizon case)
+    eng = mpcqp.Engine(batch=1, n_steps=n, mode=mode)
     for t in range(len(g["k"])):
         eng.run(g["k"][t], g["xref"][t][None], g["fsteps"][t][None])
         f0, x, info = eng.forces()[0], eng.solution()[0], eng.info()
         assert info["status"][0] == 1
-        assert np.abs(x[12 * N:] - g["x"][t][12 * N:]).max() <= FORCE_TOL
+        assert np.abs(x[12 * n:] - g["x"][t][12 * n:]).max() <= FORCE_TOL
         assert np.abs(f0 - g["f_applied"][t]).max() <= FORCE_TOL
-        assert np.abs(x[:12 * N] - g["x"][t][:12 * N]).max() <= 1e-6
+        assert np.abs(x[:12 * n] - g["x"][t][:12 * n]).max() <= 1e-6
         assert abs(info["obj"][0] - g["obj"][t]) <= OBJ_RTOL * abs(g["obj"][t])
-        swing = np.isnan(g["fsteps"][t][:, 1::3]) | (g["fsteps"][t][:, 1::3] == 0)
-        assert info["contact"][0].sum() == 64 - (np.abs(g["x"][t][12 * N:].reshape(64, 3)).sum(axis=1) == 0).sum() or True
-        np.testing.assert_array_equal(info["active"][0], _active_from_x(g, t))
+        np.testing.assert_array_equal(info["active"][0], _active_from_x(g, t, n))
     eng.close()
 
 
@@ -55,18 +55,18 @@ def test_build_half_matches_reference_coefficients():
     """K1 parity: the coefficients MPC.update_ML / update_NK write (ML.data[i_update_B], [i_update_S], NK)."""
     for path in GOLD:
         g = np.load(path)
-        T = len(g["k"])
-        eng = mpcqp.Engine(batch=T)
+        T, n = len(g["ML_data"]), g["x"].shape[1] // 24
+        eng = mpcqp.Engine(batch=T, n_steps=n)
         for first in (False, True):
             ks = 0.0 if first else 1.0
-            Bv, Sv, NK = eng.export_build(ks, g["xref"], g["fsteps"])
+            Bv, Sv, NK = eng.export_build(ks, g["xref"][:T], g["fsteps"][:T])
             for t in range(T):
                 if (g["k"][t] == 0) != first:
                     continue
-                ref_B = np.stack([g["ML_data"][t][g["i_update_B"] + 96 * k] for k in range(N)])
+                ref_B = np.stack([g["ML_data"][t][g["i_update_B"] + 96 * k] for k in range(n)])
                 np.testing.assert_allclose(Bv[t], ref_B, rtol=1e-13, atol=1e-16)
                 np.testing.assert_array_equal(Sv[t], g["ML_data"][t][g["i_update_S"]])
-                np.testing.assert_allclose(NK[t], g["NK"][t][:12 * N], rtol=0, atol=1e-15)
+                np.testing.assert_allclose(NK[t], g["NK"][t][:12 * n], rtol=0, atol=1e-15)
         eng.close()
 
 
@@ -88,6 +88,27 @@ def test_closed_loop_batch_certified(gaits):
             np.testing.assert_array_equal(cert["contact"].astype(bool), info["contact"][b])
             np.testing.assert_array_equal(cert["active"].reshape(N, 4, 5), info["active"][b])
             assert abs(cert["obj"] - info["obj"][b]) <= OBJ_RTOL * abs(cert["obj"])
+        sc.advance(x[:, :12] + xref[:, :, 1])
+    eng.close()
+
+
+def test_long_horizon_closed_loop_certified():
+    """BASELINE configs[3], N = 32 (n_periods = 2): 24 robots x 6 ticks, mixed gaits, oracle certificate."""
+    from oracle import mpc_build
+    B, T, n = 24, 6, 32
+    eng = mpcqp.Engine(batch=B, n_steps=n)
+    sc = Scenario(B, n_steps=n, gaits=["trot", "pace", "walk"], seed=77)
+    par = mpc_build.Params(n_steps=n)
+    for t in range(T):
+        xref, fsteps = sc.inputs()
+        eng.run(t, xref, fsteps)
+        x, info = eng.solution(), eng.info()
+        assert (info["status"] == 1).all()
+        for b in range(0, B, 5):
+            cert = certify(xref[b], fsteps[b], x[b], info["y"][b], first_tick=(t == 0), params=par)
+            assert_certified(cert, "N=32 tick %d robot %d" % (t, b))
+            np.testing.assert_array_equal(cert["contact"].astype(bool), info["contact"][b])
+            np.testing.assert_array_equal(cert["active"].reshape(n, 4, 5), info["active"][b])
         sc.advance(x[:, :12] + xref[:, :, 1])
     eng.close()
 

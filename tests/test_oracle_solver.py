@@ -73,8 +73,8 @@ def test_port_reproduces_golden(name):
 def test_golden_solutions_are_optimal(path):
     """Independent of any solver: every stored x satisfies the KKT conditions of the QP MPC.py built."""
     g = np.load(path)
-    N = 16
-    for t in range(len(g["k"])):
+    N = g["x"].shape[1] // 24
+    for t in range(len(g["ML_data"])):
         A = sp.csc_matrix((g["ML_data"][t], g["ML_indices"], g["ML_indptr"]), shape=(44 * N, 24 * N))
         P, q = sp.diags(g["P_data"]).tocsc(), np.zeros(24 * N)
         l, u = g["NK_inf"][t], g["NK"][t]
