@@ -130,6 +130,22 @@ int64_t mpcqp_launch_count(mpcqp_handle* h);
 int mpcqp_export_build(mpcqp_handle* h, double k, const double* xref, const double* fsteps, int location,
                        double* B_vals, double* S_vals, double* NK);
 
+/* ---- device-resident closed loop (SURVEY.md 8f rows f1 + f2; the reference's producer side) --------------
+ * The footstep planner (FootstepPlanner.update_fsteps / getRefStates, FootstepPlanner.py:76-161, 284-445) and the
+ * closed-loop state update (MPC.q_next / v_next, MPC.py:448-450, moved into the next local frame as
+ * Interface.py:100-132 does) run inside the solve kernel, so a tick needs no host producer and no input copy.
+ * Per instance: seq = 64 bits, bit 4*s + j = foot j in contact at step s of the 16-step gait period
+ * (FootstepPlanner.py:207-282), phase = offset into that period, vref = 6 commanded velocities, state = 12 initial
+ * measured states; sigma4 = Gaussian noise (position, angle, linear, angular velocity) drawn from a counter-based
+ * generator keyed by (seed, instance, tick, component).  All pointers are HOST pointers. */
+int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* phase, const double* vref,
+                        const double* state, const double* sigma4, uint64_t seed);
+/* Run `ticks` closed-loop ticks (plan -> build -> solve -> integrate) back to back on the device.  With
+ * emit_inputs != 0 the xref / fsteps generated by the last tick can be read with mpcqp_get_inputs. */
+int mpcqp_scenario_run(mpcqp_handle* h, int ticks, int emit_inputs);
+int mpcqp_scenario_get(mpcqp_handle* h, double* state /*B x 12*/, double* frame /*B x 3*/, double* feet /*B x 8*/);
+int mpcqp_get_inputs(mpcqp_handle* h, double* xref, double* fsteps);
+
 /* Measured FP64 peak of the device in TFLOP/s (DMMA m8n8k4 issue loop), for roofline reporting. */
 int mpcqp_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);
 

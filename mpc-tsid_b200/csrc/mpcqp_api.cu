@@ -63,10 +63,10 @@ cudaError_t configure_kernels() {
 }
 
 template <int N>
-void launch_solve(bool admm, int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const double* dx,
-                  const double* df, int first, int off, int n) {
-    if (admm) solve_kernel<N, true><<<grid, 32 * Cfg<N>::NW, sizeof(Smem<N, true>), s>>>(dp, st, dx, df, first, off, n);
-    else solve_kernel<N, false><<<grid, 32 * Cfg<N>::NW, sizeof(Smem<N, false>), s>>>(dp, st, dx, df, first, off, n);
+void launch_solve(bool admm, int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
+                  const double* dx, const double* df, int first, int off, int n) {
+    if (admm) solve_kernel<N, true><<<grid, 32 * Cfg<N>::NW, sizeof(Smem<N, true>), s>>>(dp, st, sc, dx, df, first, off, n);
+    else solve_kernel<N, false><<<grid, 32 * Cfg<N>::NW, sizeof(Smem<N, false>), s>>>(dp, st, sc, dx, df, first, off, n);
 }
 
 struct mpcqp_handle {
@@ -87,9 +87,17 @@ struct mpcqp_handle {
     int64_t launches = 0;
     int sms = 0;
 
-    void solve(bool admm, int grid, cudaStream_t s, const double* dx, const double* df, int first, int off, int n) {
-        if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, dx, df, first, off, n);
-        else launch_solve<32>(admm, grid, s, dp, st, dx, df, first, off, n);
+    DevScenario sc;                 // device-resident closed loop (disabled unless mpcqp_scenario_init was called)
+    void* d_scen = nullptr;
+    int scen_tick = 0;
+    bool scen_ready = false;
+
+    void solve(bool admm, int grid, cudaStream_t s, const double* dx, const double* df, int first, int off, int n,
+               bool closed_loop = false) {
+        DevScenario use = sc;
+        use.enabled = closed_loop ? 1 : 0;
+        if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, use, dx, df, first, off, n);
+        else launch_solve<32>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         ++launches;
     }
     int ctas_per_sm(bool admm) const { return p.n_steps == 16 ? (admm ? 2 : 4) : 1; }
@@ -149,6 +157,7 @@ int mpcqp_destroy(mpcqp_handle* h) {
     cudaFree(h->d_Minv);
     cudaFree(h->d_C2);
     cudaFree(h->d_block);
+    cudaFree(h->d_scen);
     for (int i = 0; i < 2; ++i) {
         if (h->side[i]) cudaStreamDestroy(h->side[i]);
         if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
@@ -186,6 +195,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     mpcqp_handle* h = new (std::nothrow) mpcqp_handle();
     if (!h) return fail(MPCQP_ERR_INVALID, "out of host memory");
     h->p = *p;
+    std::memset(&h->sc, 0, sizeof(h->sc));
     h->sms = prop.multiProcessorCount;
     const int N = p->n_steps, B = p->batch;
     DevParams& d = h->dp;
@@ -487,6 +497,99 @@ int mpcqp_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
     if (dfma_tflops) *dfma_tflops = best[0];
     if (dmma_tflops) *dmma_tflops = best[1];
+    return MPCQP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident closed loop (SURVEY 8f rows f1 + f2)
+// ------------------------------------------------------------------------------------------------
+int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* phase, const double* vref, const double* state,
+                        const double* sigma4, uint64_t seed) {
+    if (!h || !seq || !phase || !vref || !state || !sigma4) return fail(MPCQP_ERR_INVALID, "null argument");
+    const size_t B = h->p.batch;
+    const int N = h->p.n_steps;
+    if (std::fabs(h->p.T_gait / h->p.dt - 16.0) > 1e-9) return fail(MPCQP_ERR_INVALID, "closed loop needs a 16-step gait period (T_gait / dt)");
+    CU(cudaSetDevice(h->p.device));
+    CU(cudaStreamSynchronize(h->stream));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_state = take(B * 12 * 8), o_frame = take(B * 3 * 8), o_feet = take(B * 8 * 8), o_target = take(B * 8 * 8);
+    const size_t o_vref = take(B * 6 * 8), o_seq = take(B * 8), o_phase = take(B * 4), o_prev = take(B);
+    if (!h->d_scen) CU(cudaMalloc(&h->d_scen, off));
+    CU(cudaMemset(h->d_scen, 0, off));
+    char* base = (char*)h->d_scen;
+    DevScenario& s = h->sc;
+    std::memset(&s, 0, sizeof(s));
+    s.state = (double*)(base + o_state); s.frame = (double*)(base + o_frame); s.feet = (double*)(base + o_feet);
+    s.target = (double*)(base + o_target); s.vref = (const double*)(base + o_vref);
+    s.seq = (const unsigned long long*)(base + o_seq); s.phase = (const int32_t*)(base + o_phase); s.prevc = (uint8_t*)(base + o_prev);
+    std::vector<double> feet(B * 8);
+    for (size_t b = 0; b < B; ++b)
+        for (int j = 0; j < 4; ++j) { feet[b * 8 + j] = sc_shoulder_x(j); feet[b * 8 + 4 + j] = sc_shoulder_y(j); }
+    CU(cudaMemcpy(base + o_state, state, B * 12 * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(base + o_feet, feet.data(), B * 8 * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(base + o_target, feet.data(), B * 8 * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(base + o_vref, vref, B * 6 * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(base + o_seq, seq, B * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(base + o_phase, phase, B * 4, cudaMemcpyHostToDevice));
+    for (int i = 0; i < 4; ++i) s.sigma[i] = sigma4[i];
+    // numpy.linspace(start, stop, N): start + i * step with the last element set to stop exactly
+    const double a0 = 0.0, a1 = h->p.T_gait - h->p.dt, b0 = h->p.dt, b1 = h->p.T_gait;
+    for (int i = 0; i < N; ++i) {
+        s.lin_a[i] = (i == N - 1) ? a1 : a0 + i * ((a1 - a0) / (N - 1));
+        s.lin_b[i] = (i == N - 1) ? b1 : b0 + i * ((b1 - b0) / (N - 1));
+    }
+    s.seed = seed;
+    h->scen_tick = 0;
+    h->scen_ready = true;
+    CU(mpcqp_reset_warm_start(h) == 0 ? cudaSuccess : cudaErrorUnknown);
+    return MPCQP_OK;
+}
+
+int mpcqp_scenario_run(mpcqp_handle* h, int ticks, int emit_inputs) {
+    if (!h || ticks < 0) return fail(MPCQP_ERR_INVALID, "bad argument");
+    if (!h->scen_ready) return fail(MPCQP_ERR_STATE, "mpcqp_scenario_init has not been called");
+    CU(cudaSetDevice(h->p.device));
+    const int B = h->p.batch;
+    const bool stageA = (h->p.mode & MPCQP_MODE_ACTIVE_SET) != 0;
+    if (!stageA) return fail(MPCQP_ERR_INVALID, "the closed loop needs the active-set stage enabled");
+    h->sc.xref_out = emit_inputs ? h->d_xref : nullptr;
+    h->sc.fsteps_out = emit_inputs ? h->d_fsteps : nullptr;
+    for (int t = 0; t < ticks; ++t) {
+        h->sc.tick = h->scen_tick;
+        const int first = h->scen_tick == 0 ? 1 : 0;
+        CU(cudaMemsetAsync(h->st.fb_count, 0, sizeof(int32_t), h->stream));
+        h->solve(false, B, h->stream, nullptr, nullptr, first, 0, B, true);
+        if (h->p.mode & MPCQP_MODE_ADMM) {
+            const int slots = h->ctas_per_sm(true) * h->sms;
+            h->solve(true, B < slots ? B : slots, h->stream, nullptr, nullptr, first, 0, B, true);
+        }
+        ++h->scen_tick;
+    }
+    CU(cudaGetLastError());
+    h->ran = true;
+    return MPCQP_OK;
+}
+
+int mpcqp_scenario_get(mpcqp_handle* h, double* state, double* frame, double* feet) {
+    if (!h) return fail(MPCQP_ERR_INVALID, "null argument");
+    if (!h->scen_ready) return fail(MPCQP_ERR_STATE, "mpcqp_scenario_init has not been called");
+    CU(cudaSetDevice(h->p.device));
+    const size_t B = h->p.batch;
+    if (state) CU(cudaMemcpyAsync(state, h->sc.state, B * 12 * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (frame) CU(cudaMemcpyAsync(frame, h->sc.frame, B * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (feet) CU(cudaMemcpyAsync(feet, h->sc.feet, B * 8 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MPCQP_OK;
+}
+
+int mpcqp_get_inputs(mpcqp_handle* h, double* xref, double* fsteps) {
+    if (!h || !xref || !fsteps) return fail(MPCQP_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->p.device));
+    const size_t B = h->p.batch, N = h->p.n_steps;
+    CU(cudaMemcpyAsync(xref, h->d_xref, B * 12 * (N + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(fsteps, h->d_fsteps, B * 260 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return MPCQP_OK;
 }
 

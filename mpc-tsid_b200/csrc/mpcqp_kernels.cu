@@ -9,6 +9,7 @@
 // The QP is solved in condensed form (states and swing-foot forces eliminated);
 // the optimum is the same point the reference's sparse QP has (strictly convex, unique).
 #include "mpcqp_device.cuh"
+#include "mpcqp_scenario.cuh"
 
 // Optional phase timing (-DMPCQP_PROFILE): per-phase clock64() deltas of thread 0, summed over CTAs
 // into g_prof; read back through mpcqp_debug_profile().  Off in the shipped build.
@@ -62,6 +63,7 @@ struct Smem {
     unsigned long long mbar;                // mbarrier of the bulk (TMA) staging copies
     int flag;
     int pad;
+    ScenarioSmem sc;                        // device-resident closed loop (planner scratch, predicted next state)
 };
 
 // per-foot description of the affine face f = pf + Z q selected by one signature:
@@ -432,8 +434,8 @@ __device__ __forceinline__ unsigned long long sig_hash(uint8_t sig, bool hashed,
 // finish: states by forward simulation, objective, masks, outputs            [MPC.py:432-458]
 // -------------------------------------------------------------------------------------------------
 template <int N, bool ADMM>
-__device__ __forceinline__ void finish(const DevParams& P, Smem<N, ADMM>& sm, const DevState& st, int inst, bool contact,
-                       const FootSol& sol, uint8_t sig, int k, int j, bool foot_thread, bool valid_A,
+__device__ __forceinline__ void finish(const DevParams& P, const DevScenario& S, Smem<N, ADMM>& sm, const DevState& st, int inst,
+                       bool contact, const FootSol& sol, uint8_t sig, int k, int j, bool foot_thread, bool valid_A,
                        int status, int sweeps, int iters) {
     constexpr int NF = 4 * N;
     const double lin = P.dt / P.mass;
@@ -459,6 +461,7 @@ __device__ __forceinline__ void finish(const DevParams& P, Smem<N, ADMM>& sm, co
             const double pn = p + P.dt * v;
             const double vn = v + sm.u[6 * s + c] + gc;
             p = pn; v = vn;
+            if (s == 0) { sm.sc.xnext[c] = p; sm.sc.xnext[6 + c] = v; }      // MPC.q_next / v_next (MPC.py:448-450)
             const double ep = p - sm.xr[c * (N + 1) + s + 1], ev = v - sm.xr[(6 + c) * (N + 1) + s + 1];
             xs[12 * s + c] = ep;
             xs[12 * s + 6 + c] = ev;
@@ -510,6 +513,8 @@ __device__ __forceinline__ void finish(const DevParams& P, Smem<N, ADMM>& sm, co
         st.status[inst] = status;
         st.sweeps[inst] = sweeps;
         st.iters[inst] = iters;
+        // device-resident closed loop: the robot moves to the state the MPC predicted for the next tick
+        if (S.enabled && status != 3) scenario_advance(S, inst, sm.sc.xnext);
     }
 }
 
@@ -519,8 +524,8 @@ __device__ __forceinline__ void finish(const DevParams& P, Smem<N, ADMM>& sm, co
 // -------------------------------------------------------------------------------------------------
 template <int N, bool ADMM>
 __global__ void __launch_bounds__(32 * Cfg<N>::NW, ADMM ? Cfg<N>::MIN_CTAS_ADMM : Cfg<N>::MIN_CTAS)
-solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g, int first_tick,
-             int inst_offset, int inst_count) {
+solve_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g,
+             int first_tick, int inst_offset, int inst_count) {
     using S = Smem<N, ADMM>;
     constexpr int NF = 4 * N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -543,15 +548,20 @@ solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const 
         const long long inst_t0 = clock64();
 #endif
         PROF_T0();
-        // ---- stage inputs in shared memory: two bulk async copies (16-byte aligned blocks per instance)
-        if (tid == 0) {
-            fence_async_smem();
-            mbar_expect_tx(&sm.mbar, (12 * (N + 1) + 260) * 8);
-            bulk_g2s(sm.xr, xref_g + (size_t)inst * 12 * (N + 1), 12 * (N + 1) * 8, &sm.mbar);
-            bulk_g2s(sm.fs, fsteps_g + (size_t)inst * 260, 260 * 8, &sm.mbar);
+        if (SC.enabled) {
+            // ---- device-resident closed loop: the planner runs here, inputs never touch HBM
+            scenario_inputs<N>(P, SC, sm.sc, inst, sm.xr, sm.fs);
+        } else {
+            // ---- stage inputs in shared memory: two bulk async copies (16-byte aligned blocks per instance)
+            if (tid == 0) {
+                fence_async_smem();
+                mbar_expect_tx(&sm.mbar, (12 * (N + 1) + 260) * 8);
+                bulk_g2s(sm.xr, xref_g + (size_t)inst * 12 * (N + 1), 12 * (N + 1) * 8, &sm.mbar);
+                bulk_g2s(sm.fs, fsteps_g + (size_t)inst * 260, 260 * 8, &sm.mbar);
+            }
+            mbar_wait(&sm.mbar, phase);
+            phase ^= 1u;
         }
-        mbar_wait(&sm.mbar, phase);
-        phase ^= 1u;
         bool bad = false, contact = false;
         uint8_t sig = SIG_FREE;
         double A0[9];
@@ -723,7 +733,7 @@ solve_kernel(DevParams P, DevState st, const double* __restrict__ xref_g, const 
             }
         }
         PROF(8);
-        finish<N, ADMM>(P, sm, st, inst, contact, sol, sig, k, j, foot_thread, !any_bad, status, sweeps, iters);
+        finish<N, ADMM>(P, SC, sm, st, inst, contact, sol, sig, k, j, foot_thread, !any_bad, status, sweeps, iters);
         PROF(9);
 #ifdef MPCQP_PROFILE
         if (threadIdx.x == 0) { atomicAdd(&g_prof[ADMM ? 13 : 12], (unsigned long long)(clock64() - inst_t0)); atomicAdd(&g_prof[ADMM ? 11 : 10], 1ull); }

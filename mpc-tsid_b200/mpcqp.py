@@ -20,6 +20,7 @@ EXPORTS = (
     "mpcqp_get_solution", "mpcqp_get_info", "mpcqp_get_fallback_count", "mpcqp_reset_warm_start",
     "mpcqp_synchronize", "mpcqp_stream", "mpcqp_launch_count", "mpcqp_export_build",
     "mpcqp_measure_fp64_peak", "mpcqp_last_error", "mpcqp_version",
+    "mpcqp_scenario_init", "mpcqp_scenario_run", "mpcqp_scenario_get", "mpcqp_get_inputs",
 )
 
 
@@ -72,6 +73,10 @@ def load():
     lib.mpcqp_launch_count.restype = C.c_int64
     lib.mpcqp_export_build.argtypes = [vp, C.c_double, dp, dp, C.c_int, dp, dp, dp]
     lib.mpcqp_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.mpcqp_scenario_init.argtypes = [vp, dp, dp, dp, dp, dp, C.c_uint64]
+    lib.mpcqp_scenario_run.argtypes = [vp, C.c_int, C.c_int]
+    lib.mpcqp_scenario_get.argtypes = [vp, dp, dp, dp]
+    lib.mpcqp_get_inputs.argtypes = [vp, dp, dp]
     lib.mpcqp_last_error.restype = C.c_char_p
     lib.mpcqp_version.restype = C.c_char_p
     _lib = lib
@@ -186,6 +191,34 @@ class Engine:
         Bv, Sv, NK = np.empty((self.B, self.N, 48)), np.empty((self.B, 12 * self.N)), np.empty((self.B, 12 * self.N))
         _check(self.lib.mpcqp_export_build(self._h, float(k), _ptr(xref), _ptr(fsteps), HOST, _ptr(Bv), _ptr(Sv), _ptr(NK)))
         return Bv, Sv, NK
+
+    # ---- device-resident closed loop (planner + integration inside the solve kernel)
+    def scenario_init(self, scen):
+        """Take the robots of a host `scenario.Scenario` (gaits, phases, commands, initial states, noise
+        levels, seed; it must use noise_kind="hash" or zero noise to stay comparable) onto the device."""
+        if scen.B != self.B or scen.N != self.N:
+            raise ValueError("scenario and engine disagree on batch / horizon")
+        seq = np.ascontiguousarray(scen.seq_bits(), dtype=np.uint64)
+        phase = np.ascontiguousarray(scen.phase, dtype=np.int32)
+        vref = np.ascontiguousarray(scen.current_v_ref(), dtype=np.float64)
+        state = np.ascontiguousarray(scen.state, dtype=np.float64)
+        sigma = np.ascontiguousarray(scen.noise, dtype=np.float64)
+        _check(self.lib.mpcqp_scenario_init(self._h, _ptr(seq), _ptr(phase), _ptr(vref), _ptr(state), _ptr(sigma),
+                                            C.c_uint64(int(scen.seed))))
+
+    def scenario_run(self, ticks, emit_inputs=False):
+        _check(self.lib.mpcqp_scenario_run(self._h, int(ticks), 1 if emit_inputs else 0))
+
+    def scenario_state(self):
+        B = self.B
+        state, frame, feet = np.empty((B, 12)), np.empty((B, 3)), np.empty((B, 2, 4))
+        _check(self.lib.mpcqp_scenario_get(self._h, _ptr(state), _ptr(frame), _ptr(feet)))
+        return dict(state=state, frame=frame, feet=feet)
+
+    def last_inputs(self):
+        xref, fsteps = np.empty((self.B, 12, self.N + 1)), np.empty((self.B, 20, 13))
+        _check(self.lib.mpcqp_get_inputs(self._h, _ptr(xref), _ptr(fsteps)))
+        return xref, fsteps
 
     def reset_warm_start(self):
         _check(self.lib.mpcqp_reset_warm_start(self._h))

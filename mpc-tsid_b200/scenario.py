@@ -71,12 +71,32 @@ def reference_ramp(tick):
     return min(max((20.0 * tick - 960.0) / 3500.0, 0.0), 1.0)
 
 
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def hash_normal(seed, inst, tick, comp):
+    """Standard normal as a pure function of (seed, robot, tick, component): splitmix64 + Box-Muller.
+    Bit-for-bit the integer path of mpcqp_scenario.cuh::hash_normal (the libm calls may differ by an ulp)."""
+    with np.errstate(over="ignore"):
+        key = _splitmix64(seed + inst * np.uint64(0x9E3779B97F4A7C15) + tick * np.uint64(0xD1B54A32D192ED03)
+                          + comp * np.uint64(0x8CB92BA72F3D8DD7))
+        h1, h2 = _splitmix64(key), _splitmix64(key ^ np.uint64(0xA5A5A5A5A5A5A5A5))
+    u1 = ((h1 >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+    u2 = ((h2 >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(6.283185307179586 * u2)
+
+
 class Scenario:
     """B independent robots, each with its own gait, gait phase, velocity command and noise stream."""
 
     def __init__(self, batch, n_steps=16, dt=0.02, T_gait=0.32, gaits="trot", seed=20260,
                  v_ref=None, phase=None, noise=(1e-3, 5e-3, 1e-2, 2e-2), random_commands=True,
-                 ramp=False):
+                 ramp=False, noise_kind="numpy"):
         self.B, self.N, self.dt, self.T_gait = int(batch), int(n_steps), float(dt), float(T_gait)
         B, N = self.B, self.N
         self.period = int(round(T_gait / dt))
@@ -100,6 +120,10 @@ class Scenario:
             self.v_ref[:, 5] = self._bulk_rng.uniform(-0.4, 0.4, B)
         self.ramp = bool(ramp)
         self.noise = np.asarray(noise, dtype=np.float64)
+        # "numpy": one numpy Generator per robot (configs[0..2]); "hash": a counter-based generator keyed by
+        # (seed, robot, tick, component) that the device-resident closed loop reproduces (mpcqp_scenario.cuh)
+        self.noise_kind = noise_kind
+        self.seed = int(seed)
         self.tick = 0
         # measured state in the local frame: [x, y, z, roll, pitch, yaw, vx, vy, vz, wx, wy, wz]
         self.state = np.zeros((B, 12))
@@ -248,8 +272,21 @@ class Scenario:
         self._touchdown_target_w = np.where(np.isnan(tw), self._touchdown_target_w, tw)
         return self.xref.copy(), self.fsteps.copy()
 
+    def seq_bits(self):
+        """The gait period as 64 bits per robot: bit 4*s + j = foot j in contact at step s (libmpcqp's format)."""
+        bits = np.zeros(self.B, dtype=np.uint64)
+        for s_ in range(self.period):
+            for j in range(4):
+                bits |= (self.seq[:, s_, j] == 1.0).astype(np.uint64) << np.uint64(4 * s_ + j)
+        return bits
+
     def _noise(self):
         B = self.B
+        if self.noise_kind == "hash":
+            inst = np.arange(B, dtype=np.uint64)[:, None]
+            comp = np.arange(12, dtype=np.uint64)[None, :]
+            n = hash_normal(np.uint64(self.seed), inst, np.uint64(self.tick), comp)
+            return n * np.repeat(self.noise, 3)[None, :]
         if self.rng is not None:
             n = np.stack([r.standard_normal(12) for r in self.rng])
         else:

@@ -191,3 +191,56 @@ def test_full_batch_properties():
             fresh.close()
         sc.advance(x[:, :12] + xref[:, :, 1])
     eng.close()
+
+
+@pytest.mark.parametrize("noise", [(0.0, 0.0, 0.0, 0.0), (1e-3, 5e-3, 1e-2, 2e-2)], ids=["noiseless", "hash-noise"])
+def test_device_closed_loop_matches_host_loop(noise):
+    """SURVEY 8f rows f1 + f2: planner + closed-loop integration inside the solve kernel against the
+    host loop (scenario.py, itself pinned to the reference planner) driving the same engine tick by tick:
+    generated xref / fsteps, forces and robot states must agree every tick."""
+    B, T = 48, 14
+    kw = dict(gaits=["trot", "pace", "bound", "walk", "static"], seed=31, noise=noise, noise_kind="hash")
+    host_sc, dev_sc = Scenario(B, **kw), Scenario(B, **kw)
+    host, dev = mpcqp.Engine(batch=B), mpcqp.Engine(batch=B)
+    dev.scenario_init(dev_sc)
+    for t in range(T):
+        xref, fsteps = host_sc.inputs()
+        host.run(t, xref, fsteps)
+        xh = host.solution()
+        dev.scenario_run(1, emit_inputs=True)
+        xd_ref, fd = dev.last_inputs()
+        assert np.array_equal(np.isnan(fd), np.isnan(fsteps)), "tick %d: swing pattern" % t
+        np.testing.assert_allclose(np.nan_to_num(fd), np.nan_to_num(fsteps), rtol=0, atol=1e-9)
+        np.testing.assert_allclose(xd_ref, xref, rtol=0, atol=1e-9)
+        assert (dev.info()["status"] == 1).all()
+        np.testing.assert_allclose(dev.forces(), host.forces(), rtol=0, atol=1e-6)
+        host_sc.advance(xh[:, :12] + xref[:, :, 1])
+        st = dev.scenario_state()
+        np.testing.assert_allclose(st["state"], host_sc.state, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(st["frame"], host_sc.frame, rtol=0, atol=1e-9)
+    host.close(); dev.close()
+
+
+def test_mixed_gait_sweep_on_device():
+    """BASELINE configs[2] shape (65 536 robots, trot / pace / bound / walk, per-instance contact masks),
+    run as a device-resident closed loop: everything solved, forces feasible, contact masks follow the
+    gait tables, and a sample passes the oracle certificate on the inputs the device generated."""
+    B, T = 65536, 6
+    sc = Scenario(B, gaits=["trot", "pace", "bound", "walk"], seed=99, noise_kind="hash")
+    eng = mpcqp.Engine(batch=B)
+    eng.scenario_init(sc)
+    eng.scenario_run(T - 1)
+    eng.scenario_run(1, emit_inputs=True)
+    info, x = eng.info(), eng.solution()
+    assert (info["status"] == 1).all()
+    f = x[:, 12 * N:].reshape(B, N, 4, 3)
+    mu = eng.params.mu
+    assert (np.abs(f[..., 0]) <= mu * f[..., 2] + 1e-8).all() and (np.abs(f[..., 1]) <= mu * f[..., 2] + 1e-8).all()
+    assert (f[..., 2] >= -1e-9).all() and (f[..., 2] <= 25 + 1e-8).all() and (f[~info["contact"]] == 0).all()
+    idx = (T - 1 + sc.phase[:, None] + np.arange(N)[None, :]) % 16
+    expect = np.take_along_axis(sc.seq, idx[:, :, None], axis=1) == 1.0
+    np.testing.assert_array_equal(info["contact"], expect)
+    xref, fsteps = eng.last_inputs()
+    for b in range(0, B, 4099):
+        assert_certified(certify(xref[b], fsteps[b], x[b], info["y"][b]), "robot %d" % b)
+    eng.close()
