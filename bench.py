@@ -14,8 +14,8 @@ path ("weak": every GPU gets its own B robots); torch.distributed is used only f
 the max-over-ranks of the timings.
 
 `--impl reference` times the reference's CPU path instead: since `osqp` is not installable here and
-/root/reference does not travel to the GPU box, that is the oracle port (oracle/mpc_build.py +
-oracle/osqp_port.py at eps 1e-8), one process per host core.
+/root/reference does not travel to the GPU box, that is the oracle port in plain C (oracle/mpc_osqp.c at eps 1e-8),
+one robot per host thread.
 """
 import argparse
 import json
@@ -40,45 +40,46 @@ N_STEPS = 16
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port, one closed-loop robot per worker process
+# CPU arm: the plain-C restatement of MPC.py + the OSQP algorithm (oracle/mpc_osqp.c), one robot per
+# host thread.  Closed-loop input sequences are recorded first (untimed, the oracle itself in the
+# loop), then replayed by `cores` threads at once: the timed region holds nothing but the path
+# (build -> warm start -> update -> solve -> extract), tick after tick, exactly as MPC.run does.
 # ----------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    wid, warm, timed = args
-    import scipy.sparse as sp
-    from oracle import mpc_build
-    from oracle.osqp_port import OSQP
+def _record_closed_loop(args):
+    wid, ticks = args
+    from oracle import c_port
     from scenario import Scenario
     sc = Scenario(1, gaits="trot", seed=20260 + 1000 + wid)
-    p = mpc_build.Params()
-    N = p.n_steps
-    solver, x, t0 = None, None, None
-    for t in range(warm + timed):
-        if t == warm:
-            t0 = time.perf_counter()
+    m = c_port.MPC(n_steps=N_STEPS, eps=1e-8)
+    xs, fs = [], []
+    for t in range(ticks):
         xref, fsteps = sc.inputs()
-        Pd, A, l, u, _ = mpc_build.build_qp(xref[0], fsteps[0], p, first_tick=(t == 0))      # MPC.py:491-494
-        if solver is None:
-            solver = OSQP()
-            solver.setup(P=sp.diags(Pd).tocsc(), q=np.zeros(24 * N), A=A, l=l, u=u, eps_abs=1e-8, eps_rel=1e-8)
-        else:
-            solver.update(Ax=A.data, l=l, u=u)                                               # MPC.py:419
-            solver.warm_start(x=mpc_build.shift_warm_start(x, N))                            # MPC.py:403-406, 420
-        x = solver.solve().x                                                                 # MPC.py:427-428
-        _, x_robot = mpc_build.extract(x, xref[0], N)
+        r = m.run(t == 0, xref[0], fsteps[0])                                   # MPC.py:460-514
+        xs.append(xref[0]); fs.append(fsteps[0])
+        x_robot = r["x"][:12 * N_STEPS].reshape((12, N_STEPS), order="F") + xref[0][:, 1:]    # MPC.py:437
         sc.advance(x_robot[:, 0][None])
-    return time.perf_counter() - t0
+    m.close()
+    return np.stack(xs), np.stack(fs)
 
 
 def cpu_arm(steps, warmup, cores=None):
-    import multiprocessing as mp
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import c_port
+    c_port.load()
     cores = cores or os.cpu_count() or 1
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        times = pool.map(_cpu_worker, [(w, warmup, steps) for w in range(cores)])
-    wall = max(times)
+    distinct = min(cores, 16)
+    T = warmup + steps
+    with ThreadPoolExecutor(distinct) as pool:          # ctypes releases the GIL inside the C solve
+        recs = list(pool.map(_record_closed_loop, [(w, T) for w in range(distinct)]))
+    xr = np.stack([recs[i % distinct][0] for i in range(cores)])
+    fs = np.stack([recs[i % distinct][1] for i in range(cores)])
+    wall, _, iters = c_port.replay_mt(xr, fs, warm=warmup, n_steps=N_STEPS, eps=1e-8)
     return dict(value=cores * steps / wall, unit=UNIT, cores=cores, kind="port",
-                sample="%d processes x %d closed-loop trot ticks (after %d warm-up ticks) of oracle/mpc_build.py + "
-                       "oracle/osqp_port.py at eps 1e-8, no polish" % (cores, steps, warmup)), wall
+                osqp_iterations_per_solve=iters, eps=1e-8,
+                sample="%d host threads x %d consecutive closed-loop trot ticks each (after %d untimed warm-up ticks; %d distinct "
+                       "robots) through oracle/mpc_osqp.c = C restatement of MPC.py's build + the OSQP algorithm (sparse LDL', "
+                       "Ruiz scaling, adaptive rho, warm start) at eps 1e-8, polish off; the reference's own build half is "
+                       "Python (~1.3 ms per tick, SURVEY.md 6) and would be slower than this" % (cores, steps, warmup, distinct)), wall
 
 
 def reference_main(args):
@@ -94,8 +95,8 @@ def reference_main(args):
                    "sample": "one closed-loop trot robot per host core, one QP per tick (same generator, same tick shape)"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "osqp is not installable offline and /root/reference is absent on the GPU box: this is the oracle port "
-                "(restated MPC.py build + restated OSQP algorithm), a step = one tick of every worker",
+        "note": "osqp is not installable offline and /root/reference is absent on the GPU box: this is the oracle port in C "
+                "(oracle/mpc_osqp.c: restated MPC.py build + restated OSQP algorithm), a step = one tick of every host thread",
     }
     print(json.dumps(line))
     return 0
@@ -176,7 +177,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="robots per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-ticks", type=int, default=6)
+    ap.add_argument("--cpu-ticks", type=int, default=100)
     ap.add_argument("--settle", type=int, default=20,
                     help="closed-loop ticks run (untimed) before the warm-up so that the timed ticks are steady-state "
                          "operation, not the cold-start transient of robots released from rest")
@@ -307,7 +308,7 @@ def main():
         hbm_peak, hbm_src = 6650.0, "fallback"
     hbm_ach = hbm_alg * B * K / (total_ms * 1e-3) * 1e-9
     roofline = {
-        "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+        "bound": "tensor", "pipe": "FP64 tensor (DMMA m8n8k4) + FP64 FMA", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
         "traffic": 22.49e6 * B / 4096.0, "kernel": "solve_kernel<16,false> (+ ADMM fallback kernel)",
         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel<16,false> launch at 4096 "
                           "instances, ncu --set full (profiles/r01_solve_kernel_ncu_summary.txt), scaled to this batch",
@@ -325,7 +326,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_arm(args.cpu_ticks, 2)
+        cpu, _ = cpu_arm(args.cpu_ticks, 3)
 
     if rank == 0:
         line = {
