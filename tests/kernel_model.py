@@ -425,3 +425,110 @@ class Engine:
                         ntz = 1
                 out[k, j] = [nsx, nsy, ntz]
         return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Stage-wise (Riccati) form of the same equality-constrained solve: model of mpcqp_riccati.cuh.
+# State x = [p (6); v (6)], x+ = A x + [0; u + g], u = ubar + w, w = Bq q, stage input cost 1/2 q'Rq.
+# Backward:  L L' = Pvv+,  C = L' E L,  G = I + C,  Gamma = L^-T (I - G^-1) L^-1  (= (I + E Pvv)^-1 E),
+#            Pt = P+ - P+[:,v] Gamma P+[v,:],  P_k = Q + A' Pt A,  p_k = -Q xref_k + A'(Pt[:,v] beta + pt).
+# Forward:   z = A x + b, lam = P+[v,:] z + p+[v], w = -Gamma lam, x+ = z + [0; w], lamhat = lam + Pvv+ w.
+# Per foot:  q = -R^-1 Bq' lamhat, f = pf + Z q, grad = w_f f + Bv' lamhat.
+# --------------------------------------------------------------------------------------------------
+def riccati_faces(p, contact, sig):
+    N, mu = p.N, p.mu
+    Z = np.zeros((N, 4, 3, 3))
+    pf = np.zeros((N, 4, 3))
+    zz = np.zeros((N, 4, 3))
+    for k in range(N):
+        for j in range(4):
+            if not contact[k, j]:
+                continue
+            sx, sy, tz = sig[k, j]
+            if tz == 1:
+                continue
+            if sx == 0:
+                Z[k, j, 0, 0] = 1.0
+            if sy == 0:
+                Z[k, j, 1, 1] = 1.0
+            if tz == 0:
+                Z[k, j, :, 2] = [sx * mu, sy * mu, 1.0]
+            else:
+                pf[k, j] = [sx * mu * p.fz_max, sy * mu * p.fz_max, p.fz_max]
+            zz[k, j] = np.sum(Z[k, j] * Z[k, j], axis=0)
+    act = zz > 0
+    dinv = np.where(act, 1.0 / np.where(act, p.w_force * zz, 1.0), 0.0)
+    return Z, pf, dinv
+
+
+def riccati_solve(p, xref, Bv, contact, sig):
+    """-> f (N,4,3), grad (N,4,3) = H f + g of the condensed problem, X (N,12) states 1..N."""
+    N, dt = p.N, p.dt
+    Z, pf, dinv = riccati_faces(p, contact, sig)
+    Qp, Qv = p.w_state[0:6], p.w_state[6:12]
+    gv = np.zeros(6)
+    gv[2] = -p.gravity * dt
+    E = np.zeros((N, 6, 6))
+    beta = np.zeros((N, 6))
+    for k in range(N):
+        beta[k] = gv
+        for j in range(4):
+            if contact[k, j]:
+                Bq = Bv[k, j] @ Z[k, j]
+                E[k] += Bq @ (dinv[k, j][:, None] * Bq.T)
+                beta[k] += Bv[k, j] @ pf[k, j]
+    I6 = np.eye(6)
+    # terminal cost-to-go at state N
+    Ppp, Ppv, Pvv = np.diag(Qp), np.zeros((6, 6)), np.diag(Qv)
+    pp, pv = -Qp * xref[0:6, N], -Qv * xref[6:12, N]
+    store = [None] * N
+    for k in range(N - 1, -1, -1):
+        L = np.linalg.cholesky(Pvv)
+        Linv = np.linalg.inv(L)
+        C = L.T @ E[k] @ L
+        G = I6 + C
+        M = np.linalg.cholesky(G)
+        Minv = np.linalg.inv(M)
+        X = L @ Minv.T                     # Ptvv = X X'
+        Y = Ppv @ Linv.T                   # Ppv L^-T
+        Y2 = Y @ Minv.T
+        Gam = Linv.T @ (I6 - Minv.T @ Minv) @ Linv
+        store[k] = (Ppv.copy(), Pvv.copy(), pv.copy(), Gam)
+        Ptvv = X @ X.T
+        Ptpv = Y2 @ X.T
+        Ptpp = Ppp - Y @ Y.T + Y2 @ Y2.T
+        gp = Gam @ pv
+        ptp = pp - Ppv @ gp
+        ptv = pv - Pvv @ gp
+        if k == 0:
+            break
+        hp = Ptpv @ beta[k] + ptp          # [Pt[:,v] beta + pt]
+        hv = Ptvv @ beta[k] + ptv
+        nPpp = Ptpp + np.diag(Qp)
+        nPpv = dt * Ptpp + Ptpv
+        nPvv = dt * dt * Ptpp + dt * (Ptpv + Ptpv.T) + Ptvv + np.diag(Qv)
+        npp = hp - Qp * xref[0:6, k]
+        npv = dt * hp + hv - Qv * xref[6:12, k]
+        Ppp, Ppv, Pvv, pp, pv = nPpp, nPpv, 0.5 * (nPvv + nPvv.T), npp, npv
+    xp, xv = xref[0:6, 0].copy(), xref[6:12, 0].copy()
+    Xs = np.zeros((N, 12))
+    lam = np.zeros((N, 6))
+    for k in range(N):
+        Ppv_, Pvv_, pv_, Gam = store[k]
+        zp = xp + dt * xv
+        zv = xv + beta[k]
+        l0 = Ppv_.T @ zp + Pvv_ @ zv + pv_
+        w = -Gam @ l0
+        xp, xv = zp, zv + w
+        lam[k] = l0 + Pvv_ @ w
+        Xs[k, 0:6], Xs[k, 6:12] = xp, xv
+    f = np.zeros((N, 4, 3))
+    grad = np.zeros((N, 4, 3))
+    for k in range(N):
+        for j in range(4):
+            if contact[k, j]:
+                Bq = Bv[k, j] @ Z[k, j]
+                q = -dinv[k, j] * (Bq.T @ lam[k])
+                f[k, j] = pf[k, j] + Z[k, j] @ q
+                grad[k, j] = p.w_force * f[k, j] + Bv[k, j].T @ lam[k]
+    return f, grad, Xs
