@@ -47,6 +47,8 @@ extern "C" {
 /* solver stages that may run (bit mask in mpcqp_params.mode) */
 #define MPCQP_MODE_ACTIVE_SET 1     /* warm-started primal-dual active-set sweeps (fast path)   */
 #define MPCQP_MODE_ADMM 2           /* fixed-rho ADMM + guarded polish (globally convergent)    */
+#define MPCQP_MODE_STAGEWISE 4      /* active-set stage factorises stage by stage (Riccati recursion over the horizon, one warp per
+                                       robot, O(N)) instead of the dense 6N x 6N condensed system (one CTA per robot, O(N^3))      */
 
 typedef struct mpcqp_handle mpcqp_handle;
 

@@ -63,6 +63,20 @@ cudaError_t configure_kernels() {
 }
 
 template <int N>
+cudaError_t configure_stagewise() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(riccati_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RIC_WARPS * sizeof(RicWarp<N>))))) return e;
+    return cudaFuncSetAttribute(riccati_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+template <int N>
+void launch_stagewise(int n_inst, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc, const double* dx,
+                      const double* df, int first, int off) {
+    const int grid = (n_inst + RIC_WARPS - 1) / RIC_WARPS;
+    riccati_kernel<N><<<grid, 32 * RIC_WARPS, RIC_WARPS * sizeof(RicWarp<N>), s>>>(dp, st, sc, dx, df, first, off, n_inst);
+}
+
+template <int N>
 void launch_solve(bool admm, int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
                   const double* dx, const double* df, int first, int off, int n) {
     if (admm) solve_kernel<N, true><<<grid, 32 * Cfg<N>::NW, sizeof(Smem<N, true>), s>>>(dp, st, sc, dx, df, first, off, n);
@@ -96,7 +110,12 @@ struct mpcqp_handle {
                bool closed_loop = false) {
         DevScenario use = sc;
         use.enabled = closed_loop ? 1 : 0;
-        if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, use, dx, df, first, off, n);
+        if (!admm && (p.mode & MPCQP_MODE_STAGEWISE)) {
+            // active-set stage on the stage-wise factorisation: one warp per robot, grid covers the n robots
+            if (p.n_steps == 16) launch_stagewise<16>(n, s, dp, st, use, dx, df, first, off);
+            else if (p.n_steps == 32) launch_stagewise<32>(n, s, dp, st, use, dx, df, first, off);
+            else launch_stagewise<64>(n, s, dp, st, use, dx, df, first, off);
+        } else if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         else launch_solve<32>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         ++launches;
     }
@@ -172,8 +191,12 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     if (!p || !out) return fail(MPCQP_ERR_INVALID, "null argument");
     *out = nullptr;
     if (p->struct_size != (int32_t)sizeof(mpcqp_params)) return fail(MPCQP_ERR_INVALID, "mpcqp_params.struct_size mismatch");
-    if (p->n_steps != 16 && p->n_steps != 32)
-        return fail(MPCQP_ERR_INVALID, "n_steps: this build supports horizons of 16 and 32 steps");
+    if (p->n_steps != 16 && p->n_steps != 32 && p->n_steps != 64)
+        return fail(MPCQP_ERR_INVALID, "n_steps: this build supports horizons of 16, 32 and 64 steps");
+    if (p->n_steps == 64 && (!(p->mode & MPCQP_MODE_STAGEWISE) || (p->mode & MPCQP_MODE_ADMM)))
+        return fail(MPCQP_ERR_INVALID, "n_steps = 64 runs on the stage-wise active-set stage only (mode = ACTIVE_SET | STAGEWISE)");
+    if ((p->mode & MPCQP_MODE_STAGEWISE) && !(p->mode & MPCQP_MODE_ACTIVE_SET))
+        return fail(MPCQP_ERR_INVALID, "MPCQP_MODE_STAGEWISE selects the factorisation of the active-set stage: set MPCQP_MODE_ACTIVE_SET too");
     if (p->batch < 1) return fail(MPCQP_ERR_INVALID, "batch must be >= 1");
     if (!(p->dt > 0) || !(p->mass > 0) || !(p->mu > 0) || !(p->fz_max > 0) || !(p->w_force > 0))
         return fail(MPCQP_ERR_INVALID, "dt, mass, mu, fz_max, w_force must be positive");
@@ -276,7 +299,9 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     h->st.fb_list = (int32_t*)(base + o_list); h->st.fb_count = (int32_t*)(base + o_count);
     h->st.sig = (uint8_t*)(base + o_sig);
     CUH(cudaMemset(h->st.sig, SIG_FREE, (size_t)B * 4 * N));
-    if (N == 16) { CUH(configure_kernels<16>()); } else { CUH(configure_kernels<32>()); }
+    if (N == 16) { CUH(configure_kernels<16>()); CUH(configure_stagewise<16>()); }
+    else if (N == 32) { CUH(configure_kernels<32>()); CUH(configure_stagewise<32>()); }
+    else { CUH(configure_stagewise<64>()); }
 #undef CUH
     *out = h;
     return MPCQP_OK;

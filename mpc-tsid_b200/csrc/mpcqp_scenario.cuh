@@ -65,17 +65,20 @@ struct ScenarioSmem {
     int nrows;
 };
 
-// Build xref (12 x (N+1)) and fsteps (20 x 13) of instance `inst` in shared memory.  All threads call it.
-template <int N>
+// Build xref (12 x (N+1)) and fsteps (20 x 13) of instance `inst` in shared memory.  Called by every thread of
+// the group that owns the instance: the whole CTA (WARP = false) or one warp (WARP = true).
+template <int N, bool WARP = false>
 __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, ScenarioSmem& sc, int inst, double* xr, double* fs) {
-    const int tid = threadIdx.x;
+    const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    const int nthr = WARP ? 32 : (int)blockDim.x;
+    auto group_sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
     const double nanv = __longlong_as_double(0x7ff8000000000000ll);
-    for (int i = tid; i < 260; i += blockDim.x) fs[i] = (i % 13 == 0) ? 0.0 : nanv;
-    for (int i = tid; i < 12 * (N + 1); i += blockDim.x) xr[i] = 0.0;
+    for (int i = tid; i < 260; i += nthr) fs[i] = (i % 13 == 0) ? 0.0 : nanv;
+    for (int i = tid; i < 12 * (N + 1); i += nthr) xr[i] = 0.0;
     if (tid < 12) sc.st[tid] = S.state[(size_t)inst * 12 + tid];
     if (tid < 3) sc.fr[tid] = S.frame[(size_t)inst * 3 + tid];
     if (tid < 6) sc.vr[tid] = S.vref[(size_t)inst * 6 + tid];
-    __syncthreads();
+    group_sync();
     const double w = sc.vr[5];
     if (tid == 0) {
         // run-length table of the next N steps of the periodic gait (what FootstepPlanner.roll maintains)
@@ -91,14 +94,13 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
         sc.nrows = rows;
         for (int r = 0; r < rows; ++r) fs[r * 13] = (double)sc.cnt[r];
     }
-    if (tid >= 32 && tid < 32 + N) {
-        const int i = tid - 32;
+    for (int i = WARP ? tid : tid - 32; i >= 0 && i < N; i += WARP ? 32 : N) {
         double sn, cs;
         sincos(S.lin_a[i] * w, &sn, &cs);                                  // FootstepPlanner.py:95-97
         sc.vx[i] = sc.vr[0] * cs - sc.vr[1] * sn;
         sc.vy[i] = sc.vr[0] * sn + sc.vr[1] * cs;
     }
-    __syncthreads();
+    group_sync();
     if (tid < 4) {
         const int j = tid;
         double fwx = S.feet[(size_t)inst * 8 + j], fwy = S.feet[(size_t)inst * 8 + 4 + j];
@@ -155,7 +157,7 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
         S.feet[(size_t)inst * 8 + j] = fwx; S.feet[(size_t)inst * 8 + 4 + j] = fwy;
         S.target[(size_t)inst * 8 + j] = twx; S.target[(size_t)inst * 8 + 4 + j] = twy;
     }
-    if (tid == 32) {
+    if (tid == (WARP ? 4 : 32)) {
         // positions: dt * cumsum of the rotated reference velocity, from the measured position (sequential like numpy)
         double cx = 0.0, cy = 0.0;
         for (int i = 0; i < N; ++i) {
@@ -166,21 +168,20 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
             xr[7 * (N + 1) + 1 + i] = sc.vy[i];
         }
     }
-    if (tid >= 64 && tid < 64 + N) {
-        const int i = tid - 64;
+    for (int i = WARP ? tid : tid - 64; i >= 0 && i < N; i += WARP ? 32 : N) {
         xr[2 * (N + 1) + 1 + i] = SC_H_REF;
         xr[5 * (N + 1) + 1 + i] = w * S.lin_b[i];
         xr[11 * (N + 1) + 1 + i] = w;
     }
-    if (tid >= 96 && tid < 108) xr[(tid - 96) * (N + 1)] = sc.st[tid - 96];
-    __syncthreads();
+    if (WARP ? tid < 12 : (tid >= 96 && tid < 108)) { const int c = WARP ? tid : tid - 96; xr[c * (N + 1)] = sc.st[c]; }
+    group_sync();
     if (tid == 0) {
         // remember the first-step contacts for the next tick's touchdown test
         S.prevc[inst] = (uint8_t)(0x80 | (sc.mask[0] & 15));
     }
     if (S.xref_out) {
-        for (int i = tid; i < 12 * (N + 1); i += blockDim.x) S.xref_out[(size_t)inst * 12 * (N + 1) + i] = xr[i];
-        for (int i = tid; i < 260; i += blockDim.x) S.fsteps_out[(size_t)inst * 260 + i] = fs[i];
+        for (int i = tid; i < 12 * (N + 1); i += nthr) S.xref_out[(size_t)inst * 12 * (N + 1) + i] = xr[i];
+        for (int i = tid; i < 260; i += nthr) S.fsteps_out[(size_t)inst * 260 + i] = fs[i];
     }
 }
 
