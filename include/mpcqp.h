@@ -70,7 +70,7 @@ typedef struct mpcqp_params {
     double w_state[12];         /* diagonal state weights    (MPC.py:255-275) */
     double w_force;             /* force weight              (MPC.py:282-284) */
     /* solver */
-    int32_t mode;               /* MPCQP_MODE_* mask, default both */
+    int32_t mode;               /* MPCQP_MODE_* mask, default ACTIVE_SET | ADMM | STAGEWISE */
     int32_t max_sweeps;         /* active-set sweeps before falling back to ADMM */
     int32_t max_iter;           /* ADMM iteration cap */
     int32_t min_iter;           /* ADMM iterations before the first polish attempt */

@@ -63,17 +63,20 @@ cudaError_t configure_kernels() {
 }
 
 template <int N>
-cudaError_t configure_stagewise() {
+cudaError_t configure_stagewise(int* ctas_per_sm) {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(riccati_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RIC_WARPS * sizeof(RicWarp<N>))))) return e;
-    return cudaFuncSetAttribute(riccati_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const int smem = (int)(RIC_PER_CTA * sizeof(RicInst<N>));
+    if ((e = cudaFuncSetAttribute(riccati_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(riccati_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, riccati_kernel<N>, 32 * RIC_WARPS, smem);
 }
 
 template <int N>
-void launch_stagewise(int n_inst, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc, const double* dx,
-                      const double* df, int first, int off) {
-    const int grid = (n_inst + RIC_WARPS - 1) / RIC_WARPS;
-    riccati_kernel<N><<<grid, 32 * RIC_WARPS, RIC_WARPS * sizeof(RicWarp<N>), s>>>(dp, st, sc, dx, df, first, off, n_inst);
+void launch_stagewise(int n_inst, int max_ctas, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
+                      const double* dx, const double* df, double* ws, int first, int off) {
+    int grid = (n_inst + RIC_PER_CTA - 1) / RIC_PER_CTA;
+    if (grid > max_ctas) grid = max_ctas;                      // persistent: one workspace slot per resident half-warp
+    riccati_kernel<N><<<grid, 32 * RIC_WARPS, RIC_PER_CTA * sizeof(RicInst<N>), s>>>(dp, st, sc, dx, df, ws, first, off, n_inst);
 }
 
 template <int N>
@@ -111,15 +114,23 @@ struct mpcqp_handle {
         DevScenario use = sc;
         use.enabled = closed_loop ? 1 : 0;
         if (!admm && (p.mode & MPCQP_MODE_STAGEWISE)) {
-            // active-set stage on the stage-wise factorisation: one warp per robot, grid covers the n robots
-            if (p.n_steps == 16) launch_stagewise<16>(n, s, dp, st, use, dx, df, first, off);
-            else if (p.n_steps == 32) launch_stagewise<32>(n, s, dp, st, use, dx, df, first, off);
-            else launch_stagewise<64>(n, s, dp, st, use, dx, df, first, off);
+            // active-set stage on the stage-wise factorisation: half a warp per robot, persistent grid; every stream
+            // that may run it concurrently has its own gain workspace
+            double* ws = d_ric_ws + (size_t)(s == side[0] ? 1 : (s == side[1] ? 2 : 0)) * ric_ws_doubles;
+            if (p.n_steps == 16) launch_stagewise<16>(n, ric_max_ctas, s, dp, st, use, dx, df, ws, first, off);
+            else if (p.n_steps == 32) launch_stagewise<32>(n, ric_max_ctas, s, dp, st, use, dx, df, ws, first, off);
+            else launch_stagewise<64>(n, ric_max_ctas, s, dp, st, use, dx, df, ws, first, off);
         } else if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         else launch_solve<32>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         ++launches;
     }
     int ctas_per_sm(bool admm) const { return p.n_steps == 16 ? (admm ? 2 : 4) : 1; }
+    // robots of the active-set stage that are resident at once (one wave)
+    int wave(void) const { return (p.mode & MPCQP_MODE_STAGEWISE) ? ric_max_ctas * RIC_PER_CTA : ctas_per_sm(false) * sms; }
+
+    double* d_ric_ws = nullptr;     // stage-wise path: per-stage gains of the resident robots, x3 (main + two side streams)
+    size_t ric_ws_doubles = 0;
+    int ric_max_ctas = 0;
 };
 
 extern "C" {
@@ -153,7 +164,7 @@ void mpcqp_default_params(mpcqp_params* p) {
     for (int i = 0; i < 3; ++i) p->w_state[6 + i] = 2.0 * std::sqrt(p->w_state[i]);
     for (int i = 0; i < 3; ++i) p->w_state[9 + i] = 0.05 * std::sqrt(p->w_state[3 + i]);
     p->w_force = 1e-5;                                      // MPC.py:282-284
-    p->mode = MPCQP_MODE_ACTIVE_SET | MPCQP_MODE_ADMM;
+    p->mode = MPCQP_MODE_ACTIVE_SET | MPCQP_MODE_ADMM | MPCQP_MODE_STAGEWISE;
     p->max_sweeps = 6;
     p->max_iter = 1000;
     p->min_iter = 10;
@@ -177,6 +188,7 @@ int mpcqp_destroy(mpcqp_handle* h) {
     cudaFree(h->d_C2);
     cudaFree(h->d_block);
     cudaFree(h->d_scen);
+    cudaFree(h->d_ric_ws);
     for (int i = 0; i < 2; ++i) {
         if (h->side[i]) cudaStreamDestroy(h->side[i]);
         if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
@@ -299,9 +311,16 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     h->st.fb_list = (int32_t*)(base + o_list); h->st.fb_count = (int32_t*)(base + o_count);
     h->st.sig = (uint8_t*)(base + o_sig);
     CUH(cudaMemset(h->st.sig, SIG_FREE, (size_t)B * 4 * N));
-    if (N == 16) { CUH(configure_kernels<16>()); CUH(configure_stagewise<16>()); }
-    else if (N == 32) { CUH(configure_kernels<32>()); CUH(configure_stagewise<32>()); }
-    else { CUH(configure_stagewise<64>()); }
+    int ric_per_sm = 0;
+    if (N == 16) { CUH(configure_kernels<16>()); CUH(configure_stagewise<16>(&ric_per_sm)); }
+    else if (N == 32) { CUH(configure_kernels<32>()); CUH(configure_stagewise<32>(&ric_per_sm)); }
+    else { CUH(configure_stagewise<64>(&ric_per_sm)); }
+    if (p->mode & MPCQP_MODE_STAGEWISE) {
+        if (ric_per_sm < 1) return bail(fail(MPCQP_ERR_CUDA, "the stage-wise kernel does not fit on this device"));
+        h->ric_max_ctas = ric_per_sm * h->sms;
+        h->ric_ws_doubles = (size_t)h->ric_max_ctas * RIC_PER_CTA * RIC_GAIN * N;
+        CUH(cudaMalloc(&h->d_ric_ws, 3 * h->ric_ws_doubles * sizeof(double)));
+    }
 #undef CUH
     *out = h;
     return MPCQP_OK;
@@ -335,7 +354,7 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
     // Host inputs: the batch is cut into chunks of two full waves (2 x 4 CTAs x #SM instances); chunk
     // c is copied and solved on side stream c & 1, so the H2D copy of one chunk overlaps the solve of
     // the previous one and the two solve kernels fill each other's tails.
-    const int chunk = 2 * h->ctas_per_sm(false) * h->sms;
+    const int chunk = (h->p.mode & MPCQP_MODE_STAGEWISE) ? h->wave() : 2 * h->wave();
     if (location == MPCQP_HOST) {
         dx = h->d_xref; df = h->d_fsteps;
         if (stageA && B > chunk) {
@@ -620,10 +639,10 @@ int mpcqp_get_inputs(mpcqp_handle* h, double* xref, double* fsteps) {
 
 #ifdef MPCQP_PROFILE
 // debug builds only: read (and clear) the per-phase cycle counters
-int mpcqp_debug_profile(unsigned long long* out16) {
+int mpcqp_debug_profile(unsigned long long* out64) {
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16));
-    unsigned long long z[16] = {0};
+    CU(cudaMemcpyFromSymbol(out64, g_prof, sizeof(unsigned long long) * 64));
+    unsigned long long z[64] = {0};
     CU(cudaMemcpyToSymbol(g_prof, z, sizeof(z)));
     return MPCQP_OK;
 }

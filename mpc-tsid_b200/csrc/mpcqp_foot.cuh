@@ -116,6 +116,60 @@ __device__ __forceinline__ void decode_foot(const DevParams& P, const double* xr
     }
 }
 
+// The same decode split in two, for the stage-wise path (it keeps the lever arm and the per-step inertia
+// block instead of the 3x3 product, and forms  A = dt inv(R gI) [r]x  on demand with decode_foot's arithmetic):
+//   contact flag + lever arm r = foothold - xref[0:3, k] of (step k, foot j)            [MPC.py:327, 343, 635-652]
+template <int N>
+__device__ __forceinline__ void decode_lever(const DevParams& P, const double* xr, const double* fs, int k, int j, bool first_tick,
+                                             double r[3], bool& contact, bool& bad) {
+    int row = -1;
+    double cum = 0.0;
+    for (int q = 0; q < 20; ++q) {
+        const double cnt = fs[q * 13];
+        if (cnt == 0.0) break;
+        if (!(cnt > 0.0) || cnt != floor(cnt)) { bad = true; break; }
+        if ((double)k < cum + cnt) { row = q; break; }
+        cum += cnt;
+    }
+    double foot[3] = {0.0, 0.0, 0.0};
+    contact = false;
+    if (row >= 0) {
+        const double x = fs[row * 13 + 1 + 3 * j];
+        contact = !(isnan(x) || x == 0.0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double v = fs[row * 13 + 1 + 3 * j + c];
+            foot[c] = isnan(v) ? 0.0 : v;
+        }
+    }
+    if (first_tick) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) foot[c] = P.footholds[c * 4 + j];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[c] = foot[c] - xr[c * (N + 1) + k];
+}
+//   inv(R_z(yaw) gI) = gI^-1 R'                                                          [MPC.py:330, 339-340]
+__device__ __forceinline__ void step_inertia(const DevParams& P, double yaw, double Ii[9]) {
+    double sn, cs;
+    sincos(yaw, &sn, &cs);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        Ii[3 * a + 0] = P.gIinv[3 * a + 0] * cs - P.gIinv[3 * a + 1] * sn;
+        Ii[3 * a + 1] = P.gIinv[3 * a + 0] * sn + P.gIinv[3 * a + 1] * cs;
+        Ii[3 * a + 2] = P.gIinv[3 * a + 2];
+    }
+}
+//   A = dt Ii [r]x                                                                       [MPC.py:345-346, utils.py:179-185]
+__device__ __forceinline__ void lever_block(const DevParams& P, const double Ii[9], const double r[3], double A[9]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        A[3 * a + 0] = P.dt * (Ii[3 * a + 1] * r[2] - Ii[3 * a + 2] * r[1]);
+        A[3 * a + 1] = P.dt * (Ii[3 * a + 2] * r[0] - Ii[3 * a + 0] * r[2]);
+        A[3 * a + 2] = P.dt * (Ii[3 * a + 0] * r[1] - Ii[3 * a + 1] * r[0]);
+    }
+}
+
 // per-foot results of one sweep
 struct FootSol {
     double f[3];

@@ -15,7 +15,7 @@
 // Optional phase timing (-DMPCQP_PROFILE): per-phase clock64() deltas of thread 0, summed over CTAs
 // into g_prof; read back through mpcqp_debug_profile().  Off in the shipped build.
 #ifdef MPCQP_PROFILE
-__device__ unsigned long long g_prof[16];
+__device__ unsigned long long g_prof[64];     // 0..15 dense path, 16..63 stage-wise path
 #define PROF_T0() long long prof_t_ = clock64()
 #define PROF(slot) do { if (threadIdx.x == 0) { long long n_ = clock64(); atomicAdd(&g_prof[slot], (unsigned long long)(n_ - prof_t_)); prof_t_ = n_; } } while (0)
 #define PROF_COUNT(slot) do { if (threadIdx.x == 0) atomicAdd(&g_prof[slot], 1ull); } while (0)

@@ -1,4 +1,4 @@
-// mpcqp_riccati.cuh -- stage-wise (Riccati) active-set sweeps: one WARP solves one robot's QP.
+// mpcqp_riccati.cuh -- stage-wise (Riccati) active-set sweeps: HALF A WARP solves one robot's QP.
 //
 // Same mathematics as the dense path (condensed QP on the faces a signature selects,
 // KKT guard, warm-started primal-dual active-set sweeps), different factorisation.  Instead of the
@@ -6,35 +6,62 @@
 //     min  sum_s 1/2 (x_s - xref_s)' Q (x_s - xref_s) + 1/2 w_f sum |f|^2
 //     s.t. x_{k+1} = A x_k + [0; u_k + g],  u_k = sum_j Bv_kj f_kj,  f_kj = pf_kj + Z_kj q_kj
 // is solved by dynamic programming over the horizon (O(N), 6x6 blocks only), x = [p (6); v (6)],
-// A = [[I, dt I], [0, I]] (MPC.py:110-111), cost-to-go 1/2 x'P_k x + p_k'x:
+// A = [[I, dt I], [0, I]] (MPC.py:110-111), cost-to-go 1/2 x'P_k x + p_k'x.
 //   backward, stage k = N-1..0, with P+ = P_{k+1}, E_k = sum_j (Bv Z) R^-1 (Bv Z)' (6x6), beta_k = ubar_k + g:
-//       L L' = Pvv+,  G = I + L' E L = M M',  X = L M^-T,  Y = Ppv+ L^-T,  Y2 = Y M^-T,  U = M^-1 L^-1
-//       Pt = (P+^-1 + [0 0; 0 E])^-1:   Ptvv = X X',  Ptpv = Y2 X',  Ptpp = Ppp+ - Y Y' + Y2 Y2'
-//       Gamma = (I + E Pvv+)^-1 E,  Gamma Pvp = (Y L^-1 - Y2 U)',  Gamma Pvv = I - U' X'
+//       L L' = Pvv+,   G = I + L' E_k L = M M',   Gamma = (I + E_k Pvv+)^-1 E_k = L^-T (I - G^-1) L^-1
+//       every row rho of [Ppv+; Pvv+; pv+'] (13 rows, one per lane) goes through the same four products
+//           y = rho L^-T,  v = y G^-1 = (y M^-T) M^-1,  rho (I - Gamma Pvv+) = v L',  rho Gamma = (y - v) L^-1
+//       which yields Pt = (P+^-1 + [0 0; 0 E])^-1 (its [:, v] block), the closed-loop gain [Ppv; Pvv] Gamma and
+//       Gamma pv; the [:, p] block follows from  Pt[:, p] = P+[:, p] - (rho Gamma) Pvp+.
 //       P_k = Q + A' Pt A,   p_k = -Q xref_k + A'(Pt[:,v] beta_k + pt)
-//       closed loop  w_k = -(Kx x_k + k0)   stored per stage (78 doubles)
-//   forward: x_{k+1} = A x_k + [0; beta_k + w_k];  costates lam_s = Q (x_s - xref_s) + A' lam_{s+1};
+//   forward:  z = A x_k + [0; beta_k],  w = -([Ppv;Pvv] Gamma)' z - Gamma pv,  x_{k+1} = z + [0; w]
+//   costates  lam_s = Q (x_s - xref_s) + A' lam_{s+1};
 //   per foot: h = Bv' lam^v_{k+1},  q = -R^-1 Z' h,  f = pf + Z q,  grad = w_f f + h   (= H f + g of the
 //   condensed problem), then the same KKT guard as the dense path (mpcqp_foot.cuh).
-// Everything a stage needs lives in the warp's private shared-memory block; the two 6x6 Cholesky
-// factorisations per stage run redundantly in the registers of every lane (no shuffle or memory hop
-// on the pivot chain), their inverses come out of the same loop (forward substitution of the unit
-// vectors in the shadow of the pivots), all other 6x6 products are one output per lane.
+// Mapping to the machine.  The path is bound by the latency of the two 6x6 pivot chains per stage, so the
+// design maximises the number of robots in flight per SM: 16 lanes per robot (two robots per warp, every
+// collective on the half-warp's own mask), 12 KB of shared memory per robot, the per-stage gains (the only
+// O(N) state of the recursion that must survive until the forward pass) in an L2-resident workspace.
+// The two Cholesky factors of a stage and their inverses are computed redundantly in the REGISTERS of every
+// lane (static indices, no shuffle or memory hop on the pivot chain, a 5-instruction reciprocal square root;
+// the inverse rows are formed in the shadow of the pivots), so every product above is "one row in registers
+// times a register-resident triangular matrix" and a stage needs three half-warp barriers.
 // Replaces MPC.update_ML / update_NK / call_solver / retrieve_result (MPC.py:316-458) like the dense path.
 #pragma once
 #include "mpcqp_device.cuh"
 #include "mpcqp_foot.cuh"
 #include "mpcqp_scenario.cuh"
 
+// Optional phase timing (-DMPCQP_PROFILE): clock64() deltas of lane 0 summed into g_prof[16..] (mpcqp_kernels.cu)
+#ifdef MPCQP_PROFILE
+#define RPROF_T0() long long rprof_t_ = clock64()
+#define RPROF(slot) do { if ((threadIdx.x & 31) == 0) { long long n_ = clock64(); atomicAdd(&g_prof[16 + (slot)], (unsigned long long)(n_ - rprof_t_)); rprof_t_ = n_; } } while (0)
+#define RPROF_COUNT(slot) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_prof[16 + (slot)], 1ull); } while (0)
+#else
+#define RPROF_T0() do {} while (0)
+#define RPROF(slot) do {} while (0)
+#define RPROF_COUNT(slot) do {} while (0)
+#endif
+
 namespace mpcqp {
 
-constexpr int RIC_SLOT = 78;        // doubles kept per stage for the forward pass: Kx (6 x 12), k0 (6)
-constexpr int RIC_WARPS = 2;        // robots (= warps) per CTA
+constexpr int RIC_GAIN = 84;        // workspace doubles per stage: 6 impulse components x 14 (13 coefficients + pad)
+#ifndef MPCQP_RIC_WARPS
+#define MPCQP_RIC_WARPS 1
+#endif
+constexpr int RIC_WARPS = MPCQP_RIC_WARPS;      // warps per CTA
+constexpr int RIC_PER_CTA = 2 * RIC_WARPS;      // robots per CTA
+constexpr int RIC_DEPTH = 4;        // stages of gains the forward pass keeps in flight from the workspace
+
+// cost-to-go of one stage, row major 6x6 blocks (double-buffered: stage k reads one, writes the other)
+struct alignas(16) RicCost {
+    double Ppp[36], Ppv[36], Pvv[36], pp[6], pv[6];
+};
 
 template <int N>
-struct alignas(16) RicWarp {
+struct alignas(16) RicInst {
     static constexpr int NF = 4 * N;
-    static constexpr int ROUNDS = NF / 32;                     // feet per lane
+    static constexpr int ROUNDS = NF / 16;                     // feet per lane
     static constexpr int AW = (20 * N + 31) / 32, CW = (4 * N + 31) / 32;
     double xr[12 * (N + 1)];            // xref of this robot
     union {
@@ -42,97 +69,150 @@ struct alignas(16) RicWarp {
         double E[21 * N];               // per sweep: packed lower triangles of the 6x6 blocks E_k; once the
                                         // backward pass is done the same bytes hold the sweep's forces (3 x NF)
     };
-    double A[9 * NF];                   // per foot-step: dt inv(R gI) [r]x, struct of arrays
-    double beta[6 * N];                 // ubar_k + g;  in finish(): the impulses of the final forces
-    double slot[RIC_SLOT * N];          // per stage Kx, k0; after the forward pass [x_{k+1} (12), lam^v_{k+1} (6), ..]
-    double Ppp[36], Ppv[36], Pvv[36];   // cost-to-go of the stage being eliminated
-    double L[36], Li[36], Mi[36], T[36], Y[36], G[36], X[36], Y2[36], U[36], Tpp[36], Tpv[36], Tvv[36];
-    double pp[6], pv[6], av[6], cv[6], tp[6], tv[6], gam[6];
+    double lev[3 * NF];                 // lever arms foothold - xref[0:3, k], struct of arrays
+    double Ii[9 * N];                   // inv(R_z(yaw_k) gI) per step, row major
+    double beta[6 * N];                 // ubar_k + g
+    union {
+        struct { double xst[12 * N]; double lam[6 * N]; };    // states x_1..x_N of the forward pass, velocity costates
+        ScenarioSmem sc;                // planner scratch of the device-resident closed loop (dead after the inputs exist)
+    };
+    RicCost cost[2];
+    double T[36];                       // E_k L, row major
+    double hp[6];
+    double xnext[12];
     unsigned long long hist[16];        // hashes of the signatures already tried
     unsigned long long mbar;
     unsigned int amask[AW + CW];
-    ScenarioSmem sc;
     static_assert(21 * N >= 260 && 21 * N >= 12 * N, "union sizing");
+    static_assert(18 * N * 8 >= sizeof(ScenarioSmem), "union sizing");
 };
 
-__device__ __forceinline__ double dot_rr(const double* __restrict__ a, const double* __restrict__ b) {
-    double s0 = a[0] * b[0], s1 = a[1] * b[1];
-    s0 = fma(a[2], b[2], s0); s1 = fma(a[3], b[3], s1);
-    s0 = fma(a[4], b[4], s0); s1 = fma(a[5], b[5], s1);
-    return s0 + s1;
-}
-__device__ __forceinline__ double dot_rc(const double* __restrict__ a, const double* __restrict__ b) {   // b strided by 6
-    double s0 = a[0] * b[0], s1 = a[1] * b[6];
-    s0 = fma(a[2], b[12], s0); s1 = fma(a[3], b[18], s1);
-    s0 = fma(a[4], b[24], s0); s1 = fma(a[5], b[30], s1);
-    return s0 + s1;
-}
-__device__ __forceinline__ double dot_cc(const double* __restrict__ a, const double* __restrict__ b) {   // both strided by 6
-    double s0 = a[0] * b[0], s1 = a[6] * b[6];
-    s0 = fma(a[12], b[12], s0); s1 = fma(a[18], b[18], s1);
-    s0 = fma(a[24], b[24], s0); s1 = fma(a[30], b[30], s1);
-    return s0 + s1;
+#define RIC_TI(r, c) ((r) * ((r) + 1) / 2 + (c))
+
+// The two robots of a warp run CONVERGED: one instruction stream, full-mask collectives, shuffles of width 16.
+constexpr unsigned RIC_FULL = 0xffffffffu;
+__device__ __forceinline__ double hshfl_d(double v, int src) { return __shfl_sync(RIC_FULL, v, src, 16); }
+__device__ __forceinline__ double hshfl_xor_d(double v, int x) { return __shfl_xor_sync(RIC_FULL, v, x, 16); }
+// true on every lane of a half-warp iff the predicate holds on all / any of its 16 lanes
+__device__ __forceinline__ bool half_all(bool p, int sub) { return ((__ballot_sync(RIC_FULL, p) >> (16 * sub)) & 0xFFFFu) == 0xFFFFu; }
+__device__ __forceinline__ bool half_any(bool p, int sub) { return ((__ballot_sync(RIC_FULL, p) >> (16 * sub)) & 0xFFFFu) != 0u; }
+
+// 1 / sqrt(d): hardware seed (relative error ~2^-21) and one third-order correction, five dependent instructions.
+// d <= 0 or non-finite gives a non-finite result; the caller tests d separately.
+__device__ __forceinline__ double rsqrt_fast(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = d * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double ye = y * e;
+    return fma(ye, p, y);
 }
 
-// Cholesky S = L L' of a 6x6 SPD matrix in shared memory (row major, both triangles valid), redundantly in
-// the registers of every lane, fused with the inversion of L: lane c < 6 carries the unit vector e_c
-// through the forward substitution as the pivots appear, so column c of inv(L) is complete one
-// multiply after the last pivot.  Lout (if given) receives L (lower triangle only; the strictly upper part of
-// the buffer is never written and stays zero), Liout receives inv(L) (full 6x6, zeros included).
-__device__ __forceinline__ bool chol6_inv(const double* __restrict__ S, double* __restrict__ Lout, double* __restrict__ Liout, int lane) {
-    double a[21];
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) a[r * (r + 1) / 2 + c] = S[r * 6 + c];
-    const int cc = lane < 6 ? lane : 0;
-    double y[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) y[i] = (i == cc) ? 1.0 : 0.0;
+// Cholesky a = L L' of a 6x6 SPD matrix held as packed lower triangle in registers, in place, fused with the
+// inversion of L (li = inv(L), packed lower triangle).  Row j of the inverse needs only rows < j of it and row j
+// of L up to a final scaling by 1 / l_jj, so its sums are formed before the pivot is known: the inverse adds one
+// multiply to the pivot chain.  All indices are static.
+__device__ __forceinline__ bool chol6_regs(double (&a)[21], double (&li)[21]) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-        const double d = a[j * (j + 1) / 2 + j];
-        ok = ok && (d > 0.0);
-        const double inv = rsqrt(d);
+        double s[6];
 #pragma unroll
-        for (int i = j + 1; i < 6; ++i) a[i * (i + 1) / 2 + j] *= inv;
+        for (int c = 0; c < j; ++c) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = c; k < j; ++k) t = fma(a[RIC_TI(j, k)], li[RIC_TI(k, c)], t);
+            s[c] = t;
+        }
+        const double d = a[RIC_TI(j, j)];
+        ok = ok && (d > 1e-300) && (d < 1e300);
+        const double inv = rsqrt_fast(d);
+        a[RIC_TI(j, j)] = d * inv;
+        li[RIC_TI(j, j)] = inv;
+#pragma unroll
+        for (int c = 0; c < j; ++c) li[RIC_TI(j, c)] = -inv * s[c];
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) a[RIC_TI(i, j)] *= inv;
 #pragma unroll
         for (int i = j + 1; i < 6; ++i)
 #pragma unroll
-            for (int c = j + 1; c <= i; ++c)
-                a[i * (i + 1) / 2 + c] = fma(-a[i * (i + 1) / 2 + j], a[c * (c + 1) / 2 + j], a[i * (i + 1) / 2 + c]);
-        const double xj = y[j] * inv;
-#pragma unroll
-        for (int i = j + 1; i < 6; ++i) y[i] = fma(-a[i * (i + 1) / 2 + j], xj, y[i]);
-        if (Lout != nullptr && lane == j) {
-            Lout[j * 6 + j] = d * inv;
-#pragma unroll
-            for (int i = j + 1; i < 6; ++i) Lout[i * 6 + j] = a[i * (i + 1) / 2 + j];
-        }
-        if (lane < 6) Liout[j * 6 + cc] = xj;
+            for (int c = j + 1; c <= i; ++c) a[RIC_TI(i, c)] = fma(-a[RIC_TI(i, j)], a[RIC_TI(c, j)], a[RIC_TI(i, c)]);
     }
     return ok;
 }
 
-// One equality-constrained solve on the faces `sg` selects + KKT guard.  All 32 lanes of the warp call it.
-// Returns (warp-uniform) 1 if every foot passes the guard, 0 if not, -1 if a pivot was not positive.
-// On return sm.E holds the forces (3 per foot, foot-major), sm.slot[k][12..17] the velocity costates.
+// out = in * m   (m lower triangular, packed):  out[c] = sum_{r >= c} in[r] m[r][c]
+__device__ __forceinline__ void row_mul(double (&out)[6], const double (&in)[6], const double (&m)[21]) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        double t = in[c] * m[RIC_TI(c, c)];
+#pragma unroll
+        for (int r = c + 1; r < 6; ++r) t = fma(in[r], m[RIC_TI(r, c)], t);
+        out[c] = t;
+    }
+}
+// out = in * m'  (m lower triangular, packed):  out[c] = sum_{r <= c} in[r] m[c][r]
+__device__ __forceinline__ void row_mulT(double (&out)[6], const double (&in)[6], const double (&m)[21]) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        double t = in[0] * m[RIC_TI(c, 0)];
+#pragma unroll
+        for (int r = 1; r <= c; ++r) t = fma(in[r], m[RIC_TI(c, r)], t);
+        out[c] = t;
+    }
+}
+__device__ __forceinline__ void load_row6(double (&out)[6], const double* p) {       // p 16-byte aligned
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2),
+                  c = *reinterpret_cast<const double2*>(p + 4);
+    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y; out[4] = c.x; out[5] = c.y;
+}
+__device__ __forceinline__ void store_row6(double* p, const double (&v)[6]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+    *reinterpret_cast<double2*>(p + 4) = make_double2(v[4], v[5]);
+}
+// the 3x3 angular block of foot-step t: dt inv(R gI) [r]x from the stored lever arm and inertia block
 template <int N>
-__device__ int ric_sweep(const DevParams& P, RicWarp<N>& sm, unsigned conbits, const uint8_t (&sg)[RicWarp<N>::ROUNDS],
-                         uint8_t (&nsg)[RicWarp<N>::ROUNDS], int lane) {
-    using S = RicWarp<N>;
-    constexpr int NF = S::NF, ROUNDS = S::ROUNDS;
+__device__ __forceinline__ void foot_A(const DevParams& P, const RicInst<N>& sm, int t, double A[9]) {
+    constexpr int NF = 4 * N;
+    const double r[3] = {sm.lev[t], sm.lev[NF + t], sm.lev[2 * NF + t]};
+    double Ii[9];
+    const double* src = sm.Ii + 9 * (t >> 2);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Ii[i] = src[i];
+    lever_block(P, Ii, r, A);
+}
+// sum a 6-vector over the four feet of a step (lanes 4k..4k+3 of the half-warp); lane j == 0 stores it
+__device__ __forceinline__ void hstep_sum_store(double (&v)[6], double* dst, int j) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { v[c] += hshfl_xor_d(v[c], 1); }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { v[c] += hshfl_xor_d(v[c], 2); }
+    if (j == 0) store_row6(dst, v);
+}
+
+// One equality-constrained solve on the faces `sg` selects + KKT guard.  The 16 lanes of the robot call it.
+// Returns (uniform over the half-warp) 1 if every foot passes the guard, 0 if not, -1 if a pivot was not positive.
+// Both halves of the warp must call it together (full-mask collectives inside).
+// On return sm.E holds the forces (3 per foot, foot-major), sm.xst the states, sm.lam the velocity costates.
+template <int N>
+__device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl, unsigned conbits,
+                         const uint8_t (&sg)[RicInst<N>::ROUNDS], uint8_t (&nsg)[RicInst<N>::ROUNDS]) {
+    using S = RicInst<N>;
+    constexpr int ROUNDS = S::ROUNDS;
     const double lin = P.dt / P.mass, dt = P.dt;
+    RPROF_T0();
+    RPROF_COUNT(0);
 
     // ---- E_k and beta_k, feet in parallel (4 lanes = the feet of one step)
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
-        const int t = lane + 32 * r, k = t >> 2, j = t & 3;
+        const int t = hl + 16 * r, k = t >> 2, j = t & 3;
         Face fc;
         make_face(P, (conbits >> r) & 1u, sg[r], fc);
         double A[9];
-        load_A<NF>(sm.A, t, A);
+        foot_A<N>(P, sm, t, A);
         double b[3][6], d[3];
         const double zx = fc.zx ? 1.0 : 0.0, zy = fc.zy ? 1.0 : 0.0, zz = fc.zz ? 1.0 : 0.0;
         b[0][0] = lin * zx; b[0][1] = 0.0; b[0][2] = 0.0;
@@ -151,194 +231,225 @@ __device__ int ric_sweep(const DevParams& P, RicWarp<N>& sm, unsigned conbits, c
 #pragma unroll
             for (int c = 0; c <= a; ++c, ++e) {
                 double v = d[0] * b[0][a] * b[0][c] + d[1] * b[1][a] * b[1][c] + d[2] * b[2][a] * b[2][c];
-                v += shfl_xor_d(v, 1);
-                v += shfl_xor_d(v, 2);
+                v += hshfl_xor_d(v, 1);
+                v += hshfl_xor_d(v, 2);
                 if ((e & 3) == j) sm.E[21 * k + e] = v;
             }
         double ub[6];
         bv_apply(A, lin, fc.pf, ub);
         ub[2] -= (j == 0) ? P.gravity * dt : 0.0;             // g: only the z velocity, MPC.py:200-201
-        step_sum_store(ub, sm.beta + 6 * k, j);
+        hstep_sum_store(ub, sm.beta + 6 * k, j);
     }
     // ---- terminal cost-to-go: P_N = Q, p_N = -Q xref_N
-    for (int i = lane; i < 36; i += 32) {
-        const int rr = i / 6, dg = (i - 6 * rr) == rr;
-        sm.Ppp[i] = dg ? P.wp[rr] : 0.0;
-        sm.Pvv[i] = dg ? P.wv[rr] : 0.0;
-        sm.Ppv[i] = 0.0;
-    }
-    if (lane < 6) {
-        sm.pp[lane] = -P.wp[lane] * sm.xr[lane * (N + 1) + N];
-        sm.pv[lane] = -P.wv[lane] * sm.xr[(6 + lane) * (N + 1) + N];
+    {
+        RicCost& c0 = sm.cost[(N - 1) & 1];
+        for (int i = hl; i < 36; i += 16) {
+            const int rr = i / 6, dg = (i - 6 * rr) == rr;
+            c0.Ppp[i] = dg ? P.wp[rr] : 0.0;
+            c0.Pvv[i] = dg ? P.wv[rr] : 0.0;
+            c0.Ppv[i] = 0.0;
+        }
+        if (hl < 6) {
+            c0.pp[hl] = -P.wp[hl] * sm.xr[hl * (N + 1) + N];
+            c0.pv[hl] = -P.wv[hl] * sm.xr[(6 + hl) * (N + 1) + N];
+        }
     }
     __syncwarp();
+    RPROF(1);
 
-    // lane -> output maps of the 6x6 products: output `lane` (i0, c0), outputs 32..35 on lanes 0..3 (row 5),
-    // lower-triangle output (si, sj) on lanes 0..20, vector component vv on lanes 26..31
-    const int i0 = lane / 6, c0 = lane - 6 * i0;
-    const bool has1 = lane < 4;
-    const int c1 = has1 ? 2 + lane : 5;
-    const int si = (lane >= 15) ? 5 : (lane >= 10) ? 4 : (lane >= 6) ? 3 : (lane >= 3) ? 2 : (lane >= 1) ? 1 : 0;
-    const bool hsym = lane < 21;
-    const int sj = hsym ? lane - si * (si + 1) / 2 : 0;
-    const int sii = hsym ? si : 0;
-    const bool hvec = lane >= 26;
-    const int vv = hvec ? lane - 26 : 0;
-    int ie0[6];
+    // ---- lane roles in a stage: rid 0..5 rows of Ppv, 6..11 rows of Pvv, 12 pv' (13..15 repeat 12);
+    //      lanes 0..5 additionally own row hl of T = E_k L
+    const int rid = (hl < 13) ? hl : 12;
+    const bool prow = rid < 6, vrow = rid >= 6 && rid < 12;
+    const int ri = prow ? rid : (vrow ? rid - 6 : 0);          // row index inside its 6x6 block
+    int ie[6];
 #pragma unroll
-    for (int q = 0; q < 6; ++q) ie0[q] = (i0 >= q) ? i0 * (i0 + 1) / 2 + q : q * (q + 1) / 2 + i0;
+    for (int q = 0; q < 6; ++q) ie[q] = (ri >= q) ? ri * (ri + 1) / 2 + q : q * (q + 1) / 2 + ri;
 
     bool spd = true;
     for (int k = N - 1; k >= 0; --k) {
+        const RicCost& cin = sm.cost[k & 1];
+        RicCost& cout = sm.cost[(k & 1) ^ 1];
         const double* Ek = sm.E + 21 * k;
-        const double* bk = sm.beta + 6 * k;
-        // (1) L L' = Pvv, Li = inv(L)
-        spd = chol6_inv(sm.Pvv, sm.L, sm.Li, lane) && spd;
-        __syncwarp();
-        // (2) T = E L,  Y = Ppv Li',  av = Li pv
-        {
-            double t0 = 0.0, t1 = 0.0;
+        // (1) L L' = Pvv, li = inv(L): every lane, in registers
+        double L[21], Li[21];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                t0 = fma(Ek[ie0[q]], sm.L[q * 6 + c0], t0);
-                t1 = fma(Ek[15 + q], sm.L[q * 6 + c1], t1);
-            }
-            const double y0 = dot_rr(sm.Ppv + 6 * i0, sm.Li + 6 * c0);
-            const double y1 = dot_rr(sm.Ppv + 30, sm.Li + 6 * c1);
-            const double a_ = dot_rr(sm.Li + 6 * vv, sm.pv);
-            sm.T[lane] = t0; sm.Y[lane] = y0;
-            if (has1) { sm.T[32 + lane] = t1; sm.Y[32 + lane] = y1; }
-            if (hvec) sm.av[vv] = a_;
-        }
-        __syncwarp();
-        // (3) G = I + L' T
-        {
-            const double g_ = dot_cc(sm.L + sii, sm.T + sj) + ((sii == sj) ? 1.0 : 0.0);
-            if (hsym) { sm.G[sii * 6 + sj] = g_; sm.G[sj * 6 + sii] = g_; }
-        }
-        __syncwarp();
-        // (4) M M' = G, Mi = inv(M)
-        spd = chol6_inv(sm.G, nullptr, sm.Mi, lane) && spd;
-        __syncwarp();
-        // (5) X = L Mi',  Y2 = Y Mi',  U = Mi Li,  cv = Mi av
-        {
-            const double x0 = dot_rr(sm.L + 6 * i0, sm.Mi + 6 * c0), x1 = dot_rr(sm.L + 30, sm.Mi + 6 * c1);
-            const double y0 = dot_rr(sm.Y + 6 * i0, sm.Mi + 6 * c0), y1 = dot_rr(sm.Y + 30, sm.Mi + 6 * c1);
-            const double u0 = dot_rc(sm.Mi + 6 * i0, sm.Li + c0), u1 = dot_rc(sm.Mi + 30, sm.Li + c1);
-            const double c_ = dot_rr(sm.Mi + 6 * vv, sm.av);
-            sm.X[lane] = x0; sm.Y2[lane] = y0; sm.U[lane] = u0;
-            if (has1) { sm.X[32 + lane] = x1; sm.Y2[32 + lane] = y1; sm.U[32 + lane] = u1; }
-            if (hvec) sm.cv[vv] = c_;
-        }
-        __syncwarp();
-        // (6) Pt blocks, pt, and the pieces of the closed-loop gain:  KpT = Ppv Gamma (-> sm.G),  G2 = Gamma Pvv (-> sm.T)
-        {
-            const double tvv = dot_rr(sm.X + 6 * sii, sm.X + 6 * sj);
-            const double tpp = sm.Ppp[sii * 6 + sj] - dot_rr(sm.Y + 6 * sii, sm.Y + 6 * sj) + dot_rr(sm.Y2 + 6 * sii, sm.Y2 + 6 * sj);
-            const double tpv0 = dot_rr(sm.Y2 + 6 * i0, sm.X + 6 * c0), tpv1 = dot_rr(sm.Y2 + 30, sm.X + 6 * c1);
-            const double kp0 = dot_rc(sm.Y + 6 * i0, sm.Li + c0) - dot_rc(sm.Y2 + 6 * i0, sm.U + c0);
-            const double kp1 = dot_rc(sm.Y + 30, sm.Li + c1) - dot_rc(sm.Y2 + 30, sm.U + c1);
-            const double g20 = ((i0 == c0) ? 1.0 : 0.0) - dot_rc(sm.X + 6 * c0, sm.U + i0);
-            const double g21 = ((5 == c1) ? 1.0 : 0.0) - dot_rc(sm.X + 6 * c1, sm.U + 5);
-            const double tv_ = dot_rr(sm.X + 6 * vv, sm.cv);
-            const double tp_ = sm.pp[vv] - dot_rr(sm.Y + 6 * vv, sm.av) + dot_rr(sm.Y2 + 6 * vv, sm.cv);
-            const double gm_ = dot_rc(sm.av, sm.Li + vv) - dot_rc(sm.cv, sm.U + vv);
-            if (hsym) {
-                sm.Tvv[sii * 6 + sj] = tvv; sm.Tvv[sj * 6 + sii] = tvv;
-                sm.Tpp[sii * 6 + sj] = tpp; sm.Tpp[sj * 6 + sii] = tpp;
-            }
-            sm.Tpv[lane] = tpv0; sm.G[lane] = kp0; sm.T[lane] = g20;
-            if (has1) { sm.Tpv[32 + lane] = tpv1; sm.G[32 + lane] = kp1; sm.T[32 + lane] = g21; }
-            if (hvec) { sm.tv[vv] = tv_; sm.tp[vv] = tp_; sm.gam[vv] = gm_; }
-        }
-        __syncwarp();
-        // (7) gain of this stage into its slot; cost-to-go of stage k (not needed for k = 0)
-        {
-            double* slot = sm.slot + RIC_SLOT * k;
+        for (int r = 0; r < 6; ++r)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int e = lane + 32 * q;
-                if (e < 72) {
-                    const int o = e / 12, i = e - 12 * o;
-                    slot[e] = (i < 6) ? sm.G[i * 6 + o] : fma(dt, sm.G[(i - 6) * 6 + o], sm.T[o * 6 + i - 6]);
-                }
-            }
-            if (hvec) slot[72 + vv] = dot_rr(sm.T + 6 * vv, bk) + sm.gam[vv];
-            if (k > 0) {
-                const double tpp = sm.Tpp[sii * 6 + sj];
-                const double npp_ = tpp + ((sii == sj) ? P.wp[sii] : 0.0);
-                const double nvv_ = dt * dt * tpp + dt * (sm.Tpv[sii * 6 + sj] + sm.Tpv[sj * 6 + sii]) + sm.Tvv[sii * 6 + sj]
-                                    + ((sii == sj) ? P.wv[sii] : 0.0);
-                const double npv0 = fma(dt, sm.Tpp[lane], sm.Tpv[lane]);
-                const double npv1 = fma(dt, sm.Tpp[30 + c1], sm.Tpv[30 + c1]);
-                const double hp = dot_rr(sm.Tpv + 6 * vv, bk) + sm.tp[vv];
-                const double hv = dot_rr(sm.Tvv + 6 * vv, bk) + sm.tv[vv];
-                if (hsym) {
-                    sm.Ppp[sii * 6 + sj] = npp_; sm.Ppp[sj * 6 + sii] = npp_;
-                    sm.Pvv[sii * 6 + sj] = nvv_; sm.Pvv[sj * 6 + sii] = nvv_;
-                }
-                sm.Ppv[lane] = npv0;
-                if (has1) sm.Ppv[32 + lane] = npv1;
-                if (hvec) {
-                    sm.pp[vv] = hp - P.wp[vv] * sm.xr[vv * (N + 1) + k];
-                    sm.pv[vv] = fma(dt, hp, hv) - P.wv[vv] * sm.xr[(6 + vv) * (N + 1) + k];
-                }
-            }
-        }
+            for (int c = 0; c <= r; ++c) L[RIC_TI(r, c)] = cin.Pvv[r * 6 + c];
+        double rho[6], er[6];
+        load_row6(rho, prow ? cin.Ppv + 6 * ri : (vrow ? cin.Pvv + 6 * ri : cin.pv));
+#pragma unroll
+        for (int q = 0; q < 6; ++q) er[q] = Ek[ie[q]];
+        spd = chol6_regs(L, Li) && spd;
+        RPROF(2);
+        // (2) row ri of T = E L -> shared memory;  y = rho L^-T
+        double tr[6], y[6];
+        row_mul(tr, er, L);
+        if (prow) store_row6(sm.T + 6 * ri, tr);
+        row_mulT(y, rho, Li);
         __syncwarp();
+        RPROF(3);
+        // (3) G = I + L' T (every lane), M M' = G, mi = inv(M)
+        double G[21], Mi[21];
+        {
+            double Tl[21];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) Tl[RIC_TI(r, c)] = sm.T[r * 6 + c];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = 0; c <= a; ++c) {
+                    double t = (a == c) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int r = a; r < 6; ++r) t = fma(L[RIC_TI(r, a)], Tl[RIC_TI(r, c)], t);
+                    G[RIC_TI(a, c)] = t;
+                }
+        }
+        RPROF(4);
+        spd = chol6_regs(G, Mi) && spd;
+        RPROF(5);
+        // (4) v = y G^-1,  t = v L' (row of Pt[:, v]),  kr = (y - v) L^-1 (row of [Ppv; Pvv; pv'] Gamma)
+        double v[6], kr[6];
+        {
+            double y2[6], dr[6];
+            row_mulT(y2, y, Mi);
+            row_mul(v, y2, Mi);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) dr[q] = y[q] - v[q];
+            row_mulT(tr, v, L);
+            row_mul(kr, dr, Li);
+        }
+        if (hl < 13) {
+            double* g = ws + (size_t)RIC_GAIN * k + rid;                // gain of impulse component o: coefficient rid
+#pragma unroll
+            for (int o = 0; o < 6; ++o) g[14 * o] = kr[o];
+        }
+        RPROF(6);
+        if (k > 0) {
+            // (5) wr = row of Pt[:, p] = P+[:, p] row - kr Pvp;  wvv = component of pt
+            double wr[6], wvv;
+            {
+                const double* base = prow ? cin.Ppp + 6 * ri : cin.Ppv + ri;
+                const int stride = prow ? 1 : 6;
+                double pvv[6];
+                load_row6(pvv, cin.pv);
+                wvv = prow ? cin.pp[ri] : cin.pv[ri];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) wvv = fma(-kr[q], pvv[q], wvv);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    double pr[6];
+                    load_row6(pr, cin.Ppv + 6 * c);
+                    double t = base[c * stride];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) t = fma(-kr[q], pr[q], t);
+                    wr[c] = t;
+                }
+            }
+            double bk[6];
+            load_row6(bk, sm.beta + 6 * k);
+            double hb = wvv;                                   // Pt[:, v] beta + pt, this row's component
+#pragma unroll
+            for (int q = 0; q < 6; ++q) hb = fma(tr[q], bk[q], hb);
+            RPROF(7);
+            // (6) rows of P_k: lanes 0..5 write Ppp, Ppv, pp; then lanes 6..11 write Pvv, pv
+            if (prow) {
+                double npp[6], npv[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    npp[c] = wr[c] + ((c == ri) ? P.wp[ri] : 0.0);
+                    npv[c] = fma(dt, wr[c], tr[c]);
+                }
+                store_row6(cout.Ppp + 6 * ri, npp);
+                store_row6(cout.Ppv + 6 * ri, npv);
+                sm.hp[ri] = hb;
+                cout.pp[ri] = hb - P.wp[ri] * sm.xr[ri * (N + 1) + k];
+            }
+            __syncwarp();
+            if (vrow) {
+                double npv[6], nvv[6];
+                load_row6(npv, cout.Ppv + 6 * ri);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) nvv[c] = fma(dt, npv[c] + wr[c], tr[c]) + ((c == ri) ? P.wv[ri] : 0.0);
+                store_row6(cout.Pvv + 6 * ri, nvv);
+                cout.pv[ri] = fma(dt, sm.hp[ri], hb) - P.wv[ri] * sm.xr[(6 + ri) * (N + 1) + k];
+            }
+            __syncwarp();
+            RPROF(8);
+        }
     }
-    if (!__all_sync(0xffffffffu, spd)) return -1;
+    __syncwarp();                                            // the gains in the workspace are visible to the half-warp
+    const bool spd_all = half_all(spd, sub);                   // uniform over the half-warp; a robot whose pivots failed
+                                                               // runs on with harmless garbage so that the warp stays converged
 
-    // ---- forward pass: x replicated in the registers of every lane
+    // ---- forward pass: x replicated in the registers of every lane; lane o (mod 6) forms impulse component o from
+    //      its 13 gain coefficients, fetched RIC_DEPTH stages ahead from the (L2-resident) workspace
     {
         double x[12];
 #pragma unroll
         for (int c = 0; c < 12; ++c) x[c] = sm.xr[c * (N + 1)];
-        const int o = lane % 6;
-        for (int k = 0; k < N; ++k) {
-            double* slot = sm.slot + RIC_SLOT * k;
-            const double* row = slot + 12 * o;
-            double a0 = slot[72 + o], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const int o = hl % 6;
+        const double* gcol = ws + 14 * o;
+        double2 g[RIC_DEPTH][7];
 #pragma unroll
-            for (int i = 0; i < 12; i += 4) {
-                a0 = fma(row[i], x[i], a0); a1 = fma(row[i + 1], x[i + 1], a1);
-                a2 = fma(row[i + 2], x[i + 2], a2); a3 = fma(row[i + 3], x[i + 3], a3);
-            }
-            const double w = -((a0 + a1) + (a2 + a3));
-            const double* bk = sm.beta + 6 * k;
+        for (int d = 0; d < RIC_DEPTH; ++d)
 #pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                const double wc = shfl_d(w, c);
-                const double xp = fma(dt, x[6 + c], x[c]);
-                x[6 + c] = x[6 + c] + bk[c] + wc;
-                x[c] = xp;
-            }
-            __syncwarp();                       // everyone has read this stage's gain
-            if (lane == 0) {
+            for (int i = 0; i < 7; ++i) g[d][i] = __ldcg(reinterpret_cast<const double2*>(gcol + (size_t)RIC_GAIN * d) + i);
+        for (int k0 = 0; k0 < N; k0 += RIC_DEPTH) {
 #pragma unroll
-                for (int c = 0; c < 12; c += 2) *reinterpret_cast<double2*>(slot + c) = make_double2(x[c], x[c + 1]);
+            for (int d = 0; d < RIC_DEPTH; ++d) {
+                const int k = k0 + d;
+                double bk[6], z[12];
+                load_row6(bk, sm.beta + 6 * k);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { z[c] = fma(dt, x[6 + c], x[c]); z[6 + c] = x[6 + c] + bk[c]; }
+                double a0 = g[d][6].x, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 6; i += 2) {
+                    a0 = fma(g[d][i].x, z[2 * i], a0); a1 = fma(g[d][i].y, z[2 * i + 1], a1);
+                    a2 = fma(g[d][i + 1].x, z[2 * i + 2], a2); a3 = fma(g[d][i + 1].y, z[2 * i + 3], a3);
+                }
+                const double w = -((a0 + a1) + (a2 + a3));
+                if (k + RIC_DEPTH < N) {
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) g[d][i] = __ldcg(reinterpret_cast<const double2*>(gcol + (size_t)RIC_GAIN * (k + RIC_DEPTH)) + i);
+                }
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { x[c] = z[c]; x[6 + c] = z[6 + c] + hshfl_d(w, c); }
+                if (hl == 0) {
+                    double* xs = sm.xst + 12 * k;
+#pragma unroll
+                    for (int c = 0; c < 12; c += 2) *reinterpret_cast<double2*>(xs + c) = make_double2(x[c], x[c + 1]);
+                }
             }
         }
     }
     __syncwarp();
-    // ---- costates of the velocities: lam_s = Q e_s + A' lam_{s+1}  ->  slot[s-1][12..17]
-    if (lane < 6) {
-        const int c = lane;
+    RPROF(9);
+    // ---- costates of the velocities: lam_s = Q e_s + A' lam_{s+1}  ->  lam[6 (s-1) ..]
+    if (hl < 6) {
+        const int c = hl;
+        const double wpc = P.wp[c], wvc = P.wv[c];
         double lp = 0.0, lv = 0.0;
+#pragma unroll 8
         for (int s = N; s >= 1; --s) {
-            const double* slot = sm.slot + RIC_SLOT * (s - 1);
-            const double ep = slot[c] - sm.xr[c * (N + 1) + s], ev = slot[6 + c] - sm.xr[(6 + c) * (N + 1) + s];
-            lv = fma(P.wv[c], ev, fma(dt, lp, lv));
-            lp = fma(P.wp[c], ep, lp);
-            sm.slot[RIC_SLOT * (s - 1) + 12 + c] = lv;
+            const double* xs = sm.xst + 12 * (s - 1);
+            const double ep = xs[c] - sm.xr[c * (N + 1) + s], ev = xs[6 + c] - sm.xr[(6 + c) * (N + 1) + s];
+            lv = fma(wvc, ev, fma(dt, lp, lv));
+            lp = fma(wpc, ep, lp);
+            sm.lam[6 * (s - 1) + c] = lv;
         }
     }
     __syncwarp();
+    RPROF(10);
     // ---- per foot: forces on the face, gradient, KKT guard
     bool ok = true;
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
-        const int t = lane + 32 * r, k = t >> 2;
+        const int t = hl + 16 * r, k = t >> 2;
         const bool contact = (conbits >> r) & 1u;
         double f[3] = {0.0, 0.0, 0.0};
         nsg[r] = sg[r];
@@ -346,8 +457,8 @@ __device__ int ric_sweep(const DevParams& P, RicWarp<N>& sm, unsigned conbits, c
             Face fc;
             make_face(P, true, sg[r], fc);
             double A[9], h[3];
-            load_A<NF>(sm.A, t, A);
-            bvT_apply(A, lin, sm.slot + RIC_SLOT * k + 12, h);
+            foot_A<N>(P, sm, t, A);
+            bvT_apply(A, lin, sm.lam + 6 * k, h);
             const double qx = fc.zx ? -fc.dx * h[0] : 0.0;
             const double qy = fc.zy ? -fc.dy * h[1] : 0.0;
             const double qz = fc.zz ? -fc.dz * (fc.czx * h[0] + fc.czy * h[1] + h[2]) : 0.0;
@@ -360,53 +471,48 @@ __device__ int ric_sweep(const DevParams& P, RicWarp<N>& sm, unsigned conbits, c
         }
         sm.E[3 * t] = f[0]; sm.E[3 * t + 1] = f[1]; sm.E[3 * t + 2] = f[2];
     }
-    const int all_ok = __all_sync(0xffffffffu, ok);
-    return all_ok ? 1 : 0;
+    const bool all_ok = half_all(ok, sub);
+    RPROF(11);
+    return !spd_all ? -1 : (all_ok ? 1 : 0);
 }
 
-// Outputs of one robot (the warp version of finish() in mpcqp_kernels.cu)                 [MPC.py:432-458]
+// Outputs of one robot (the half-warp version of finish() in mpcqp_kernels.cu)                 [MPC.py:432-458]
+// The states are those of the accepted sweep's forward pass (sm.xst), i.e. the dynamics driven by exactly the
+// impulses of the forces returned.
 template <int N>
-__device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicWarp<N>& sm, const DevState& st, int inst, unsigned conbits,
-                           const uint8_t (&sg)[RicWarp<N>::ROUNDS], bool solved, int status, int sweeps, int lane) {
-    using S = RicWarp<N>;
+__device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>& sm, const DevState& st, int inst, int sub, int hl,
+                           unsigned conbits, const uint8_t (&sg)[RicInst<N>::ROUNDS], bool solved, int status, int sweeps, bool commit) {
+    using S = RicInst<N>;
     constexpr int NF = S::NF, ROUNDS = S::ROUNDS, AW = S::AW, CW = S::CW;
     const double lin = P.dt / P.mass;
-    for (int i = lane; i < AW + CW; i += 32) sm.amask[i] = 0u;
-    // impulses of the final forces -> sm.beta
-#pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int t = lane + 32 * r, k = t >> 2, j = t & 3;
-        double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        if (solved && ((conbits >> r) & 1u)) {
-            double A[9];
-            load_A<NF>(sm.A, t, A);
-            const double f[3] = {sm.E[3 * t], sm.E[3 * t + 1], sm.E[3 * t + 2]};
-            bv_apply(A, lin, f, v);
+    for (int i = hl; i < AW + CW; i += 16) sm.amask[i] = 0u;
+    if (!solved) {
+        // no forces: the states are the free response  p_{s+1} = p_s + dt v_s, v_{s+1} = v_s + g   (MPC.py:110-111, 200-205)
+        if (hl < 6) {
+            const int c = hl;
+            double p = sm.xr[c * (N + 1)], v = sm.xr[(6 + c) * (N + 1)];
+            const double gc = (c == 2) ? -P.gravity * P.dt : 0.0;
+            for (int s = 0; s < N; ++s) {
+                const double pn = p + P.dt * v;
+                v += gc; p = pn;
+                sm.xst[12 * s + c] = p; sm.xst[12 * s + 6 + c] = v;
+            }
         }
-        step_sum_store(v, sm.beta + 6 * k, j);
     }
     __syncwarp();
     double part = 0.0;
-    if (lane < 6) {
-        // component c: p_{s+1} = p_s + dt v_s, v_{s+1} = v_s + u_s + g_c                   (MPC.py:110-111, 200-205)
-        const int c = lane;
-        double p = sm.xr[c * (N + 1)], v = sm.xr[(6 + c) * (N + 1)];
-        const double gc = (c == 2) ? -P.gravity * P.dt : 0.0;
-        double* xs = st.xs + (size_t)inst * 12 * N;
-        for (int s = 0; s < N; ++s) {
-            const double pn = p + P.dt * v;
-            const double vn = v + sm.beta[6 * s + c] + gc;
-            p = pn; v = vn;
-            if (s == 0) { sm.sc.xnext[c] = p; sm.sc.xnext[6 + c] = v; }                     // MPC.q_next / v_next (MPC.py:448-450)
-            const double ep = p - sm.xr[c * (N + 1) + s + 1], ev = v - sm.xr[(6 + c) * (N + 1) + s + 1];
-            xs[12 * s + c] = ep;
-            xs[12 * s + 6 + c] = ev;
-            part += 0.5 * (P.wp[c] * ep * ep + P.wv[c] * ev * ev);
-        }
+    double* xs = st.xs + (size_t)inst * 12 * N;
+    for (int i = hl; i < 12 * N; i += 16) {
+        const int s = i / 12, c = i - 12 * s;
+        const double e = sm.xst[i] - sm.xr[c * (N + 1) + s + 1];
+        const double ee = isfinite(e) ? e : 0.0;                                             // malformed input: never NaN out
+        if (commit) xs[i] = ee;                                                              // MPC.x[:12N] (MPC.py:428)
+        part = fma(0.5 * (c < 6 ? P.wp[c] : P.wv[c - 6]) * ee, ee, part);
     }
+    if (hl < 12) sm.xnext[hl] = sm.xst[hl];                                                  // MPC.q_next / v_next (MPC.py:448-450)
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
-        const int t = lane + 32 * r, k = t >> 2, j = t & 3;
+        const int t = hl + 16 * r, k = t >> 2, j = t & 3;
         const bool contact = (conbits >> r) & 1u;
         double f[3] = {0.0, 0.0, 0.0};
         FootSol sol;
@@ -416,22 +522,24 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicWarp<N>
             // multipliers: the guard's closed form on the gradient of the accepted sweep
             f[0] = sm.E[3 * t]; f[1] = sm.E[3 * t + 1]; f[2] = sm.E[3 * t + 2];
             double A[9], h[3];
-            load_A<NF>(sm.A, t, A);
-            bvT_apply(A, lin, sm.slot + RIC_SLOT * k + 12, h);
+            foot_A<N>(P, sm, t, A);
+            bvT_apply(A, lin, sm.lam + 6 * k, h);
             const double grad[3] = {fma(P.w_force, f[0], h[0]), fma(P.w_force, f[1], h[1]), fma(P.w_force, f[2], h[2])};
             uint8_t dummy;
             kkt_guard(P, sg[r], f, grad, sol, dummy);
         }
         part += 0.5 * P.w_force * (f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
-        double* fo = st.f + (size_t)inst * 12 * N + 3 * t;
-        fo[0] = f[0]; fo[1] = f[1]; fo[2] = f[2];
-        double* yo = st.y + (size_t)inst * 20 * N + 5 * t;
+        if (commit) {
+            double* fo = st.f + (size_t)inst * 12 * N + 3 * t;
+            fo[0] = f[0]; fo[1] = f[1]; fo[2] = f[2];
+            double* yo = st.y + (size_t)inst * 20 * N + 5 * t;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) yo[q] = sol.y[q];
-        st.sig[(size_t)inst * NF + t] = sg[r];
-        if (k == 0) {
-            double* f0 = st.f0 + (size_t)inst * 12 + 3 * j;
-            f0[0] = f[0]; f0[1] = f[1]; f0[2] = f[2];
+            for (int q = 0; q < 5; ++q) yo[q] = sol.y[q];
+            st.sig[(size_t)inst * NF + t] = sg[r];
+            if (k == 0) {
+                double* f0 = st.f0 + (size_t)inst * 12 + 3 * j;
+                f0[0] = f[0]; f0[1] = f[1]; f0[2] = f[2];
+            }
         }
         // rows that hold with equality; a swing foot is pinned to f = 0 (MPC.py:355-358): all five of its rows do
         const double mu = P.mu, tol = 1e-9;
@@ -442,44 +550,53 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicWarp<N>
             const bool act = (fabs(row[q]) <= tol) || (q == 4 && fabs(row[4] + P.fz_max) <= tol);
             if (act) atomicOr(&sm.amask[(b0 + q) >> 5], 1u << ((b0 + q) & 31));
         }
-        const unsigned cb = __ballot_sync(0xffffffffu, contact);
-        if (lane == 0) sm.amask[AW + r] = cb;
+        const unsigned cb = (__ballot_sync(RIC_FULL, contact) >> (16 * sub)) & 0xFFFFu;      // feet 16 r .. 16 r + 15
+        if (hl == 0 && cb) atomicOr(&sm.amask[AW + (r >> 1)], cb << (16 * (r & 1)));
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(RIC_FULL, part, o, 16);
     __syncwarp();
-    for (int i = lane; i < AW; i += 32) st.active[(size_t)inst * AW + i] = sm.amask[i];
-    for (int i = lane; i < CW; i += 32) st.contact[(size_t)inst * CW + i] = sm.amask[AW + i];
-    if (lane == 0) {
+    if (!commit) return;
+    for (int i = hl; i < AW; i += 16) st.active[(size_t)inst * AW + i] = sm.amask[i];
+    for (int i = hl; i < CW; i += 16) st.contact[(size_t)inst * CW + i] = sm.amask[AW + i];
+    if (hl == 0) {
         st.obj[inst] = part;
         st.status[inst] = status;
         st.sweeps[inst] = sweeps;
         st.iters[inst] = 0;
-        if (SC.enabled && status != 3) scenario_advance(SC, inst, sm.sc.xnext);
+        if (SC.enabled && status != 3) scenario_advance(SC, inst, sm.xnext);
     }
 }
 
-// The active-set stage, stage-wise factorisation: grid = ceil(instances / RIC_WARPS), one warp per robot.
+// The active-set stage, stage-wise factorisation.  Persistent grid: the two robots 2 m, 2 m + 1 of the launch are
+// solved by the two halves of warp (m mod warps), warps = RIC_WARPS * gridDim.x; `ws` holds RIC_GAIN * N doubles per
+// half-warp.  The halves share one instruction stream: control flow is warp-uniform, a half that has nothing (left)
+// to do shadows the computation with its stores masked.
 template <int N>
 __global__ void __launch_bounds__(32 * RIC_WARPS)
 riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g,
-               int first_tick, int inst_offset, int inst_count) {
-    using S = RicWarp<N>;
+               double* __restrict__ ws_g, int first_tick, int inst_offset, int inst_count) {
+    using S = RicInst<N>;
     constexpr int NF = S::NF, ROUNDS = S::ROUNDS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    S& sm = reinterpret_cast<S*>(smem_raw)[warp];
-    if (lane == 0) mbar_init(&sm.mbar, 1);
-    for (int i = lane; i < 36; i += 32) sm.L[i] = 0.0;          // the strictly upper triangle of L stays zero
+    const int sub = lane >> 4, hl = lane & 15;
+    const int gwarp = blockIdx.x * RIC_WARPS + warp;
+    S& sm = reinterpret_cast<S*>(smem_raw)[warp * 2 + sub];
+    double* ws = ws_g + (size_t)(gwarp * 2 + sub) * RIC_GAIN * N;
+    if (hl == 0) mbar_init(&sm.mbar, 1);
     __syncwarp();
     unsigned int phase = 0;
-    for (int w = blockIdx.x * RIC_WARPS + warp; w < inst_count; w += gridDim.x * RIC_WARPS) {
-        const int inst = w + inst_offset;
+    for (int w0 = gwarp * 2; w0 < inst_count; w0 += gridDim.x * RIC_PER_CTA) {
+        const bool valid = w0 + sub < inst_count;
+        const int inst = inst_offset + (valid ? w0 + sub : w0);     // an idle half shadows its neighbour, stores masked
         __syncwarp();
+        RPROF_T0();
+        RPROF_COUNT(12);
         if (SC.enabled) {
-            scenario_inputs<N, true>(P, SC, sm.sc, inst, sm.xr, sm.fs);
+            scenario_inputs<N, 16>(P, SC, sm.sc, inst, sm.xr, sm.fs, valid);
         } else {
-            if (lane == 0) {
+            if (hl == 0) {
                 fence_async_smem();
                 mbar_expect_tx(&sm.mbar, (12 * (N + 1) + 260) * 8);
                 bulk_g2s(sm.xr, xref_g + (size_t)inst * 12 * (N + 1), 12 * (N + 1) * 8, &sm.mbar);
@@ -487,20 +604,21 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
             }
             mbar_wait(&sm.mbar, phase);
             phase ^= 1u;
+            __syncwarp();
         }
-        // ---- decode: contact flags, lever-arm blocks, warm-start signature      [MPC.py:316-360, 403-406, 635-652]
+        RPROF(13);
+        // ---- decode: contact flags, lever arms, inertia blocks, warm-start signature   [MPC.py:316-360, 403-406, 635-652]
         const bool warm = P.warm_start && !first_tick;
         bool bad = false;
         unsigned conbits = 0u;
         uint8_t sg[ROUNDS], nsg[ROUNDS];
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
-            const int t = lane + 32 * r, k = t >> 2, j = t & 3;
-            double A0[9];
+            const int t = hl + 16 * r, k = t >> 2, j = t & 3;
+            double lv[3];
             bool contact = false;
-            decode_foot<N>(P, sm.xr, sm.fs, k, j, first_tick != 0, A0, contact, bad);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) sm.A[i * NF + t] = A0[i];
+            decode_lever<N>(P, sm.xr, sm.fs, k, j, first_tick != 0, lv, contact, bad);
+            sm.lev[t] = lv[0]; sm.lev[NF + t] = lv[1]; sm.lev[2 * NF + t] = lv[2];
             conbits |= contact ? (1u << r) : 0u;
             sg[r] = SIG_FREE;
             if (warm && contact) {
@@ -509,58 +627,69 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
                 sg[r] = s8 > 26 ? SIG_FREE : s8;
             }
         }
-        for (int i = lane; i < 12 * (N + 1); i += 32) bad = bad || !isfinite(sm.xr[i]);
-        const bool any_bad = __any_sync(0xffffffffu, bad);       // also orders the reads of fs before E is written
+        for (int k = hl; k < N; k += 16) {
+            double Ii[9];
+            step_inertia(P, sm.xr[5 * (N + 1) + k], Ii);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) sm.Ii[9 * k + i] = Ii[i];
+        }
+        for (int i = hl; i < 12 * (N + 1); i += 16) bad = bad || !isfinite(sm.xr[i]);
+        const bool any_bad = half_any(bad, sub);
+        __syncwarp();                                            // fs is dead from here on (E overwrites it)
         int sweeps = 0, status = 0;
-        bool done = false;
+        bool done = false, stop = any_bad || !valid;
+        RPROF(14);
         if (any_bad) {
             status = 3;
             conbits = 0u;
 #pragma unroll
             for (int r = 0; r < ROUNDS; ++r) sg[r] = SIG_FREE;
-        } else {
-            int nhist = 0;
-            for (int s = 0; s < P.max_sweeps && !done; ++s) {
-                unsigned long long h = 0ull;
+        }
+        int nhist = 0;
+        for (int s = 0; s < P.max_sweeps; ++s) {
+            unsigned long long h = 0ull;
 #pragma unroll
-                for (int r = 0; r < ROUNDS; ++r) {
-                    if ((conbits >> r) & 1u) {
-                        unsigned long long q = (unsigned long long)(sg[r] + 1) * 0x9E3779B97F4A7C15ull;
-                        q ^= q >> 29; q *= (2ull * (lane + 32 * r) + 0xBF58476D1CE4E5B9ull); q ^= q >> 32;
-                        h += q;
-                    }
+            for (int r = 0; r < ROUNDS; ++r) {
+                if ((conbits >> r) & 1u) {
+                    unsigned long long q = (unsigned long long)(sg[r] + 1) * 0x9E3779B97F4A7C15ull;
+                    q ^= q >> 29; q *= (2ull * (hl + 16 * r) + 0xBF58476D1CE4E5B9ull); q ^= q >> 32;
+                    h += q;
                 }
+            }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+            for (int o = 8; o > 0; o >>= 1) h += __shfl_xor_sync(RIC_FULL, h, o, 16);
+            bool need = !done && !stop;
+            if (need) {
                 bool seen = false;
                 for (int i = 0; i < nhist; ++i) seen = seen || (sm.hist[i] == h);
-                if (seen) break;
-                __syncwarp();
-                if (lane == 0 && nhist < 16) sm.hist[nhist] = h;
-                nhist = (nhist < 16) ? nhist + 1 : nhist;
-                __syncwarp();
-                const int rc = ric_sweep<N>(P, sm, conbits, sg, nsg, lane);
+                if (seen) { stop = true; need = false; }         // the active-set iteration cycles: give up
+            }
+            if (!__any_sync(RIC_FULL, need)) break;
+            __syncwarp();
+            if (need && hl == 0 && nhist < 16) sm.hist[nhist] = h;
+            if (need) nhist = (nhist < 16) ? nhist + 1 : nhist;
+            __syncwarp();
+            const int rc = ric_sweep<N>(P, sm, ws, sub, hl, conbits, sg, nsg);
+            if (need) {
                 ++sweeps;
-                if (rc < 0) break;
-                if (rc > 0) { done = true; status = 1; }
+                if (rc < 0) stop = true;
+                else if (rc > 0) { done = true; status = 1; }
                 else {
 #pragma unroll
                     for (int r = 0; r < ROUNDS; ++r) sg[r] = nsg[r];
                 }
             }
-            if (!done) {
-                if (P.mode & 2) {
-                    if (lane == 0) {
-                        const int slot = atomicAdd(st.fb_count, 1);
-                        st.fb_list[slot] = inst;
-                        st.sweeps[inst] = sweeps;
-                    }
-                    continue;       // state of this robot is left untouched for the ADMM stage
-                }
-                status = 0;
-            }
         }
-        ric_finish<N>(P, SC, sm, st, inst, conbits, sg, done, status, sweeps, lane);
+        // a robot the sweeps gave up on goes to the ADMM stage with its carried state untouched
+        const bool pushed = valid && !done && !any_bad && (P.mode & 2);
+        if (pushed && hl == 0) {
+            const int q = atomicAdd(st.fb_count, 1);
+            st.fb_list[q] = inst;
+            st.sweeps[inst] = sweeps;
+        }
+        RPROF(15);
+        ric_finish<N>(P, SC, sm, st, inst, sub, hl, conbits, sg, done, status, sweeps, valid && !pushed);
+        RPROF(16);
     }
 }
 

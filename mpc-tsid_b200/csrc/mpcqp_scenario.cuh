@@ -66,11 +66,14 @@ struct ScenarioSmem {
 };
 
 // Build xref (12 x (N+1)) and fsteps (20 x 13) of instance `inst` in shared memory.  Called by every thread of
-// the group that owns the instance: the whole CTA (WARP = false) or one warp (WARP = true).
-template <int N, bool WARP = false>
-__device__ void scenario_inputs(const DevParams& P, const DevScenario& S, ScenarioSmem& sc, int inst, double* xr, double* fs) {
-    const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-    const int nthr = WARP ? 32 : (int)blockDim.x;
+// the group that owns the instance: the whole CTA (GROUP = 0), one warp (GROUP = 32) or half a warp (GROUP = 16).
+template <int N, int GROUP = 0>
+__device__ void scenario_inputs(const DevParams& P, const DevScenario& S, ScenarioSmem& sc, int inst, double* xr, double* fs,
+                                bool commit = true) {
+    constexpr bool WARP = GROUP != 0;
+    const int tid = WARP ? (int)(threadIdx.x & (GROUP - 1)) : (int)threadIdx.x;
+    const int nthr = WARP ? GROUP : (int)blockDim.x;
+    // GROUP = 16: both halves of the warp call this together (one instruction stream), so the barrier is the full warp's
     auto group_sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
     const double nanv = __longlong_as_double(0x7ff8000000000000ll);
     for (int i = tid; i < 260; i += nthr) fs[i] = (i % 13 == 0) ? 0.0 : nanv;
@@ -94,7 +97,7 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
         sc.nrows = rows;
         for (int r = 0; r < rows; ++r) fs[r * 13] = (double)sc.cnt[r];
     }
-    for (int i = WARP ? tid : tid - 32; i >= 0 && i < N; i += WARP ? 32 : N) {
+    for (int i = WARP ? tid : tid - 32; i >= 0 && i < N; i += WARP ? GROUP : N) {
         double sn, cs;
         sincos(S.lin_a[i] * w, &sn, &cs);                                  // FootstepPlanner.py:95-97
         sc.vx[i] = sc.vr[0] * cs - sc.vr[1] * sn;
@@ -154,8 +157,10 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
             }
             prev_st = stn;
         }
-        S.feet[(size_t)inst * 8 + j] = fwx; S.feet[(size_t)inst * 8 + 4 + j] = fwy;
-        S.target[(size_t)inst * 8 + j] = twx; S.target[(size_t)inst * 8 + 4 + j] = twy;
+        if (commit) {
+            S.feet[(size_t)inst * 8 + j] = fwx; S.feet[(size_t)inst * 8 + 4 + j] = fwy;
+            S.target[(size_t)inst * 8 + j] = twx; S.target[(size_t)inst * 8 + 4 + j] = twy;
+        }
     }
     if (tid == (WARP ? 4 : 32)) {
         // positions: dt * cumsum of the rotated reference velocity, from the measured position (sequential like numpy)
@@ -168,7 +173,7 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
             xr[7 * (N + 1) + 1 + i] = sc.vy[i];
         }
     }
-    for (int i = WARP ? tid : tid - 64; i >= 0 && i < N; i += WARP ? 32 : N) {
+    for (int i = WARP ? tid : tid - 64; i >= 0 && i < N; i += WARP ? GROUP : N) {
         xr[2 * (N + 1) + 1 + i] = SC_H_REF;
         xr[5 * (N + 1) + 1 + i] = w * S.lin_b[i];
         xr[11 * (N + 1) + 1 + i] = w;
@@ -177,9 +182,9 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
     group_sync();
     if (tid == 0) {
         // remember the first-step contacts for the next tick's touchdown test
-        S.prevc[inst] = (uint8_t)(0x80 | (sc.mask[0] & 15));
+        if (commit) S.prevc[inst] = (uint8_t)(0x80 | (sc.mask[0] & 15));
     }
-    if (S.xref_out) {
+    if (S.xref_out && commit) {
         for (int i = tid; i < 12 * (N + 1); i += nthr) S.xref_out[(size_t)inst * 12 * (N + 1) + i] = xr[i];
         for (int i = tid; i < 260; i += nthr) S.fsteps_out[(size_t)inst * 260 + i] = fs[i];
     }

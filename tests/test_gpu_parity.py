@@ -32,7 +32,7 @@ def _active_from_x(g, t, n):
     return ((np.abs(Ax - u) <= 1e-9) | (np.abs(Ax - l) <= 1e-9)).reshape(n, 4, 5)
 
 
-@pytest.mark.parametrize("mode", [3, 2], ids=["activeset+admm", "admm-only"])
+@pytest.mark.parametrize("mode", [7, 3, 2], ids=["stagewise+admm", "dense+admm", "admm-only"])
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[6:-4] for p in GOLD])
 def test_golden_sequences(path, mode):
     """Replay each golden closed-loop sequence tick by tick (warm start carried like the reference)."""
@@ -70,12 +70,13 @@ def test_build_half_matches_reference_coefficients():
         eng.close()
 
 
+@pytest.mark.parametrize("mode", [7, 3], ids=["stagewise", "dense"])
 @pytest.mark.parametrize("gaits", [["trot"], ["pace", "bound", "walk", "static"]], ids=["trot", "mixed"])
-def test_closed_loop_batch_certified(gaits):
-    """64 robots x 12 closed-loop ticks: every solution passes the oracle's KKT certificate on the QP
-    the reference would have built; masks identical."""
-    B, T = 64, 12
-    eng = mpcqp.Engine(batch=B)
+def test_closed_loop_batch_certified(gaits, mode):
+    """63 robots (odd: one half-warp of the stage-wise kernel idles) x 12 closed-loop ticks: every solution passes the
+    oracle's KKT certificate on the QP the reference would have built; masks identical."""
+    B, T = 63, 12
+    eng = mpcqp.Engine(batch=B, mode=mode)
     sc = Scenario(B, gaits=gaits, seed=123)
     for t in range(T):
         xref, fsteps = sc.inputs()
@@ -92,11 +93,12 @@ def test_closed_loop_batch_certified(gaits):
     eng.close()
 
 
-def test_long_horizon_closed_loop_certified():
+@pytest.mark.parametrize("mode", [7, 3], ids=["stagewise", "dense"])
+def test_long_horizon_closed_loop_certified(mode):
     """BASELINE configs[3], N = 32 (n_periods = 2): 24 robots x 6 ticks, mixed gaits, oracle certificate."""
     from oracle import mpc_build
     B, T, n = 24, 6, 32
-    eng = mpcqp.Engine(batch=B, n_steps=n)
+    eng = mpcqp.Engine(batch=B, n_steps=n, mode=mode)
     sc = Scenario(B, n_steps=n, gaits=["trot", "pace", "walk"], seed=77)
     par = mpc_build.Params(n_steps=n)
     for t in range(T):
@@ -118,17 +120,19 @@ def test_stages_agree_and_warm_start_is_only_a_speedup():
     B = 32
     sc = Scenario(B, gaits=["trot", "walk"], seed=9)
     a, b, c = mpcqp.Engine(batch=B, mode=3), mpcqp.Engine(batch=B, mode=2), mpcqp.Engine(batch=B, mode=3, warm_start=0)
+    d = mpcqp.Engine(batch=B, mode=7)                      # stage-wise factorisation of the active-set stage
     for t in range(6):
         xref, fsteps = sc.inputs()
         xs = []
-        for e in (a, b, c):
+        for e in (a, b, c, d):
             e.run(t, xref, fsteps)
             xs.append(e.solution())
             assert (e.info()["status"] == 1).all()
-        assert np.abs(xs[0] - xs[1]).max() <= 1e-7 and np.abs(xs[0] - xs[2]).max() <= 1e-7
+        assert np.abs(xs[0] - xs[1]).max() <= 1e-7 and np.abs(xs[0] - xs[2]).max() <= 1e-7 and np.abs(xs[0] - xs[3]).max() <= 1e-7
+        np.testing.assert_array_equal(a.info()["sweeps"], d.info()["sweeps"])      # same active-set path, other factorisation
         sc.advance(xs[0][:, :12] + xref[:, :, 1])
     assert b.info()["iters"].min() > 0 and a.info()["sweeps"].mean() <= c.info()["sweeps"].mean() + 1e-9
-    for e in (a, b, c):
+    for e in (a, b, c, d):
         e.close()
 
 

@@ -30,7 +30,13 @@ for r in csv.reader(io.StringIO(out)):
 secs = [s for s in sections if ksub in s["name"]]
 sec = secs[which]
 H, body = sec["rows"][0], sec["rows"][1:]
-mangled = [f for f in funcs if ("Lb0" in f) == ("(bool)0" in sec["name"]) and "solve_kernel" in f] if "solve_kernel" in ksub else list(funcs)
+if "solve_kernel" in ksub:
+    mangled = [f for f in funcs if ("Lb0" in f) == ("(bool)0" in sec["name"]) and "solve_kernel" in f]
+elif "riccati_kernel" in ksub:
+    n = re.search(r"\(int\)(\d+)", sec["name"]).group(1)
+    mangled = [f for f in funcs if "riccati_kernelILi%sE" % n in f]
+else:
+    mangled = list(funcs)
 lines = funcs[mangled[0]]
 si = H.index("# Samples"); ii = H.index("Instructions Executed")
 stall_cols = [i for i, h in enumerate(H) if h.startswith("stall_") and "Not Issued" not in h]
