@@ -153,7 +153,7 @@ class ClockSampler:
 # FLOP model of what the engine actually executes, per instance-tick
 # ----------------------------------------------------------------------------------------------
 def flops_per_tick(sweeps, iters, fallbacks, n=96, N=N_STEPS, refine=0):
-    """What the engine executes per instance-tick, counted from the algorithm (not from SASS):
+    """DENSE path (mode 3), per instance-tick, counted from the algorithm (not from SASS):
     sweep      = Cholesky n^3/3 + triangular inverse n^3/3 (DMMA) + block assembly
                  + (1 + refine) solves (two triangular mat-vecs, 2 n^2) + (1 + refine) Hessian applies
     admm setup = the same factorisation once;  admm iteration = one solve + per-foot projection."""
@@ -169,6 +169,32 @@ def flops_per_tick(sweeps, iters, fallbacks, n=96, N=N_STEPS, refine=0):
     return sweeps * sweep + fallbacks * admm_setup + iters * admm_iter + fixed
 
 
+def flops_stagewise_sweep(N=N_STEPS):
+    """STAGE-WISE path (default), one active-set sweep of one robot, counted from the algorithm of
+    mpcqp_riccati.cuh (useful work only: the redundant per-lane copies of the 6x6 factorisations are not counted).
+    Per stage: two 6x6 Cholesky factorisations + triangular inverses (2 x 2 n^3/3), T = E L and G = I + L'T
+    (triangular / symmetric products), 13 rows x 4 triangular row products (21 FMA each), 12 rows x (36 + 6) FMA for
+    Pt[:, p] and pt, 12 x 6 FMA for Pt[:, v] beta, the assembly of P_k."""
+    n = 6
+    chol = 2 * (2.0 * n ** 3 / 3.0)
+    t_g = 2 * 126 + 2 * 56
+    rows = 13 * 4 * 21 * 2
+    wpart = 12 * (36 + 6) * 2 + 12 * 6 * 2
+    assemble_p = 21 * 2 + 36 * 2 + 21 * 5 + 12 * 3
+    stage = chol + t_g + rows + wpart + assemble_p
+    feet = 4 * N
+    e_beta = feet * (21 * 6 + 27 + 18 + 12)          # lever block, B Z columns, 21 entries, impulse of pf
+    forward = N * (12 * 2 + 6 * 13 * 2 + 6)
+    costate = N * 6 * 6
+    per_foot = feet * (18 + 18 + 12 + 12 + 20)       # lever block, Bv' lam, face solve, gradient, guard
+    return N * stage + e_beta + forward + costate + per_foot
+
+
+def flops_stagewise_fixed(N=N_STEPS):
+    feet = 4 * N
+    return feet * 40 + N * 30 + 12 * N * 4 + feet * 40   # decode, inertia blocks, outputs/objective, multipliers
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,6 +203,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="robots per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", type=int, default=7, help="solver stages (include/mpcqp.h MPCQP_MODE_*): 7 = stage-wise active set + ADMM fallback (default), 3 = dense")
     ap.add_argument("--cpu-ticks", type=int, default=100)
     ap.add_argument("--settle", type=int, default=20,
                     help="closed-loop ticks run (untimed) before the warm-up so that the timed ticks are steady-state "
@@ -222,7 +249,7 @@ def main():
     B, N, K = args.batch, N_STEPS, args.steps
     W = max(args.warmup, 3) + max(args.settle, 0)       # untimed ticks: settle + warm-up
     T = W + K
-    eng = mpcqp.Engine(batch=B, device=local_rank)
+    eng = mpcqp.Engine(batch=B, device=local_rank, mode=args.mode)
     peaks = mpcqp.measure_fp64_peak(local_rank)
 
     # ---- untimed: closed loop through the engine to produce the input sequence (pinned host copies)
@@ -294,32 +321,51 @@ def main():
     e2e_value = world * B * K / e2e_s
     checksum = float(np.abs(out_np).sum())
 
-    # ---- roofline of the dominant kernel (solve_kernel<16,false>): FP64 pipe, not HBM
-    flop = flops_per_tick(tot_sweeps, tot_iters, tot_fb)            # this rank, K ticks
+    # ---- roofline of the dominant kernel.  Neither HBM nor tensor bound: the stage-wise kernel is a chain of
+    #      6x6 FP64 factorisations per robot, bounded by FP64-FMA-pipe latency/throughput; the denominator is the FP64
+    #      FMA peak measured on this GPU in this run.  The fallback (dense ADMM) kernel's work is counted with its own model.
+    stagewise = bool(eng.params.mode & 4)
+    if stagewise:
+        flop = (tot_sweeps * flops_stagewise_sweep() + B * K * flops_stagewise_fixed()
+                + flops_per_tick(0, tot_iters, tot_fb) - flops_per_tick(0, 0, 0))
+        peak, peak_name = peaks["dfma_tflops"], "FP64 FMA"
+        kernel = "riccati_kernel<16> (+ dense ADMM fallback kernel for the robots the sweeps give up on)"
+        traffic = 26.92e6 * B / 4096.0
+        traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum of one riccati_kernel<16> launch at 4096 robots, ncu --set full "
+                       "(profiles/r01_riccati_kernel_ncu_summary.txt), scaled to this batch")
+        model = "engine's own count, DESIGN.md section 5: sweeps*%.0f + %.0f per solve (+ fallback work)" % (
+            flops_stagewise_sweep(), flops_stagewise_fixed())
+    else:
+        flop = flops_per_tick(tot_sweeps, tot_iters, tot_fb)        # this rank, K ticks
+        peak, peak_name = peaks["dmma_tflops"], "FP64 tensor (DMMA m8n8k4)"
+        kernel = "solve_kernel<16,false> (+ ADMM fallback kernel)"
+        traffic = 22.49e6 * B / 4096.0
+        traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel<16,false> launch at 4096 instances, ncu --set full "
+                       "(profiles/r01_solve_kernel_ncu_summary.txt), scaled to this batch")
+        model = "engine's own count, DESIGN.md section 5: sweeps*%.0f + admm_iters*%.0f per solve" % (
+            flops_per_tick(1, 0, 0) - flops_per_tick(0, 0, 0), flops_per_tick(0, 1, 0) - flops_per_tick(0, 0, 0))
     flop_all = sum_over_ranks(flop)
     achieved = flop_all / world / (total_ms * 1e-3) * 1e-12          # per GPU
-    peak = peaks["dmma_tflops"]
     hbm_alg = 21216.0                                               # B per solve, SURVEY.md 8(d)
-    hbm_peak = 6533.8
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         hbm_src = "measured"
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback"
     hbm_ach = hbm_alg * B * K / (total_ms * 1e-3) * 1e-9
+    canon = 4.31e6 * world * B * K / (total_ms * 1e-3) * 1e-12 / world
     roofline = {
-        "bound": "tensor", "pipe": "FP64 tensor (DMMA m8n8k4) + FP64 FMA", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-        "traffic": 22.49e6 * B / 4096.0, "kernel": "solve_kernel<16,false> (+ ADMM fallback kernel)",
-        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel<16,false> launch at 4096 "
-                          "instances, ncu --set full (profiles/r01_solve_kernel_ncu_summary.txt), scaled to this batch",
-        "peak_source": "DMMA m8n8k4 issue loop measured on this GPU in this run (mpcqp_measure_fp64_peak); "
+        "bound": "fp64", "bound_note": "neither hbm nor tensor: FP64 FMA pipe latency/throughput (SURVEY.md 8d)", "pipe": peak_name,
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+        "traffic": traffic, "kernel": kernel, "traffic_source": traffic_src,
+        "peak_source": "issue loop of that instruction measured on this GPU in this run (mpcqp_measure_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 entry",
-        "flop_model": "engine's own count, DESIGN.md section 5: sweeps*%.0f + admm_iters*%.0f per solve" % (
-            flops_per_tick(1, 0, 0) - flops_per_tick(0, 0, 0), flops_per_tick(0, 1, 0) - flops_per_tick(0, 0, 0)),
+        "flop_model": model,
         "mflop_per_solve": flop / (B * K) * 1e-6, "canonical_mflop_per_solve_survey_8d_it60": 4.31,
+        "canonical_equivalent_tflops": canon,
         "sweeps_per_solve": tot_sweeps / (B * K), "admm_iters_per_solve": tot_iters / (B * K),
         "fallback_frac": tot_fb / (B * K),
-        "dfma_peak_tflops": peaks["dfma_tflops"],
+        "dfma_peak_tflops": peaks["dfma_tflops"], "dmma_peak_tflops": peaks["dmma_tflops"],
         "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                 "bytes_per_solve": hbm_alg, "peak_source": hbm_src},
     }

@@ -165,7 +165,7 @@ void mpcqp_default_params(mpcqp_params* p) {
     for (int i = 0; i < 3; ++i) p->w_state[9 + i] = 0.05 * std::sqrt(p->w_state[3 + i]);
     p->w_force = 1e-5;                                      // MPC.py:282-284
     p->mode = MPCQP_MODE_ACTIVE_SET | MPCQP_MODE_ADMM | MPCQP_MODE_STAGEWISE;
-    p->max_sweeps = 6;
+    p->max_sweeps = 12;
     p->max_iter = 1000;
     p->min_iter = 10;
     p->check_every = 5;

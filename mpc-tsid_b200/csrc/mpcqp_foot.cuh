@@ -195,7 +195,13 @@ __device__ __forceinline__ bool kkt_guard(const DevParams& P, uint8_t sig, doubl
         sol.y[2] = fmax(qy, 0.0); sol.y[3] = fmax(-qy, 0.0);
         sol.y[4] = -qz - mu * (fabs(qx) + fabs(qy));
         f[0] = f[1] = f[2] = 0.0;
-        if (sol.y[4] < -ytol) { ok = false; nsx = 0; nsy = 0; ntz = 0; }
+        if (sol.y[4] < -ytol) {
+            // leave the apex by releasing the fz >= 0 row only: the friction rows the gradient pushes against stay active
+            ok = false;
+            nsx = (qx > ytol) ? 1 : ((qx < -ytol) ? -1 : 0);
+            nsy = (qy > ytol) ? 1 : ((qy < -ytol) ? -1 : 0);
+            ntz = 0;
+        }
     } else {
         const double yx = (sx != 0) ? -sx * grad[0] : 0.0;
         const double yy = (sy != 0) ? -sy * grad[1] : 0.0;

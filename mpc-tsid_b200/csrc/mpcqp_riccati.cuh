@@ -645,38 +645,76 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
 #pragma unroll
             for (int r = 0; r < ROUNDS; ++r) sg[r] = SIG_FREE;
         }
-        int nhist = 0;
-        for (int s = 0; s < P.max_sweeps; ++s) {
+        // order-sensitive hash of a signature, uniform over the half-warp (cycle detection)
+        auto sig_hash = [&](const uint8_t (&g)[ROUNDS]) {
             unsigned long long h = 0ull;
 #pragma unroll
             for (int r = 0; r < ROUNDS; ++r) {
                 if ((conbits >> r) & 1u) {
-                    unsigned long long q = (unsigned long long)(sg[r] + 1) * 0x9E3779B97F4A7C15ull;
+                    unsigned long long q = (unsigned long long)(g[r] + 1) * 0x9E3779B97F4A7C15ull;
                     q ^= q >> 29; q *= (2ull * (hl + 16 * r) + 0xBF58476D1CE4E5B9ull); q ^= q >> 32;
                     h += q;
                 }
             }
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) h += __shfl_xor_sync(RIC_FULL, h, o, 16);
-            bool need = !done && !stop;
-            if (need) {
-                bool seen = false;
-                for (int i = 0; i < nhist; ++i) seen = seen || (sm.hist[i] == h);
-                if (seen) { stop = true; need = false; }         // the active-set iteration cycles: give up
-            }
+            return h;
+        };
+        int nhist = 0;
+        bool careful = false;       // set once the full primal-dual update proposed a signature that was tried before
+        for (int s = 0; s < P.max_sweeps; ++s) {
+            const bool need = !done && !stop;
             if (!__any_sync(RIC_FULL, need)) break;
+            const unsigned long long h = sig_hash(sg);
             __syncwarp();
             if (need && hl == 0 && nhist < 16) sm.hist[nhist] = h;
             if (need) nhist = (nhist < 16) ? nhist + 1 : nhist;
             __syncwarp();
             const int rc = ric_sweep<N>(P, sm, ws, sub, hl, conbits, sg, nsg);
+            bool search = false;
             if (need) {
                 ++sweeps;
                 if (rc < 0) stop = true;
                 else if (rc > 0) { done = true; status = 1; }
+                else search = true;
+            }
+            // ---- next signature.  First choice: every foot adopts its proposal (primal-dual active-set step).  If that
+            // signature was already tried the iteration would cycle: from then on one foot changes per sweep, in index order.
+            auto seen = [&](unsigned long long q) {
+                bool f = false;
+                for (int i = 0; i < nhist; ++i) f = f || (sm.hist[i] == q);
+                return f;
+            };
+            const unsigned long long hfull = sig_hash(nsg);
+            if (search && !careful) {
+                if (seen(hfull)) careful = true;
                 else {
 #pragma unroll
                     for (int r = 0; r < ROUNDS; ++r) sg[r] = nsg[r];
+                    search = false;
+                }
+            }
+            int tlast = -1;
+            while (__any_sync(RIC_FULL, search)) {
+                int tm = 0x7fffffff;
+#pragma unroll
+                for (int r = 0; r < ROUNDS; ++r) {
+                    const int t = hl + 16 * r;
+                    if (nsg[r] != sg[r] && t > tlast && t < tm) tm = t;
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) { const int q = __shfl_xor_sync(RIC_FULL, tm, o, 16); tm = q < tm ? q : tm; }
+                uint8_t cand[ROUNDS];
+#pragma unroll
+                for (int r = 0; r < ROUNDS; ++r) cand[r] = (hl + 16 * r == tm) ? nsg[r] : sg[r];
+                const unsigned long long hc = sig_hash(cand);
+                if (search) {
+                    if (tm == 0x7fffffff) { stop = true; search = false; }            // every single change was tried before
+                    else if (!seen(hc)) {
+#pragma unroll
+                        for (int r = 0; r < ROUNDS; ++r) sg[r] = cand[r];
+                        search = false;
+                    } else tlast = tm;
                 }
             }
         }

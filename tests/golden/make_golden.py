@@ -131,9 +131,18 @@ def long_horizon():
     run_case("trot_N32", s, 5)
 
 
+def long_horizon_64():
+    # 7. N = 64 (n_periods = 4, BASELINE configs[3])
+    s = Scenario(1, n_steps=64, gaits="trot", v_ref=[0.4, -0.1, 0, 0, 0, -0.25], phase=[6], random_commands=False, seed=17)
+    run_case("trot_N64", s, 3)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "long":
         long_horizon()
+    elif len(sys.argv) > 1 and sys.argv[1] == "long64":
+        long_horizon_64()
     else:
         main()
         long_horizon()
+        long_horizon_64()
