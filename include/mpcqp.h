@@ -49,6 +49,8 @@ extern "C" {
 #define MPCQP_MODE_ADMM 2           /* fixed-rho ADMM + guarded polish (globally convergent)    */
 #define MPCQP_MODE_STAGEWISE 4      /* active-set stage factorises stage by stage (Riccati recursion over the horizon, one warp per
                                        robot, O(N)) instead of the dense 6N x 6N condensed system (one CTA per robot, O(N^3))      */
+#define MPCQP_MODE_ADMM_STAGEWISE 8 /* the ADMM stage iterates on the stage-wise factorisation too, inside the active-set kernel (no
+                                       second kernel, any horizon; slower per iteration than the dense ADMM stage for N <= 32)     */
 
 typedef struct mpcqp_handle mpcqp_handle;
 
@@ -106,7 +108,7 @@ int mpcqp_get_solution(mpcqp_handle* h, double* x, int location);
 
 /* Per-instance diagnostics the reference never exposes (it ignores sol.info.status, MPC.py:427):
  * any pointer may be NULL.  status[B], sweeps[B] (active-set factorizations), iters[B] (ADMM
- * iterations), obj[B] (1/2 x'Px), contact[B*2] (4N bits: bit 4k+j = foot j in stance at step k),
+ * iterations), obj[B] (1/2 x'Px), contact[B*ceil(4N/32)] (4N bits: bit 4k+j = foot j in stance at step k),
  * active[B*ceil(20N/32)] (bit 20k+5j+r = pyramid row r of foot j at step k holds with equality),
  * y[B*20N] multipliers of the pyramid rows (rows of L in MPC.py:136-148). */
 int mpcqp_get_info(mpcqp_handle* h, int32_t* status, int32_t* sweeps, int32_t* iters, double* obj,

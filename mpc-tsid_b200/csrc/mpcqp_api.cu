@@ -205,8 +205,10 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     if (p->struct_size != (int32_t)sizeof(mpcqp_params)) return fail(MPCQP_ERR_INVALID, "mpcqp_params.struct_size mismatch");
     if (p->n_steps != 16 && p->n_steps != 32 && p->n_steps != 64)
         return fail(MPCQP_ERR_INVALID, "n_steps: this build supports horizons of 16, 32 and 64 steps");
-    if (p->n_steps == 64 && (!(p->mode & MPCQP_MODE_STAGEWISE) || (p->mode & MPCQP_MODE_ADMM)))
-        return fail(MPCQP_ERR_INVALID, "n_steps = 64 runs on the stage-wise active-set stage only (mode = ACTIVE_SET | STAGEWISE)");
+    if (p->n_steps == 64 && (!(p->mode & MPCQP_MODE_STAGEWISE) || ((p->mode & MPCQP_MODE_ADMM) && !(p->mode & MPCQP_MODE_ADMM_STAGEWISE))))
+        return fail(MPCQP_ERR_INVALID, "n_steps = 64 needs the stage-wise stages: MPCQP_MODE_STAGEWISE, and MPCQP_MODE_ADMM_STAGEWISE with MPCQP_MODE_ADMM");
+    if ((p->mode & MPCQP_MODE_ADMM_STAGEWISE) && (p->mode & (MPCQP_MODE_STAGEWISE | MPCQP_MODE_ADMM)) != (MPCQP_MODE_STAGEWISE | MPCQP_MODE_ADMM))
+        return fail(MPCQP_ERR_INVALID, "MPCQP_MODE_ADMM_STAGEWISE runs inside the stage-wise active-set kernel: set MPCQP_MODE_STAGEWISE and MPCQP_MODE_ADMM too");
     if ((p->mode & MPCQP_MODE_STAGEWISE) && !(p->mode & MPCQP_MODE_ACTIVE_SET))
         return fail(MPCQP_ERR_INVALID, "MPCQP_MODE_STAGEWISE selects the factorisation of the active-set stage: set MPCQP_MODE_ACTIVE_SET too");
     if (p->batch < 1) return fail(MPCQP_ERR_INVALID, "batch must be >= 1");
@@ -318,7 +320,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     if (p->mode & MPCQP_MODE_STAGEWISE) {
         if (ric_per_sm < 1) return bail(fail(MPCQP_ERR_CUDA, "the stage-wise kernel does not fit on this device"));
         h->ric_max_ctas = ric_per_sm * h->sms;
-        h->ric_ws_doubles = (size_t)h->ric_max_ctas * RIC_PER_CTA * RIC_GAIN * N;
+        h->ric_ws_doubles = (size_t)h->ric_max_ctas * RIC_PER_CTA * (RIC_GAIN + 4 * RIC_ADM) * N;
         CUH(cudaMalloc(&h->d_ric_ws, 3 * h->ric_ws_doubles * sizeof(double)));
     }
 #undef CUH
@@ -388,7 +390,7 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
         CU(cudaMemcpyAsync(h->st.fb_count, &B, 4, cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
-    if (h->p.mode & MPCQP_MODE_ADMM) {
+    if ((h->p.mode & MPCQP_MODE_ADMM) && !(h->p.mode & MPCQP_MODE_ADMM_STAGEWISE)) {
         const int slots = h->ctas_per_sm(true) * h->sms;
         h->solve(true, B < slots ? B : slots, h->stream, dx, df, first, 0, B);
     }
@@ -495,7 +497,8 @@ int mpcqp_export_build(mpcqp_handle* h, double k, const double* xref, const doub
         dB = B_vals; dS = S_vals; dN = NK;
     }
     if (N == 16) export_build_kernel<16><<<(int)B, 128, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
-    else export_build_kernel<32><<<(int)B, 128, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
+    else if (N == 32) export_build_kernel<32><<<(int)B, 128, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
+    else export_build_kernel<64><<<(int)B, 256, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
     ++h->launches;
     CU(cudaGetLastError());
     if (host) {
@@ -604,7 +607,7 @@ int mpcqp_scenario_run(mpcqp_handle* h, int ticks, int emit_inputs) {
         const int first = h->scen_tick == 0 ? 1 : 0;
         CU(cudaMemsetAsync(h->st.fb_count, 0, sizeof(int32_t), h->stream));
         h->solve(false, B, h->stream, nullptr, nullptr, first, 0, B, true);
-        if (h->p.mode & MPCQP_MODE_ADMM) {
+        if ((h->p.mode & MPCQP_MODE_ADMM) && !(h->p.mode & MPCQP_MODE_ADMM_STAGEWISE)) {
             const int slots = h->ctas_per_sm(true) * h->sms;
             h->solve(true, B < slots ? B : slots, h->stream, nullptr, nullptr, first, 0, B, true);
         }

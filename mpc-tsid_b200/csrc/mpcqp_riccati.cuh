@@ -192,54 +192,13 @@ __device__ __forceinline__ void hstep_sum_store(double (&v)[6], double* dst, int
     if (j == 0) store_row6(dst, v);
 }
 
-// One equality-constrained solve on the faces `sg` selects + KKT guard.  The 16 lanes of the robot call it.
-// Returns (uniform over the half-warp) 1 if every foot passes the guard, 0 if not, -1 if a pivot was not positive.
-// Both halves of the warp must call it together (full-mask collectives inside).
-// On return sm.E holds the forces (3 per foot, foot-major), sm.xst the states, sm.lam the velocity costates.
+// The LQ solve itself: backward recursion over sm.E (packed E_k) and sm.beta, forward pass, velocity costates.
+// Returns (uniform over the half-warp) false if a pivot was not positive.  On return sm.xst holds the states
+// x_1..x_N and sm.lam the velocity costates lam^v_1..lam^v_N; sm.E is dead.
 template <int N>
-__device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl, unsigned conbits,
-                         const uint8_t (&sg)[RicInst<N>::ROUNDS], uint8_t (&nsg)[RicInst<N>::ROUNDS]) {
-    using S = RicInst<N>;
-    constexpr int ROUNDS = S::ROUNDS;
-    const double lin = P.dt / P.mass, dt = P.dt;
+__device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl) {
+    const double dt = P.dt;
     RPROF_T0();
-    RPROF_COUNT(0);
-
-    // ---- E_k and beta_k, feet in parallel (4 lanes = the feet of one step)
-#pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int t = hl + 16 * r, k = t >> 2, j = t & 3;
-        Face fc;
-        make_face(P, (conbits >> r) & 1u, sg[r], fc);
-        double A[9];
-        foot_A<N>(P, sm, t, A);
-        double b[3][6], d[3];
-        const double zx = fc.zx ? 1.0 : 0.0, zy = fc.zy ? 1.0 : 0.0, zz = fc.zz ? 1.0 : 0.0;
-        b[0][0] = lin * zx; b[0][1] = 0.0; b[0][2] = 0.0;
-        b[1][0] = 0.0; b[1][1] = lin * zy; b[1][2] = 0.0;
-        b[2][0] = lin * fc.czx * zz; b[2][1] = lin * fc.czy * zz; b[2][2] = lin * zz;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            b[0][3 + q] = A[3 * q] * zx;
-            b[1][3 + q] = A[3 * q + 1] * zy;
-            b[2][3 + q] = (A[3 * q] * fc.czx + A[3 * q + 1] * fc.czy + A[3 * q + 2]) * zz;
-        }
-        d[0] = fc.dx; d[1] = fc.dy; d[2] = fc.dz;
-        int e = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int c = 0; c <= a; ++c, ++e) {
-                double v = d[0] * b[0][a] * b[0][c] + d[1] * b[1][a] * b[1][c] + d[2] * b[2][a] * b[2][c];
-                v += hshfl_xor_d(v, 1);
-                v += hshfl_xor_d(v, 2);
-                if ((e & 3) == j) sm.E[21 * k + e] = v;
-            }
-        double ub[6];
-        bv_apply(A, lin, fc.pf, ub);
-        ub[2] -= (j == 0) ? P.gravity * dt : 0.0;             // g: only the z velocity, MPC.py:200-201
-        hstep_sum_store(ub, sm.beta + 6 * k, j);
-    }
     // ---- terminal cost-to-go: P_N = Q, p_N = -Q xref_N
     {
         RicCost& c0 = sm.cost[(N - 1) & 1];
@@ -445,6 +404,68 @@ __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict_
     }
     __syncwarp();
     RPROF(10);
+    return spd_all;
+}
+
+// E_k = sum_j (Bv Z) R^-1 (Bv Z)' (packed lower triangle) and beta_k = g + sum_j Bv pf for every step, feet in parallel
+// (4 lanes = the feet of one step); face_of(r, t, fc) describes foot-step t = hl + 16 r.
+template <int N, class FaceFn>
+__device__ __forceinline__ void ric_assemble(const DevParams& P, RicInst<N>& sm, int hl, FaceFn face_of) {
+    constexpr int ROUNDS = RicInst<N>::ROUNDS;
+    const double lin = P.dt / P.mass, dt = P.dt;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int t = hl + 16 * r, k = t >> 2, j = t & 3;
+        Face fc;
+        face_of(r, t, fc);
+        double A[9];
+        foot_A<N>(P, sm, t, A);
+        double b[3][6], d[3];
+        const double zx = fc.zx ? 1.0 : 0.0, zy = fc.zy ? 1.0 : 0.0, zz = fc.zz ? 1.0 : 0.0;
+        b[0][0] = lin * zx; b[0][1] = 0.0; b[0][2] = 0.0;
+        b[1][0] = 0.0; b[1][1] = lin * zy; b[1][2] = 0.0;
+        b[2][0] = lin * fc.czx * zz; b[2][1] = lin * fc.czy * zz; b[2][2] = lin * zz;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            b[0][3 + q] = A[3 * q] * zx;
+            b[1][3 + q] = A[3 * q + 1] * zy;
+            b[2][3 + q] = (A[3 * q] * fc.czx + A[3 * q + 1] * fc.czy + A[3 * q + 2]) * zz;
+        }
+        d[0] = fc.dx; d[1] = fc.dy; d[2] = fc.dz;
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int c = 0; c <= a; ++c, ++e) {
+                double v = d[0] * b[0][a] * b[0][c] + d[1] * b[1][a] * b[1][c] + d[2] * b[2][a] * b[2][c];
+                v += hshfl_xor_d(v, 1);
+                v += hshfl_xor_d(v, 2);
+                if ((e & 3) == j) sm.E[21 * k + e] = v;
+            }
+        double ub[6];
+        bv_apply(A, lin, fc.pf, ub);
+        ub[2] -= (j == 0) ? P.gravity * dt : 0.0;             // g: only the z velocity, MPC.py:200-201
+        hstep_sum_store(ub, sm.beta + 6 * k, j);
+    }
+}
+
+// One equality-constrained solve on the faces `sg` selects + KKT guard.  The 16 lanes of the robot call it.
+// Returns (uniform over the half-warp) 1 if every foot passes the guard, 0 if not, -1 if a pivot was not positive.
+// Both halves of the warp must call it together (full-mask collectives inside).
+// On return sm.E holds the forces (3 per foot, foot-major), sm.xst the states, sm.lam the velocity costates.
+template <int N>
+__device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl, unsigned conbits,
+                         const uint8_t (&sg)[RicInst<N>::ROUNDS], uint8_t (&nsg)[RicInst<N>::ROUNDS]) {
+    using S = RicInst<N>;
+    constexpr int ROUNDS = S::ROUNDS;
+    const double lin = P.dt / P.mass;
+    RPROF_T0();
+    RPROF_COUNT(0);
+
+    ric_assemble<N>(P, sm, hl, [&](int r, int, Face& fc) { make_face(P, (conbits >> r) & 1u, sg[r], fc); });
+    __syncwarp();
+    RPROF(1);
+    const bool spd_all = ric_core<N>(P, sm, ws, sub, hl);
     // ---- per foot: forces on the face, gradient, KKT guard
     bool ok = true;
 #pragma unroll
@@ -476,12 +497,91 @@ __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict_
     return !spd_all ? -1 : (all_ok ? 1 : 0);
 }
 
+// Doubles of ADMM state per foot-step in the workspace (struct of arrays): f (3), z (5), y (5)
+constexpr int RIC_ADM = 13;
+
+// One iteration of the ADMM stage in stage-wise form (same splitting as the dense ADMM stage in mpcqp_kernels.cu: OSQP's
+// iteration on the condensed QP  l <= C f <= u  with fixed rho, sigma, alpha).  The x-update
+//     (H + sigma I + rho C'C) ft = sigma f - g + C'(rho z - y),      C'C = diag(2, 2, 4 mu^2 + 1) per foot,
+// is the same LQ problem as a sweep with every stance force free, R = w_f + sigma + rho C'C on the diagonal and the
+// offset pf = R^-1 (sigma f + C'(rho z - y)):  ft = pf - R^-1 Bv' lam.  Then OSQP's relaxed z / y updates per foot.
+// `cur` receives the active set the iterate suggests (OSQP's polish rule).  Returns false if a pivot failed.
+template <int N>
+__device__ bool ric_admm_iter(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, double* __restrict__ adm, int sub, int hl,
+                              unsigned conbits, uint8_t (&cur)[RicInst<N>::ROUNDS]) {
+    constexpr int NF = RicInst<N>::NF, ROUNDS = RicInst<N>::ROUNDS;
+    const double rho = P.rho, sigma = P.sigma, alpha = P.alpha, mu = P.mu, lin = P.dt / P.mass;
+    const double ddx = 1.0 / (P.w_force + sigma + 2.0 * rho), ddz = 1.0 / (P.w_force + sigma + rho * (4.0 * mu * mu + 1.0));
+    auto offset = [&](int t, double (&pf)[3]) {
+        double f[3], z[5], y[5];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f[c] = adm[c * NF + t];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { z[q] = adm[(3 + q) * NF + t]; y[q] = adm[(8 + q) * NF + t]; }
+        const double v0 = rho * z[0] - y[0], v1 = rho * z[1] - y[1], v2 = rho * z[2] - y[2], v3 = rho * z[3] - y[3], v4 = rho * z[4] - y[4];
+        pf[0] = ddx * (sigma * f[0] + (v0 - v1));
+        pf[1] = ddx * (sigma * f[1] + (v2 - v3));
+        pf[2] = ddz * (sigma * f[2] - mu * (v0 + v1 + v2 + v3) - v4);
+    };
+    ric_assemble<N>(P, sm, hl, [&](int r, int t, Face& fc) {
+        const bool live = (conbits >> r) & 1u;
+        fc.zx = fc.zy = fc.zz = live;
+        fc.czx = 0.0; fc.czy = 0.0;
+        fc.dx = live ? ddx : 0.0; fc.dy = fc.dx; fc.dz = live ? ddz : 0.0;
+        fc.pf[0] = fc.pf[1] = fc.pf[2] = 0.0;
+        if (live) offset(t, fc.pf);
+    });
+    __syncwarp();
+    const bool spd_all = ric_core<N>(P, sm, ws, sub, hl);
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int t = hl + 16 * r, k = t >> 2;
+        cur[r] = SIG_FREE;
+        if ((conbits >> r) & 1u) {
+            double A[9], h[3], pf[3], f[3], z[5], y[5];
+            foot_A<N>(P, sm, t, A);
+            bvT_apply(A, lin, sm.lam + 6 * k, h);
+            offset(t, pf);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[c] = adm[c * NF + t];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) { z[q] = adm[(3 + q) * NF + t]; y[q] = adm[(8 + q) * NF + t]; }
+            const double ftx = pf[0] - ddx * h[0], fty = pf[1] - ddx * h[1], ftz = pf[2] - ddz * h[2];
+            const double zt[5] = {ftx - mu * ftz, -ftx - mu * ftz, fty - mu * ftz, -fty - mu * ftz, -ftz};
+            f[0] = alpha * ftx + (1.0 - alpha) * f[0];
+            f[1] = alpha * fty + (1.0 - alpha) * f[1];
+            f[2] = alpha * ftz + (1.0 - alpha) * f[2];
+            bool upp[5], low4 = false;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const double zr = alpha * zt[q] + (1.0 - alpha) * z[q];
+                double zn = fmin(zr + y[q] / rho, 0.0);
+                if (q == 4) zn = fmax(zn, -P.fz_max);
+                y[q] += rho * (zr - zn);
+                z[q] = zn;
+                upp[q] = (0.0 - zn) < y[q];                    // OSQP's polish rule
+                if (q == 4) low4 = (zn + P.fz_max) < -y[q];
+            }
+            const int sx = (upp[0] ? 1 : 0) - (upp[1] ? 1 : 0), sy = (upp[2] ? 1 : 0) - (upp[3] ? 1 : 0);
+            const bool apex = upp[4] || (upp[0] && upp[1]) || (upp[2] && upp[3]);
+            cur[r] = sig_pack(sx, sy, apex ? 1 : (low4 ? 2 : 0));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) adm[c * NF + t] = f[c];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) { adm[(3 + q) * NF + t] = z[q]; adm[(8 + q) * NF + t] = y[q]; }
+        }
+    }
+    __syncwarp();
+    return spd_all;
+}
+
 // Outputs of one robot (the half-warp version of finish() in mpcqp_kernels.cu)                 [MPC.py:432-458]
 // The states are those of the accepted sweep's forward pass (sm.xst), i.e. the dynamics driven by exactly the
 // impulses of the forces returned.
 template <int N>
 __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>& sm, const DevState& st, int inst, int sub, int hl,
-                           unsigned conbits, const uint8_t (&sg)[RicInst<N>::ROUNDS], bool solved, int status, int sweeps, bool commit) {
+                           unsigned conbits, const uint8_t (&sg)[RicInst<N>::ROUNDS], bool solved, int status, int sweeps, int iters,
+                           const double* __restrict__ adm, bool commit) {
     using S = RicInst<N>;
     constexpr int NF = S::NF, ROUNDS = S::ROUNDS, AW = S::AW, CW = S::CW;
     const double lin = P.dt / P.mass;
@@ -518,7 +618,17 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
         FootSol sol;
 #pragma unroll
         for (int q = 0; q < 5; ++q) sol.y[q] = 0.0;
-        if (solved && contact) {
+        if (adm != nullptr && contact) {
+            // ADMM ran out of iterations: its iterate, unpolished (status MPCQP_STATUS_MAX_ITER)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[c] = adm[c * NF + t];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) sol.y[q] = adm[(8 + q) * NF + t];
+            // ... clipped into the friction pyramid, so that even a flagged answer is a force the robot can apply
+            f[2] = fmin(fmax(f[2], 0.0), P.fz_max);
+            f[0] = fmin(fmax(f[0], -P.mu * f[2]), P.mu * f[2]);
+            f[1] = fmin(fmax(f[1], -P.mu * f[2]), P.mu * f[2]);
+        } else if (solved && contact) {
             // multipliers: the guard's closed form on the gradient of the accepted sweep
             f[0] = sm.E[3 * t]; f[1] = sm.E[3 * t + 1]; f[2] = sm.E[3 * t + 2];
             double A[9], h[3];
@@ -563,7 +673,7 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
         st.obj[inst] = part;
         st.status[inst] = status;
         st.sweeps[inst] = sweeps;
-        st.iters[inst] = 0;
+        st.iters[inst] = iters;
         if (SC.enabled && status != 3) scenario_advance(SC, inst, sm.xnext);
     }
 }
@@ -583,7 +693,7 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
     const int sub = lane >> 4, hl = lane & 15;
     const int gwarp = blockIdx.x * RIC_WARPS + warp;
     S& sm = reinterpret_cast<S*>(smem_raw)[warp * 2 + sub];
-    double* ws = ws_g + (size_t)(gwarp * 2 + sub) * RIC_GAIN * N;
+    double* ws = ws_g + (size_t)(gwarp * 2 + sub) * (RIC_GAIN + 4 * RIC_ADM) * N;      // per half-warp: stage gains, then ADMM state
     if (hl == 0) mbar_init(&sm.mbar, 1);
     __syncwarp();
     unsigned int phase = 0;
@@ -718,15 +828,85 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
                 }
             }
         }
-        // a robot the sweeps gave up on goes to the ADMM stage with its carried state untouched
-        const bool pushed = valid && !done && !any_bad && (P.mode & 2);
+        // ---- ADMM stage, stage-wise (MPCQP_MODE_ADMM_STAGEWISE): the robots the sweeps gave up on iterate here, in the same
+        //      warp; every check_every iterations a stable active set is handed to a sweep, accepted only if its guard passes
+        int iters = 0;
+        bool admm_out = false;
+        const bool want_admm = (P.mode & 8) && (P.mode & 2) && valid && !done && !any_bad;
+        if (__any_sync(RIC_FULL, want_admm)) {
+            double* adm = ws + (size_t)RIC_GAIN * N;
+            const double mu = P.mu;
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r) {
+                const int t = hl + 16 * r, k = t >> 2, j = t & 3;
+                double f[3] = {0.0, 0.0, 0.0}, z[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, y[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+                if (warm && ((conbits >> r) & 1u)) {
+                    const int ks = (k + 1 < N) ? k + 1 : 0;                   // MPC.py:403-406
+                    const double* fp = st.f + (size_t)inst * 12 * N + 12 * ks + 3 * j;
+                    const double* yp = st.y + (size_t)inst * 20 * N + 20 * ks + 5 * j;
+                    f[0] = fp[0]; f[1] = fp[1]; f[2] = fp[2];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) y[q] = yp[q];
+                    const double cf[5] = {f[0] - mu * f[2], -f[0] - mu * f[2], f[1] - mu * f[2], -f[1] - mu * f[2], -f[2]};
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) z[q] = fmin(cf[q], 0.0);
+                    z[4] = fmax(z[4], -P.fz_max);
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) adm[c * NF + t] = f[c];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) { adm[(3 + q) * NF + t] = z[q]; adm[(8 + q) * NF + t] = y[q]; }
+            }
+            uint8_t cur[ROUNDS], prev[ROUNDS];
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r) prev[r] = 255;
+            bool astop = false;
+            for (int it = 1; it <= P.max_iter; ++it) {
+                const bool needa = want_admm && !done && !astop;
+                if (!__any_sync(RIC_FULL, needa)) break;
+                const bool spd = ric_admm_iter<N>(P, sm, ws, adm, sub, hl, conbits, cur);
+                if (needa) { ++iters; if (!spd) astop = true; }
+#ifdef RIC_DEBUG
+                if (hl == 0 && it < 14) printf("inst %d sub %d it %d needa %d spd %d astop %d cur0 %d f0z %g\n", inst, sub, it, (int)needa, (int)spd, (int)astop, (int)cur[0], adm[2 * NF]);
+#endif
+                if (it >= P.min_iter && (it % P.check_every) == 0) {
+                    bool same = true;
+#pragma unroll
+                    for (int r = 0; r < ROUNDS; ++r) { same = same && (cur[r] == prev[r]); prev[r] = cur[r]; }
+                    const bool stable = half_all(same, sub);          // a collective: evaluated by every lane, never short-circuited
+                    const bool tryp = needa && !astop && stable;
+                    if (__any_sync(RIC_FULL, tryp)) {
+                        const int rc = ric_sweep<N>(P, sm, ws, sub, hl, conbits, cur, nsg);
+                        if (tryp) {
+                            ++sweeps;
+                            if (rc > 0) {
+                                done = true; status = 1;
+#pragma unroll
+                                for (int r = 0; r < ROUNDS; ++r) sg[r] = cur[r];
+                            }
+                        }
+                    }
+                }
+            }
+            // The iterations above ran on both halves of the warp: a robot that was already solved (or got solved first) had
+            // its sweep results overwritten by the shadow work.  One more sweep on the accepted signatures restores them.
+            ric_sweep<N>(P, sm, ws, sub, hl, conbits, sg, nsg);
+            if (want_admm && !done) {
+                status = 2; admm_out = true;
+#pragma unroll
+                for (int r = 0; r < ROUNDS; ++r) sg[r] = SIG_FREE;
+            }
+        }
+        // a robot the sweeps gave up on goes to the (dense) ADMM stage with its carried state untouched
+        const bool pushed = valid && !done && !any_bad && (P.mode & 2) && !(P.mode & 8);
         if (pushed && hl == 0) {
             const int q = atomicAdd(st.fb_count, 1);
             st.fb_list[q] = inst;
             st.sweeps[inst] = sweeps;
         }
         RPROF(15);
-        ric_finish<N>(P, SC, sm, st, inst, sub, hl, conbits, sg, done, status, sweeps, valid && !pushed);
+        ric_finish<N>(P, SC, sm, st, inst, sub, hl, conbits, sg, done || admm_out, status, sweeps, iters,
+                      admm_out ? ws + (size_t)RIC_GAIN * N : nullptr, valid && !pushed);
         RPROF(16);
     }
 }

@@ -126,10 +126,9 @@ class Engine:
     def __init__(self, batch=1, n_steps=16, device=0, **overrides):
         self.lib = load()
         if int(n_steps) == 64:
-            # horizons beyond 32 steps run on the stage-wise active-set stage alone (the ADMM stage keeps a dense 6N x 6N
-            # factor in shared memory, which stops fitting): more sweeps instead of a fallback
-            overrides.setdefault("mode", 5)
-            overrides.setdefault("max_sweeps", 40)
+            # horizons beyond 32 steps run both stages on the stage-wise factorisation (the dense ADMM stage keeps a
+            # 6N x 6N factor in shared memory, which stops fitting)
+            overrides.setdefault("mode", 15)
         self.params = default_params(batch=int(batch), n_steps=int(n_steps), device=int(device), **overrides)
         self.B, self.N = int(batch), int(n_steps)
         h = C.c_void_p()

@@ -37,8 +37,13 @@ def _active_from_x(g, t, n):
 def test_golden_sequences(path, mode):
     """Replay each golden closed-loop sequence tick by tick (warm start carried like the reference)."""
     g = np.load(path)
-    n = g["x"].shape[1] // 24                       # horizon of this fixture (16, or 32 for the long-horizon case)
-    eng = mpcqp.Engine(batch=1, n_steps=n, mode=mode)
+    n = g["x"].shape[1] // 24                       # horizon of this fixture (16, or 32 / 64 for the long-horizon cases)
+    if n == 64:
+        if mode != 7:
+            pytest.skip("N = 64 runs on the stage-wise active-set stage only")
+        eng = mpcqp.Engine(batch=1, n_steps=n)      # the wrapper's N = 64 default: mode 15 (both stages stage-wise)
+    else:
+        eng = mpcqp.Engine(batch=1, n_steps=n, mode=mode)
     for t in range(len(g["k"])):
         eng.run(g["k"][t], g["xref"][t][None], g["fsteps"][t][None])
         f0, x, info = eng.forces()[0], eng.solution()[0], eng.info()
@@ -112,6 +117,76 @@ def test_long_horizon_closed_loop_certified(mode):
             np.testing.assert_array_equal(cert["contact"].astype(bool), info["contact"][b])
             np.testing.assert_array_equal(cert["active"].reshape(n, 4, 5), info["active"][b])
         sc.advance(x[:, :12] + xref[:, :, 1])
+    eng.close()
+
+
+def test_horizon_64_trot_closed_loop_certified():
+    """BASELINE configs[3], N = 64 (n_periods = 4): both stages on the stage-wise factorisation (no dense ADMM factor fits),
+    16 trot robots x 5 ticks released from rest with moderate commands; oracle certificate on a sample; every robot solved."""
+    from oracle import mpc_build
+    B, T, n = 16, 5, 64
+    eng = mpcqp.Engine(batch=B, n_steps=n)
+    assert eng.params.mode == 15
+    rng = np.random.default_rng(64)
+    v_ref = np.zeros((B, 6))
+    v_ref[:, 0], v_ref[:, 1], v_ref[:, 5] = rng.uniform(-0.2, 0.45, B), rng.uniform(-0.15, 0.15, B), rng.uniform(-0.3, 0.3, B)
+    sc = Scenario(B, n_steps=n, gaits=["trot"], seed=64, v_ref=v_ref)
+    par = mpc_build.Params(n_steps=n)
+    for t in range(T):
+        xref, fsteps = sc.inputs()
+        eng.run(t, xref, fsteps)
+        x, info = eng.solution(), eng.info()
+        assert (info["status"] == 1).all(), (t, info["status"], info["sweeps"], info["iters"])
+        for b in (0, 7):
+            cert = certify(xref[b], fsteps[b], x[b], info["y"][b], first_tick=(t == 0), params=par)
+            assert_certified(cert, "N=64 tick %d robot %d" % (t, b))
+            np.testing.assert_array_equal(cert["contact"].astype(bool), info["contact"][b])
+        sc.advance(x[:, :12] + xref[:, :, 1])
+    eng.close()
+
+
+def test_stagewise_admm_stage_is_the_dense_admm_stage():
+    """MPCQP_MODE_ADMM_STAGEWISE runs the same splitting as the dense ADMM stage on the stage-wise factorisation: with the
+    active-set sweeps switched off (max_sweeps = 0) both engines must take the same number of ADMM iterations and polish
+    attempts, robot by robot, and land on the same optimum (cold and warm ticks, mixed gaits, odd batch)."""
+    B = 9
+    sc = Scenario(B, gaits=["trot", "walk", "bound"], seed=5)
+    dense, sw = mpcqp.Engine(batch=B, mode=2), mpcqp.Engine(batch=B, mode=15, max_sweeps=0)
+    for t in range(4):
+        xref, fsteps = sc.inputs()
+        dense.run(t, xref, fsteps)
+        sw.run(t, xref, fsteps)
+        xd, xs, idn, isw = dense.solution(), sw.solution(), dense.info(), sw.info()
+        assert (idn["status"] == 1).all() and (isw["status"] == 1).all()
+        np.testing.assert_array_equal(idn["iters"], isw["iters"])
+        np.testing.assert_array_equal(idn["sweeps"], isw["sweeps"])
+        assert np.abs(xd - xs).max() <= 1e-8
+        np.testing.assert_array_equal(idn["active"], isw["active"])
+        sc.advance(xd[:, :12] + xref[:, :, 1])
+    dense.close(); sw.close()
+
+
+def test_hard_long_horizon_instances_are_flagged_not_wrong():
+    """N = 64 released from rest with a 1 m/s command is close to bang-bang (most stance foot-steps at the apex or at fz_max,
+    degenerate multipliers): robots neither stage can certify within the iteration cap must come back flagged
+    MPCQP_STATUS_MAX_ITER with finite forces inside the friction pyramid; the certified ones must pass the oracle's check."""
+    from oracle import mpc_build
+    B, n = 8, 64
+    v_ref = np.zeros((B, 6))
+    v_ref[:, 0] = np.linspace(0.7, 1.0, B)
+    sc = Scenario(B, n_steps=n, gaits=["trot"], seed=3, v_ref=v_ref)
+    eng = mpcqp.Engine(batch=B, n_steps=n, max_iter=60)
+    xref, fsteps = sc.inputs()
+    eng.run(0, xref, fsteps)
+    x, info = eng.solution(), eng.info()
+    assert np.isfinite(x).all() and set(np.unique(info["status"])) <= {1, 2}
+    f = x[:, 12 * n:].reshape(B, n, 4, 3)
+    mu = eng.params.mu
+    assert (np.abs(f[..., 0]) <= mu * f[..., 2] + 1e-9).all() and (np.abs(f[..., 1]) <= mu * f[..., 2] + 1e-9).all()
+    assert (f[..., 2] >= 0).all() and (f[..., 2] <= 25).all() and (info["status"] == 2).any()
+    par = mpc_build.Params(n_steps=n)
+    for b in np.flatnonzero(info["status"] == 1)[:2]:
+        assert_certified(certify(xref[b], fsteps[b], x[b], info["y"][b], first_tick=True, params=par), "robot %d" % b)
     eng.close()
 
 
