@@ -10,6 +10,8 @@ import numpy as np
 
 HOST, DEVICE = 0, 1
 MODE_ACTIVE_SET, MODE_ADMM = 1, 2
+MODE_STAGEWISE = 4           # active-set stage on the stage-wise (Riccati) factorisation, half a warp per robot
+MODE_ADMM_STAGEWISE = 8      # ADMM stage on the stage-wise factorisation too (any horizon)
 STATUS = {0: "unsolved", 1: "solved", 2: "max_iter", 3: "bad_input"}
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmpcqp.so")

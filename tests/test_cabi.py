@@ -32,7 +32,7 @@ def test_params_layout_matches_header():
     assert (p.n_steps, p.dt, p.T_gait, p.mu, p.fz_max) == (16, 0.02, 0.32, 0.9, 25.0)
     assert abs(p.mass - 2.50000279) < 1e-15 and abs(p.gI[4] - 5.106100e-2) < 1e-18
     assert abs(p.w_state[6] - 2 * 0.1 ** 0.5) < 1e-15 and p.w_force == 1e-5
-    assert p.mode == mpcqp.MODE_ACTIVE_SET | mpcqp.MODE_ADMM
+    assert p.mode == mpcqp.MODE_ACTIVE_SET | mpcqp.MODE_ADMM | mpcqp.MODE_STAGEWISE and p.max_sweeps == 12
     assert b"sm_100a" in mpcqp.load().mpcqp_version()
 
 
