@@ -195,6 +195,59 @@ def flops_stagewise_fixed(N=N_STEPS):
     return feet * 40 + N * 30 + 12 * N * 4 + feet * 40   # decode, inertia blocks, outputs/objective, multipliers
 
 
+def sweep_main(args, torch, mpcqp, Scenario, rank, local_rank, world, dist, barrier, max_over_ranks, sum_over_ranks):
+    """BASELINE configs[4] shape: a closed-loop scenario sweep that never leaves the GPU.  Every tick plans footsteps and
+    the reference trajectory, builds and solves the QP and integrates the centroidal state, per robot, inside one kernel
+    (mpcqp_scenario_run).  `value` times K ticks back to back; `e2e` runs the same ticks one C-ABI call at a time and reads
+    every robot's state back to pinned host memory after each tick."""
+    B, K, W = args.batch, args.steps, max(args.warmup, 3) + max(args.settle, 0)
+    gaits = ["trot"] if args.workload == "sweep" else ["trot", "pace", "bound", "walk"]
+    sc = Scenario(B, gaits=gaits, seed=4242 + rank, noise_kind="hash")
+    eng = mpcqp.Engine(batch=B, device=local_rank, mode=args.mode)
+    eng.scenario_init(sc)
+    eng.scenario_run(W)
+    eng.synchronize()
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = eng.launches
+    e0.record(stream)
+    eng.scenario_run(K)
+    e1.record(stream)
+    eng.synchronize()
+    barrier()
+    launches = eng.launches - l0
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    info = eng.info(with_y=False)
+    unsolved = int((info["status"] != 1).sum())
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(K):
+        eng.scenario_run(1)
+        st = eng.scenario_state()
+    e2e_s = max_over_ranks(time.perf_counter() - w0)
+    clocks = sampler.stop()
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC.replace("Solo trot", "closed-loop sweep"), "value": world * B * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[4] shape: device-resident closed-loop sweep, %d robots per GPU, gaits %s, N=16: footstep "
+                                   "planner + QP build + solve + centroidal state integration per tick inside the solve kernel, seeded "
+                                   "counter-based state noise" % (B, "/".join(gaits)),
+                       "instances_per_gpu": B, "settle_ticks": max(args.settle, 0), "l2": "no inputs: the planner runs in the kernel; carried state %.0f MB" % (B * 6.5e-3)},
+            "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": B * 23 * 8,
+                    "ms_per_step": 1e3 * e2e_s / K, "what": "one mpcqp_scenario_run(1) + mpcqp_scenario_get per tick (states, frames, feet to the host)"},
+            "gpu_launches": int(launches), "clocks": clocks, "unsolved_instances_last_tick": unsolved,
+            "sweeps_per_solve_last_tick": float(info["sweeps"].mean()), "fallback_frac_last_tick": float((info["iters"] > 0).mean()),
+            "state_checksum": float(np.abs(st["state"]).sum())}))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,6 +258,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", type=int, default=7, help="solver stages (include/mpcqp.h MPCQP_MODE_*): 7 = stage-wise active set + ADMM fallback (default), 3 = dense")
     ap.add_argument("--cpu-ticks", type=int, default=100)
+    ap.add_argument("--workload", default="trot", choices=["trot", "sweep", "mixed-sweep"],
+                    help="trot = BASELINE configs[1] (the headline line, default); sweep / mixed-sweep = device-resident closed-loop "
+                         "scenario sweep (configs[4] shape: planner + QP + state integration per tick on the GPU, trot or mixed gaits)")
     ap.add_argument("--settle", type=int, default=20,
                     help="closed-loop ticks run (untimed) before the warm-up so that the timed ticks are steady-state "
                          "operation, not the cold-start transient of robots released from rest")
@@ -245,6 +301,9 @@ def main():
         t = torch.tensor([v], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
+
+    if args.workload != "trot":
+        return sweep_main(args, torch, mpcqp, Scenario, rank, local_rank, world, dist, barrier, max_over_ranks, sum_over_ranks)
 
     B, N, K = args.batch, N_STEPS, args.steps
     W = max(args.warmup, 3) + max(args.settle, 0)       # untimed ticks: settle + warm-up
