@@ -66,9 +66,18 @@ template <int N>
 cudaError_t configure_stagewise(int* ctas_per_sm) {
     cudaError_t e;
     const int smem = (int)(RIC_PER_CTA * sizeof(RicInst<N>));
-    if ((e = cudaFuncSetAttribute(riccati_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    if ((e = cudaFuncSetAttribute(riccati_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, riccati_kernel<N>, 32 * RIC_WARPS, smem);
+    if (N != 64) {
+        if ((e = cudaFuncSetAttribute(riccati_kernel<(N == 64 ? 16 : N), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+        if ((e = cudaFuncSetAttribute(riccati_kernel<(N == 64 ? 16 : N), false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
+    }
+    if ((e = cudaFuncSetAttribute(riccati_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(riccati_kernel<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
+    int a = 0, b = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, riccati_kernel<(N == 64 ? 16 : N), false>, 32 * RIC_WARPS, N == 64 ? (int)(RIC_PER_CTA * sizeof(RicInst<16>)) : smem))) return e;
+    if (N == 64) a = 1 << 30;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, riccati_kernel<N, true>, 32 * RIC_WARPS, smem))) return e;
+    *ctas_per_sm = a < b ? a : b;
+    return cudaSuccess;
 }
 
 template <int N>
@@ -76,7 +85,11 @@ void launch_stagewise(int n_inst, int max_ctas, cudaStream_t s, const DevParams&
                       const double* dx, const double* df, double* ws, int first, int off) {
     int grid = (n_inst + RIC_PER_CTA - 1) / RIC_PER_CTA;
     if (grid > max_ctas) grid = max_ctas;                      // persistent: one workspace slot per resident half-warp
-    riccati_kernel<N><<<grid, 32 * RIC_WARPS, RIC_PER_CTA * sizeof(RicInst<N>), s>>>(dp, st, sc, dx, df, ws, first, off, n_inst);
+    if ((dp.mode & MPCQP_MODE_ADMM_STAGEWISE) || N == 64)       // N = 64: one instance only (build time), the stage is a run-time flag
+        riccati_kernel<N, true><<<grid, 32 * RIC_WARPS, RIC_PER_CTA * sizeof(RicInst<N>), s>>>(dp, st, sc, dx, df, ws, first, off, n_inst);
+    else
+        riccati_kernel<(N == 64 ? 16 : N), false><<<grid, 32 * RIC_WARPS, RIC_PER_CTA * sizeof(RicInst<N>), s>>>(
+            dp, st, sc, dx, df, ws, first, off, n_inst);
 }
 
 template <int N>

@@ -678,11 +678,12 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
     }
 }
 
-// The active-set stage, stage-wise factorisation.  Persistent grid: the two robots 2 m, 2 m + 1 of the launch are
+// The active-set stage, stage-wise factorisation (SWADMM: with the stage-wise ADMM stage compiled in; the default mode runs the
+// instance without it, whose code is a quarter of the size).  Persistent grid: the two robots 2 m, 2 m + 1 of the launch are
 // solved by the two halves of warp (m mod warps), warps = RIC_WARPS * gridDim.x; `ws` holds RIC_GAIN * N doubles per
 // half-warp.  The halves share one instruction stream: control flow is warp-uniform, a half that has nothing (left)
 // to do shadows the computation with its stores masked.
-template <int N>
+template <int N, bool SWADMM>
 __global__ void __launch_bounds__(32 * RIC_WARPS)
 riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g,
                double* __restrict__ ws_g, int first_tick, int inst_offset, int inst_count) {
@@ -832,8 +833,8 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
         //      warp; every check_every iterations a stable active set is handed to a sweep, accepted only if its guard passes
         int iters = 0;
         bool admm_out = false;
-        const bool want_admm = (P.mode & 8) && (P.mode & 2) && valid && !done && !any_bad;
-        if (__any_sync(RIC_FULL, want_admm)) {
+        const bool want_admm = SWADMM && (P.mode & 8) && (P.mode & 2) && valid && !done && !any_bad;
+        if (SWADMM && __any_sync(RIC_FULL, want_admm)) {
             double* adm = ws + (size_t)RIC_GAIN * N;
             const double mu = P.mu;
 #pragma unroll
