@@ -62,34 +62,34 @@ cudaError_t configure_kernels() {
     return cudaFuncSetAttribute(solve_kernel<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-template <int N>
-cudaError_t configure_stagewise(int* ctas_per_sm) {
-    cudaError_t e;
-    const int smem = (int)(RIC_PER_CTA * sizeof(RicInst<N>));
-    if (N != 64) {
-        if ((e = cudaFuncSetAttribute(riccati_kernel<(N == 64 ? 16 : N), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-        if ((e = cudaFuncSetAttribute(riccati_kernel<(N == 64 ? 16 : N), false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
-    }
-    if ((e = cudaFuncSetAttribute(riccati_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    if ((e = cudaFuncSetAttribute(riccati_kernel<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
-    int a = 0, b = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, riccati_kernel<(N == 64 ? 16 : N), false>, 32 * RIC_WARPS, N == 64 ? (int)(RIC_PER_CTA * sizeof(RicInst<16>)) : smem))) return e;
-    if (N == 64) a = 1 << 30;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, riccati_kernel<N, true>, 32 * RIC_WARPS, smem))) return e;
-    *ctas_per_sm = a < b ? a : b;
-    return cudaSuccess;
-}
+// Stage-wise solver: one translation unit per horizon (mpcqp_ric_inst.cu); in a single-TU build (profiling) they are included here.
+#ifdef MPCQP_SINGLE_TU
+#include "mpcqp_riccati.cuh"
+#define RIC_N 16
+#include "mpcqp_ric_inst.cu"
+#define RIC_N 32
+#include "mpcqp_ric_inst.cu"
+#define RIC_N 64
+#include "mpcqp_ric_inst.cu"
+#else
+#include "mpcqp_ric_consts.h"
+#endif
+namespace mpcqp {
+#define RIC_DECL(N)                                                                                                   \
+    cudaError_t ric_configure_##N(int* ctas_per_sm);                                                                  \
+    void ric_launch_##N(int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,      \
+                        const double* dx, const double* df, double* ws, int first, int off, int n_inst);
+RIC_DECL(16) RIC_DECL(32) RIC_DECL(64)
+#undef RIC_DECL
+}  // namespace mpcqp
 
-template <int N>
-void launch_stagewise(int n_inst, int max_ctas, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
+void launch_stagewise(int N, int n_inst, int max_ctas, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
                       const double* dx, const double* df, double* ws, int first, int off) {
     int grid = (n_inst + RIC_PER_CTA - 1) / RIC_PER_CTA;
     if (grid > max_ctas) grid = max_ctas;                      // persistent: one workspace slot per resident half-warp
-    if ((dp.mode & MPCQP_MODE_ADMM_STAGEWISE) || N == 64)       // N = 64: one instance only (build time), the stage is a run-time flag
-        riccati_kernel<N, true><<<grid, 32 * RIC_WARPS, RIC_PER_CTA * sizeof(RicInst<N>), s>>>(dp, st, sc, dx, df, ws, first, off, n_inst);
-    else
-        riccati_kernel<(N == 64 ? 16 : N), false><<<grid, 32 * RIC_WARPS, RIC_PER_CTA * sizeof(RicInst<N>), s>>>(
-            dp, st, sc, dx, df, ws, first, off, n_inst);
+    if (N == 16) ric_launch_16(grid, s, dp, st, sc, dx, df, ws, first, off, n_inst);
+    else if (N == 32) ric_launch_32(grid, s, dp, st, sc, dx, df, ws, first, off, n_inst);
+    else ric_launch_64(grid, s, dp, st, sc, dx, df, ws, first, off, n_inst);
 }
 
 template <int N>
@@ -130,9 +130,7 @@ struct mpcqp_handle {
             // active-set stage on the stage-wise factorisation: half a warp per robot, persistent grid; every stream
             // that may run it concurrently has its own gain workspace
             double* ws = d_ric_ws + (size_t)(s == side[0] ? 1 : (s == side[1] ? 2 : 0)) * ric_ws_doubles;
-            if (p.n_steps == 16) launch_stagewise<16>(n, ric_max_ctas, s, dp, st, use, dx, df, ws, first, off);
-            else if (p.n_steps == 32) launch_stagewise<32>(n, ric_max_ctas, s, dp, st, use, dx, df, ws, first, off);
-            else launch_stagewise<64>(n, ric_max_ctas, s, dp, st, use, dx, df, ws, first, off);
+            launch_stagewise(p.n_steps, n, ric_max_ctas, s, dp, st, use, dx, df, ws, first, off);
         } else if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         else launch_solve<32>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         ++launches;
@@ -327,9 +325,9 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     h->st.sig = (uint8_t*)(base + o_sig);
     CUH(cudaMemset(h->st.sig, SIG_FREE, (size_t)B * 4 * N));
     int ric_per_sm = 0;
-    if (N == 16) { CUH(configure_kernels<16>()); CUH(configure_stagewise<16>(&ric_per_sm)); }
-    else if (N == 32) { CUH(configure_kernels<32>()); CUH(configure_stagewise<32>(&ric_per_sm)); }
-    else { CUH(configure_stagewise<64>(&ric_per_sm)); }
+    if (N == 16) { CUH(configure_kernels<16>()); CUH(ric_configure_16(&ric_per_sm)); }
+    else if (N == 32) { CUH(configure_kernels<32>()); CUH(ric_configure_32(&ric_per_sm)); }
+    else { CUH(ric_configure_64(&ric_per_sm)); }
     if (p->mode & MPCQP_MODE_STAGEWISE) {
         if (ric_per_sm < 1) return bail(fail(MPCQP_ERR_CUDA, "the stage-wise kernel does not fit on this device"));
         h->ric_max_ctas = ric_per_sm * h->sms;

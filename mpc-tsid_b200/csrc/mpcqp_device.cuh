@@ -149,7 +149,7 @@ __device__ MPCQP_TILE_FN double2 syrk_sum(const double* __restrict__ rowI, const
 // (rsqrt, scale, rank-1 update: no shuffle or memory hop between dependent steps); lane c < 8 then
 // builds column c of the inverse by forward substitution.  Kept out of line so that its 36-double
 // working set does not inflate the register allocation of the tile loop around it.
-__device__ __noinline__ void diag_factor_invert(double* __restrict__ D, int lane, int* __restrict__ flag) {
+static __device__ __noinline__ void diag_factor_invert(double* __restrict__ D, int lane, int* __restrict__ flag) {
     double L[36];                                       // packed lower triangle
 #pragma unroll
     for (int r = 0; r < 8; ++r)

@@ -53,7 +53,7 @@ __device__ __forceinline__ void bvT_apply(const double A[9], double lin, const d
 
 // sum a 6-vector over the four feet of a step (lanes 4k..4k+3) and let lane j == 0 store it.
 // Out of line (code size): called from every per-foot phase.
-__device__ __noinline__ void step_sum_store6(double v0, double v1, double v2, double v3, double v4, double v5, double* dst, int j) {
+static __device__ __noinline__ void step_sum_store6(double v0, double v1, double v2, double v3, double v4, double v5, double* dst, int j) {
     v0 += shfl_xor_d(v0, 1); v1 += shfl_xor_d(v1, 1); v2 += shfl_xor_d(v2, 1);
     v3 += shfl_xor_d(v3, 1); v4 += shfl_xor_d(v4, 1); v5 += shfl_xor_d(v5, 1);
     v0 += shfl_xor_d(v0, 2); v1 += shfl_xor_d(v1, 2); v2 += shfl_xor_d(v2, 2);

@@ -653,4 +653,3 @@ __global__ void peak_dmma_kernel(double* out, int iters, double a, double b) {
 
 }  // namespace mpcqp
 
-#include "mpcqp_riccati.cuh"

@@ -45,12 +45,9 @@
 
 namespace mpcqp {
 
-constexpr int RIC_GAIN = 84;        // workspace doubles per stage: 6 impulse components x 14 (13 coefficients + pad)
-#ifndef MPCQP_RIC_WARPS
-#define MPCQP_RIC_WARPS 1
-#endif
-constexpr int RIC_WARPS = MPCQP_RIC_WARPS;      // warps per CTA
-constexpr int RIC_PER_CTA = 2 * RIC_WARPS;      // robots per CTA
+}  // namespace mpcqp
+#include "mpcqp_ric_consts.h"
+namespace mpcqp {
 constexpr int RIC_DEPTH = 4;        // stages of gains the forward pass keeps in flight from the workspace
 
 // cost-to-go of one stage, row major 6x6 blocks (double-buffered: stage k reads one, writes the other)
@@ -497,8 +494,6 @@ __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict_
     return !spd_all ? -1 : (all_ok ? 1 : 0);
 }
 
-// Doubles of ADMM state per foot-step in the workspace (struct of arrays): f (3), z (5), y (5)
-constexpr int RIC_ADM = 13;
 
 // One iteration of the ADMM stage in stage-wise form (same splitting as the dense ADMM stage in mpcqp_kernels.cu: OSQP's
 // iteration on the condensed QP  l <= C f <= u  with fixed rho, sigma, alpha).  The x-update
