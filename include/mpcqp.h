@@ -150,6 +150,19 @@ int mpcqp_scenario_run(mpcqp_handle* h, int ticks, int emit_inputs);
 int mpcqp_scenario_get(mpcqp_handle* h, double* state /*B x 12*/, double* frame /*B x 3*/, double* feet /*B x 8*/);
 int mpcqp_get_inputs(mpcqp_handle* h, double* xref, double* fsteps);
 
+/* ---- logger-facing outputs ------------------------------------------------------------
+ * Logger.log_cost_function (Logger.py:406-418): cost[B x 13], cost_i = sum over the horizon of x_i P_i x_i for the 12 state
+ * components, cost_12 = the same over all forces.  (MPC.x_robot, Logger.py:455-461, is mpcqp_get_solution + xref.) */
+int mpcqp_get_cost_components(mpcqp_handle* h, double* cost, int location);
+
+/* ---- asynchronous result protocol (replaces the reference's unfinished process-based wrapper,
+ * MPC_Wrapper.py:116-260): after mpcqp_run, mpcqp_result_async(h, slot) enqueues the copy of the B x 12 forces into the
+ * handle's pinned slot 0 or 1 and returns immediately; mpcqp_result_wait(h, slot, forces) blocks until THAT copy has
+ * landed.  Alternating the slots lets a control loop apply the forces of tick k-1 while tick k is being solved. */
+int mpcqp_result_async(mpcqp_handle* h, int slot);
+int mpcqp_result_ready(mpcqp_handle* h, int slot);      /* 1 landed, 0 in flight, < 0 error; never blocks */
+int mpcqp_result_wait(mpcqp_handle* h, int slot, double* forces);
+
 /* Measured FP64 peak of the device in TFLOP/s (DMMA m8n8k4 issue loop), for roofline reporting. */
 int mpcqp_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);
 

@@ -108,6 +108,23 @@ class MPC:
         self.status = None
         return 0
 
+    def run_async(self, k, xref, fsteps, slot):
+        """Enqueue one tick and the copy of its forces into the engine's pinned slot; returns without waiting.
+        Used by MPC_Wrapper's asynchronous mode; the caller owns xref / fsteps until the result has been collected."""
+        xref = np.asarray(xref, dtype=np.float64)
+        fsteps = np.asarray(fsteps, dtype=np.float64)
+        batched = xref.ndim == 3
+        xb = xref if batched else xref[None]
+        fb = fsteps if batched else fsteps[None]
+        if xb.shape[1:] != (12, self.n_steps + 1) or fb.shape[1:] != (20, 13) or fb.shape[0] != xb.shape[0]:
+            raise ValueError("xref must be ([B,] 12, %d) and fsteps ([B,] 20, 13)" % (self.n_steps + 1))
+        if self._engine is None or self._engine.B != xb.shape[0]:
+            self._make_engine(xb.shape[0])
+        self._batched = batched
+        self._engine.run(float(k), np.array(xb), np.array(fb))      # private copies: the planner reuses its arrays
+        self._engine.result_async(slot)
+        return 0
+
     @property
     def info(self):
         """Per-instance solver diagnostics of the last run (status, sweeps, iters, obj, masks, y)."""

@@ -117,6 +117,10 @@ struct mpcqp_handle {
     int64_t launches = 0;
     int sms = 0;
 
+    double* pin[2] = {nullptr, nullptr};            // asynchronous result slots (pinned host memory)
+    cudaEvent_t ev_pin[2] = {nullptr, nullptr};
+    bool pin_valid[2] = {false, false};
+
     DevScenario sc;                 // device-resident closed loop (disabled unless mpcqp_scenario_init was called)
     void* d_scen = nullptr;
     int scen_tick = 0;
@@ -200,6 +204,10 @@ int mpcqp_destroy(mpcqp_handle* h) {
     cudaFree(h->d_block);
     cudaFree(h->d_scen);
     cudaFree(h->d_ric_ws);
+    for (int i = 0; i < 2; ++i) {
+        if (h->pin[i]) cudaFreeHost(h->pin[i]);
+        if (h->ev_pin[i]) cudaEventDestroy(h->ev_pin[i]);
+    }
     for (int i = 0; i < 2; ++i) {
         if (h->side[i]) cudaStreamDestroy(h->side[i]);
         if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
@@ -648,6 +656,64 @@ int mpcqp_get_inputs(mpcqp_handle* h, double* xref, double* fsteps) {
     CU(cudaMemcpyAsync(xref, h->d_xref, B * 12 * (N + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(fsteps, h->d_fsteps, B * 260 * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return MPCQP_OK;
+}
+
+// Logger.log_cost_function (Logger.py:406-418) for every robot of the last run: cost is B x 13 (12 state components, forces)
+int mpcqp_get_cost_components(mpcqp_handle* h, double* cost, int location) {
+    if (!h || !cost) return fail(MPCQP_ERR_INVALID, "null argument");
+    if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
+    if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "location must be MPCQP_HOST or MPCQP_DEVICE");
+    CU(cudaSetDevice(h->p.device));
+    const size_t B = h->p.batch, bytes = B * 13 * sizeof(double);
+    double* d = cost;
+    if (location == MPCQP_HOST) CU(cudaMalloc(&d, bytes));
+    cost_components_kernel<<<(int)((B + 3) / 4), 128, 0, h->stream>>>(h->dp, h->st, h->p.n_steps, d);
+    ++h->launches;
+    CU(cudaGetLastError());
+    if (location == MPCQP_HOST) {
+        CU(cudaMemcpyAsync(cost, d, bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(d);
+    }
+    return MPCQP_OK;
+}
+
+// ---- asynchronous result protocol (the reference's intent in MPC_Wrapper.py:116-260: the control loop
+// picks up the forces of the PREVIOUS solve while the current one runs).  mpcqp_result_async enqueues the copy of the forces
+// of the run just issued into pinned slot 0 / 1 and returns at once; mpcqp_result_wait blocks on that slot only.
+int mpcqp_result_async(mpcqp_handle* h, int slot) {
+    if (!h || slot < 0 || slot > 1) return fail(MPCQP_ERR_INVALID, "bad argument");
+    if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
+    CU(cudaSetDevice(h->p.device));
+    const size_t bytes = (size_t)h->p.batch * 12 * sizeof(double);
+    if (!h->pin[slot]) {
+        CU(cudaMallocHost(&h->pin[slot], bytes));
+        CU(cudaEventCreateWithFlags(&h->ev_pin[slot], cudaEventDisableTiming));
+    }
+    CU(cudaMemcpyAsync(h->pin[slot], h->st.f0, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev_pin[slot], h->stream));
+    h->pin_valid[slot] = true;
+    return MPCQP_OK;
+}
+
+// 1 if the copy requested in `slot` has landed, 0 if it is still in flight (never blocks)
+int mpcqp_result_ready(mpcqp_handle* h, int slot) {
+    if (!h || slot < 0 || slot > 1) return fail(MPCQP_ERR_INVALID, "bad argument");
+    if (!h->pin_valid[slot]) return 0;
+    cudaSetDevice(h->p.device);
+    const cudaError_t e = cudaEventQuery(h->ev_pin[slot]);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+    return fail(MPCQP_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(e));
+}
+
+int mpcqp_result_wait(mpcqp_handle* h, int slot, double* forces) {
+    if (!h || !forces || slot < 0 || slot > 1) return fail(MPCQP_ERR_INVALID, "bad argument");
+    if (!h->pin_valid[slot]) return fail(MPCQP_ERR_STATE, "no result was requested in this slot");
+    CU(cudaSetDevice(h->p.device));
+    CU(cudaEventSynchronize(h->ev_pin[slot]));
+    std::memcpy(forces, h->pin[slot], (size_t)h->p.batch * 12 * sizeof(double));
     return MPCQP_OK;
 }
 

@@ -627,6 +627,30 @@ __global__ void export_build_kernel(DevParams P, const double* __restrict__ xref
 }
 
 // -------------------------------------------------------------------------------------------------
+// Logger-facing output: contribution of each state component and of the forces to the
+// cost over the horizon, cost_i = sum_k x_i P_i x_i (Logger.log_cost_function, Logger.py:406-418; no 1/2).
+// One warp per robot; cost is B x 13.
+// -------------------------------------------------------------------------------------------------
+__global__ void cost_components_kernel(DevParams P, DevState st, int N, double* __restrict__ cost) {
+    const int robot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (robot >= P.batch) return;
+    const double* xs = st.xs + (size_t)robot * 12 * N;
+    const double* f = st.f + (size_t)robot * 12 * N;
+    double acc = 0.0;                                   // lanes 0..11: state component `lane`; lanes 12..31: forces
+    if (lane < 12) {
+        const double w = lane < 6 ? P.wp[lane] : P.wv[lane - 6];
+        for (int k = 0; k < N; ++k) { const double e = xs[12 * k + lane]; acc = fma(w * e, e, acc); }
+    } else {
+        for (int i = lane - 12; i < 12 * N; i += 20) acc = fma(P.w_force * f[i], f[i], acc);
+    }
+    double fsum = lane >= 12 ? acc : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, o);
+    if (lane < 12) cost[(size_t)robot * 13 + lane] = acc;
+    if (lane == 12) cost[(size_t)robot * 13 + 12] = fsum;
+}
+
+// -------------------------------------------------------------------------------------------------
 // FP64 peak probes (roofline denominators; MEASURED_PEAKS.json has no FP64 entry)
 // -------------------------------------------------------------------------------------------------
 __global__ void peak_dfma_kernel(double* out, int iters, double a, double b) {

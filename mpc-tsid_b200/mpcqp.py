@@ -23,6 +23,7 @@ EXPORTS = (
     "mpcqp_synchronize", "mpcqp_stream", "mpcqp_launch_count", "mpcqp_export_build",
     "mpcqp_measure_fp64_peak", "mpcqp_last_error", "mpcqp_version",
     "mpcqp_scenario_init", "mpcqp_scenario_run", "mpcqp_scenario_get", "mpcqp_get_inputs",
+    "mpcqp_get_cost_components", "mpcqp_result_async", "mpcqp_result_ready", "mpcqp_result_wait",
 )
 
 
@@ -79,6 +80,10 @@ def load():
     lib.mpcqp_scenario_run.argtypes = [vp, C.c_int, C.c_int]
     lib.mpcqp_scenario_get.argtypes = [vp, dp, dp, dp]
     lib.mpcqp_get_inputs.argtypes = [vp, dp, dp]
+    lib.mpcqp_get_cost_components.argtypes = [vp, dp, C.c_int]
+    lib.mpcqp_result_async.argtypes = [vp, C.c_int]
+    lib.mpcqp_result_ready.argtypes = [vp, C.c_int]
+    lib.mpcqp_result_wait.argtypes = [vp, C.c_int, dp]
     lib.mpcqp_last_error.restype = C.c_char_p
     lib.mpcqp_version.restype = C.c_char_p
     _lib = lib
@@ -225,6 +230,27 @@ class Engine:
         xref, fsteps = np.empty((self.B, 12, self.N + 1)), np.empty((self.B, 20, 13))
         _check(self.lib.mpcqp_get_inputs(self._h, _ptr(xref), _ptr(fsteps)))
         return xref, fsteps
+
+    def cost_components(self):
+        """Logger.log_cost_function (Logger.py:406-418) per robot: (B, 13)."""
+        out = np.empty((self.B, 13))
+        _check(self.lib.mpcqp_get_cost_components(self._h, _ptr(out), HOST))
+        return out
+
+    def result_async(self, slot):
+        """Enqueue the copy of the forces of the run just issued into pinned slot 0 / 1; returns at once."""
+        _check(self.lib.mpcqp_result_async(self._h, int(slot)))
+
+    def result_ready(self, slot):
+        rc = self.lib.mpcqp_result_ready(self._h, int(slot))
+        if rc < 0:
+            _check(rc)
+        return bool(rc)
+
+    def result_wait(self, slot, out=None):
+        out = np.empty((self.B, 12)) if out is None else out
+        _check(self.lib.mpcqp_result_wait(self._h, int(slot), _ptr(out)))
+        return out
 
     def reset_warm_start(self):
         _check(self.lib.mpcqp_reset_warm_start(self._h))

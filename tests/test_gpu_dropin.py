@@ -56,7 +56,44 @@ def test_wrapper_and_virtual_batched():
     assert (info["status"] == 1).all()
 
 
-def test_async_flag_matches_reference_behaviour():
+def test_asynchronous_wrapper_pipeline():
+    """multiprocessing=True is a stream pipeline here (the reference's process-based version is dead code,
+    MPC_Wrapper.py:48-51, 116-260).  solve() returns without waiting; get_latest_result() never blocks and hands out the
+    newest forces that have arrived; after wait() they are those of the last tick, equal to the synchronous wrapper's."""
     import MPC_Wrapper
-    with pytest.raises(NotImplementedError):
-        MPC_Wrapper.MPC_Wrapper(0.02, 16, 20, 0.32, multiprocessing=True)
+    g = np.load(os.path.join(G, "solve_trot.npz"))
+    sync = MPC_Wrapper.MPC_Wrapper(0.02, 16, 20, 0.32, multiprocessing=False)
+    asyn = MPC_Wrapper.MPC_Wrapper(0.02, 16, 20, 0.32, multiprocessing=True)
+    seen = []
+    for t in range(10):
+        planner = _Planner(g["xref"][t], g["fsteps"][t])
+        sync.solve(20 * t, planner)
+        fs = sync.get_latest_result()
+        if t == 0:
+            fs = sync.get_latest_result()
+        assert asyn.solve(20 * t, planner) == 0
+        fa = asyn.get_latest_result()                       # tick 0: the reference's [0, 0, 8] x 4; later: whatever has landed
+        if t == 0:
+            np.testing.assert_array_equal(fa, np.array([0.0, 0.0, 8.0] * 4))
+        assert fa.shape == (12,) and np.isfinite(fa).all()
+        seen.append(fa.copy())
+        fw = asyn.wait()                                    # everything issued so far has landed
+        assert np.abs(fw - fs).max() <= 1e-9, t
+        assert np.abs(fw - g["f_applied"][t]).max() <= FORCE_TOL
+    # the non-blocking answers are always forces of SOME earlier-or-current tick
+    for t, fa in enumerate(seen[1:], start=1):
+        assert min(np.abs(fa - g["f_applied"][u]).max() for u in range(t + 1)) <= FORCE_TOL
+
+
+def test_logger_cost_components():
+    """Logger.log_cost_function (Logger.py:406-418) on the device, against its numpy formula on MPC.x."""
+    import MPC
+    g = np.load(os.path.join(G, "solve_walk.npz"))
+    m = MPC.MPC(0.02, 16, 0.32)
+    m.run(0, g["xref"][:3], g["fsteps"][:3])                # three robots at once
+    cost = m._engine.cost_components()
+    P = m.P.data
+    for b in range(3):
+        c = m.x[b] * P * m.x[b]                             # diag(x) diag(P) x
+        ref = np.array([c[i:12 * 16:12].sum() for i in range(12)] + [c[12 * 16:].sum()])
+        np.testing.assert_allclose(cost[b], ref, rtol=1e-12, atol=1e-15)
