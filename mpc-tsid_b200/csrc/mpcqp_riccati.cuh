@@ -410,7 +410,7 @@ template <int N, class FaceFn>
 __device__ __forceinline__ void ric_assemble(const DevParams& P, RicInst<N>& sm, int hl, FaceFn face_of) {
     constexpr int ROUNDS = RicInst<N>::ROUNDS;
     const double lin = P.dt / P.mass, dt = P.dt;
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < ROUNDS; ++r) {
         const int t = hl + 16 * r, k = t >> 2, j = t & 3;
         Face fc;
@@ -465,7 +465,7 @@ __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict_
     const bool spd_all = ric_core<N>(P, sm, ws, sub, hl);
     // ---- per foot: forces on the face, gradient, KKT guard
     bool ok = true;
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < ROUNDS; ++r) {
         const int t = hl + 16 * r, k = t >> 2;
         const bool contact = (conbits >> r) & 1u;
@@ -528,7 +528,7 @@ __device__ bool ric_admm_iter(const DevParams& P, RicInst<N>& sm, double* __rest
     });
     __syncwarp();
     const bool spd_all = ric_core<N>(P, sm, ws, sub, hl);
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < ROUNDS; ++r) {
         const int t = hl + 16 * r, k = t >> 2;
         cur[r] = SIG_FREE;
@@ -605,7 +605,7 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
         part = fma(0.5 * (c < 6 ? P.wp[c] : P.wv[c - 6]) * ee, ee, part);
     }
     if (hl < 12) sm.xnext[hl] = sm.xst[hl];                                                  // MPC.q_next / v_next (MPC.py:448-450)
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < ROUNDS; ++r) {
         const int t = hl + 16 * r, k = t >> 2, j = t & 3;
         const bool contact = (conbits >> r) & 1u;
@@ -718,7 +718,7 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
         bool bad = false;
         unsigned conbits = 0u;
         uint8_t sg[ROUNDS], nsg[ROUNDS];
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < ROUNDS; ++r) {
             const int t = hl + 16 * r, k = t >> 2, j = t & 3;
             double lv[3];
@@ -748,13 +748,13 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
         if (any_bad) {
             status = 3;
             conbits = 0u;
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < ROUNDS; ++r) sg[r] = SIG_FREE;
         }
         // order-sensitive hash of a signature, uniform over the half-warp (cycle detection)
         auto sig_hash = [&](const uint8_t (&g)[ROUNDS]) {
             unsigned long long h = 0ull;
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < ROUNDS; ++r) {
                 if ((conbits >> r) & 1u) {
                     unsigned long long q = (unsigned long long)(g[r] + 1) * 0x9E3779B97F4A7C15ull;
@@ -795,7 +795,7 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
             if (search && !careful) {
                 if (seen(hfull)) careful = true;
                 else {
-#pragma unroll
+#pragma unroll 1
                     for (int r = 0; r < ROUNDS; ++r) sg[r] = nsg[r];
                     search = false;
                 }
@@ -803,7 +803,7 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
             int tlast = -1;
             while (__any_sync(RIC_FULL, search)) {
                 int tm = 0x7fffffff;
-#pragma unroll
+#pragma unroll 1
                 for (int r = 0; r < ROUNDS; ++r) {
                     const int t = hl + 16 * r;
                     if (nsg[r] != sg[r] && t > tlast && t < tm) tm = t;
@@ -811,13 +811,13 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) { const int q = __shfl_xor_sync(RIC_FULL, tm, o, 16); tm = q < tm ? q : tm; }
                 uint8_t cand[ROUNDS];
-#pragma unroll
+#pragma unroll 1
                 for (int r = 0; r < ROUNDS; ++r) cand[r] = (hl + 16 * r == tm) ? nsg[r] : sg[r];
                 const unsigned long long hc = sig_hash(cand);
                 if (search) {
                     if (tm == 0x7fffffff) { stop = true; search = false; }            // every single change was tried before
                     else if (!seen(hc)) {
-#pragma unroll
+#pragma unroll 1
                         for (int r = 0; r < ROUNDS; ++r) sg[r] = cand[r];
                         search = false;
                     } else tlast = tm;
@@ -832,7 +832,7 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
         if (SWADMM && __any_sync(RIC_FULL, want_admm)) {
             double* adm = ws + (size_t)RIC_GAIN * N;
             const double mu = P.mu;
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < ROUNDS; ++r) {
                 const int t = hl + 16 * r, k = t >> 2, j = t & 3;
                 double f[3] = {0.0, 0.0, 0.0}, z[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, y[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -854,7 +854,7 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
                 for (int q = 0; q < 5; ++q) { adm[(3 + q) * NF + t] = z[q]; adm[(8 + q) * NF + t] = y[q]; }
             }
             uint8_t cur[ROUNDS], prev[ROUNDS];
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < ROUNDS; ++r) prev[r] = 255;
             bool astop = false;
             for (int it = 1; it <= P.max_iter; ++it) {
@@ -867,7 +867,7 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
 #endif
                 if (it >= P.min_iter && (it % P.check_every) == 0) {
                     bool same = true;
-#pragma unroll
+#pragma unroll 1
                     for (int r = 0; r < ROUNDS; ++r) { same = same && (cur[r] == prev[r]); prev[r] = cur[r]; }
                     const bool stable = half_all(same, sub);          // a collective: evaluated by every lane, never short-circuited
                     const bool tryp = needa && !astop && stable;
@@ -877,7 +877,7 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
                             ++sweeps;
                             if (rc > 0) {
                                 done = true; status = 1;
-#pragma unroll
+#pragma unroll 1
                                 for (int r = 0; r < ROUNDS; ++r) sg[r] = cur[r];
                             }
                         }
@@ -889,7 +889,7 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
             ric_sweep<N>(P, sm, ws, sub, hl, conbits, sg, nsg);
             if (want_admm && !done) {
                 status = 2; admm_out = true;
-#pragma unroll
+#pragma unroll 1
                 for (int r = 0; r < ROUNDS; ++r) sg[r] = SIG_FREE;
             }
         }

@@ -6,7 +6,7 @@ O=gpurun_out
 mkdir -p $O
 python bench.py --steps 50 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err || { tail -20 $O/${TAG}_bench.err; exit 1; }
 cat $O/${TAG}_bench.json
-if [ -f mpc-tsid_b200/libmpcqp_prof.so ]; then python tools/dev_ric_profile.py 4096 24 2>&1 | tail -3 > $O/${TAG}_phases.txt; cat $O/${TAG}_phases.txt; fi
+
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 4 --warmup 3 --settle 14 --no-cpu-baseline > $O/${TAG}_ncu_list.log 2>&1
 # launches of riccati_kernel: 2 per tick of the (host-input, chunked) generation loop = 42, then one per device-resident tick;
