@@ -80,6 +80,7 @@ struct alignas(16) RicInst {
     unsigned long long hist[16];        // hashes of the signatures already tried
     unsigned long long mbar;
     unsigned int amask[AW + CW];
+    uint8_t sigb[NF];                   // per foot-step: signature of the sweep being assembled | contact << 7
     static_assert(21 * N >= 260 && 21 * N >= 12 * N, "union sizing");
     static_assert(18 * N * 8 >= sizeof(ScenarioSmem), "union sizing");
 };
@@ -404,45 +405,59 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
     return spd_all;
 }
 
-// E_k = sum_j (Bv Z) R^-1 (Bv Z)' (packed lower triangle) and beta_k = g + sum_j Bv pf for every step, feet in parallel
-// (4 lanes = the feet of one step); face_of(r, t, fc) describes foot-step t = hl + 16 r.
+// E_k = sum_j (Bv Z) R^-1 (Bv Z)' (packed lower triangle) and beta_k = g + sum_j Bv pf for every step.  One lane per step
+// (lane hl owns steps hl, hl + 16, ...), the four feet of a step in sequence, no shuffles: with S = Z R^-1 Z' (3x3, a
+// closed form of the face) and Bv = [lin I; A],  E = [[lin^2 S, lin (A S)'], [lin A S, A S A']].
+// face_of(t, fc) describes foot-step t; it must not depend on which lane asks.
 template <int N, class FaceFn>
 __device__ __forceinline__ void ric_assemble(const DevParams& P, RicInst<N>& sm, int hl, FaceFn face_of) {
-    constexpr int ROUNDS = RicInst<N>::ROUNDS;
-    const double lin = P.dt / P.mass, dt = P.dt;
+    const double lin = P.dt / P.mass, lin2 = lin * lin;
 #pragma unroll 1
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int t = hl + 16 * r, k = t >> 2, j = t & 3;
-        Face fc;
-        face_of(r, t, fc);
-        double A[9];
-        foot_A<N>(P, sm, t, A);
-        double b[3][6], d[3];
-        const double zx = fc.zx ? 1.0 : 0.0, zy = fc.zy ? 1.0 : 0.0, zz = fc.zz ? 1.0 : 0.0;
-        b[0][0] = lin * zx; b[0][1] = 0.0; b[0][2] = 0.0;
-        b[1][0] = 0.0; b[1][1] = lin * zy; b[1][2] = 0.0;
-        b[2][0] = lin * fc.czx * zz; b[2][1] = lin * fc.czy * zz; b[2][2] = lin * zz;
+    for (int k = hl; k < N; k += 16) {
+        double e[21], ub[6];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            b[0][3 + q] = A[3 * q] * zx;
-            b[1][3 + q] = A[3 * q + 1] * zy;
-            b[2][3 + q] = (A[3 * q] * fc.czx + A[3 * q + 1] * fc.czy + A[3 * q + 2]) * zz;
-        }
-        d[0] = fc.dx; d[1] = fc.dy; d[2] = fc.dz;
-        int e = 0;
+        for (int i = 0; i < 21; ++i) e[i] = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
+        for (int i = 0; i < 6; ++i) ub[i] = 0.0;
+        ub[2] = -P.gravity * P.dt;                             // g: only the z velocity, MPC.py:200-201
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int t = 4 * k + j;
+            Face fc;
+            face_of(t, fc);
+            double A[9];
+            foot_A<N>(P, sm, t, A);
+            const double S[6] = {fc.dx + fc.dz * fc.czx * fc.czx, fc.dz * fc.czx * fc.czy, fc.dy + fc.dz * fc.czy * fc.czy,
+                                 fc.dz * fc.czx, fc.dz * fc.czy, fc.dz};      // S00, S10, S11, S20, S21, S22
+            double M[9];                                       // M = A S
 #pragma unroll
-            for (int c = 0; c <= a; ++c, ++e) {
-                double v = d[0] * b[0][a] * b[0][c] + d[1] * b[1][a] * b[1][c] + d[2] * b[2][a] * b[2][c];
-                v += hshfl_xor_d(v, 1);
-                v += hshfl_xor_d(v, 2);
-                if ((e & 3) == j) sm.E[21 * k + e] = v;
+            for (int q = 0; q < 3; ++q) {
+                M[3 * q + 0] = A[3 * q] * S[0] + A[3 * q + 1] * S[1] + A[3 * q + 2] * S[3];
+                M[3 * q + 1] = A[3 * q] * S[1] + A[3 * q + 1] * S[2] + A[3 * q + 2] * S[4];
+                M[3 * q + 2] = A[3 * q] * S[3] + A[3 * q + 1] * S[4] + A[3 * q + 2] * S[5];
             }
-        double ub[6];
-        bv_apply(A, lin, fc.pf, ub);
-        ub[2] -= (j == 0) ? P.gravity * dt : 0.0;             // g: only the z velocity, MPC.py:200-201
-        hstep_sum_store(ub, sm.beta + 6 * k, j);
+            e[RIC_TI(0, 0)] = fma(lin2, S[0], e[RIC_TI(0, 0)]);
+            e[RIC_TI(1, 0)] = fma(lin2, S[1], e[RIC_TI(1, 0)]);
+            e[RIC_TI(1, 1)] = fma(lin2, S[2], e[RIC_TI(1, 1)]);
+            e[RIC_TI(2, 0)] = fma(lin2, S[3], e[RIC_TI(2, 0)]);
+            e[RIC_TI(2, 1)] = fma(lin2, S[4], e[RIC_TI(2, 1)]);
+            e[RIC_TI(2, 2)] = fma(lin2, S[5], e[RIC_TI(2, 2)]);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) e[RIC_TI(3 + q, c)] = fma(lin, M[3 * q + c], e[RIC_TI(3 + q, c)]);
+#pragma unroll
+                for (int c = 0; c <= q; ++c)
+                    e[RIC_TI(3 + q, 3 + c)] += M[3 * q] * A[3 * c] + M[3 * q + 1] * A[3 * c + 1] + M[3 * q + 2] * A[3 * c + 2];
+            }
+            double u6[6];
+            bv_apply(A, lin, fc.pf, u6);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) ub[i] += u6[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 21; ++i) sm.E[21 * k + i] = e[i];
+        store_row6(sm.beta + 6 * k, ub);
     }
 }
 
@@ -459,7 +474,10 @@ __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict_
     RPROF_T0();
     RPROF_COUNT(0);
 
-    ric_assemble<N>(P, sm, hl, [&](int r, int, Face& fc) { make_face(P, (conbits >> r) & 1u, sg[r], fc); });
+#pragma unroll 1
+    for (int r = 0; r < ROUNDS; ++r) sm.sigb[hl + 16 * r] = (uint8_t)(sg[r] | (((conbits >> r) & 1u) << 7));
+    __syncwarp();
+    ric_assemble<N>(P, sm, hl, [&](int t, Face& fc) { const uint8_t sb = sm.sigb[t]; make_face(P, (sb >> 7) != 0, sb & 127, fc); });
     __syncwarp();
     RPROF(1);
     const bool spd_all = ric_core<N>(P, sm, ws, sub, hl);
@@ -518,8 +536,11 @@ __device__ bool ric_admm_iter(const DevParams& P, RicInst<N>& sm, double* __rest
         pf[1] = ddx * (sigma * f[1] + (v2 - v3));
         pf[2] = ddz * (sigma * f[2] - mu * (v0 + v1 + v2 + v3) - v4);
     };
-    ric_assemble<N>(P, sm, hl, [&](int r, int t, Face& fc) {
-        const bool live = (conbits >> r) & 1u;
+#pragma unroll 1
+    for (int r = 0; r < ROUNDS; ++r) sm.sigb[hl + 16 * r] = (uint8_t)(((conbits >> r) & 1u) << 7);
+    __syncwarp();
+    ric_assemble<N>(P, sm, hl, [&](int t, Face& fc) {
+        const bool live = (sm.sigb[t] >> 7) != 0;
         fc.zx = fc.zy = fc.zz = live;
         fc.czx = 0.0; fc.czy = 0.0;
         fc.dx = live ? ddx : 0.0; fc.dy = fc.dx; fc.dz = live ? ddz : 0.0;
