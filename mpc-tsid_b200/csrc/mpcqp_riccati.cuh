@@ -68,9 +68,12 @@ struct alignas(16) RicInst {
     };
     double lev[3 * NF];                 // lever arms foothold - xref[0:3, k], struct of arrays
     double Ii[9 * N];                   // inv(R_z(yaw_k) gI) per step, row major
-    double beta[6 * N];                 // ubar_k + g
     union {
-        struct { double xst[12 * N]; double lam[6 * N]; };    // states x_1..x_N of the forward pass, velocity costates
+        double beta[6 * N];             // ubar_k + g (dead once the forward pass is done)
+        double lam[6 * N];              // velocity costates lam^v_1..lam^v_N (written by the costate pass that follows it)
+    };
+    union {
+        double xst[12 * N];             // states x_1..x_N of the forward pass
         ScenarioSmem sc;                // planner scratch of the device-resident closed loop (dead after the inputs exist)
     };
     RicCost cost[2];
@@ -82,7 +85,7 @@ struct alignas(16) RicInst {
     unsigned int amask[AW + CW];
     uint8_t sigb[NF];                   // per foot-step: signature of the sweep being assembled | contact << 7
     static_assert(21 * N >= 260 && 21 * N >= 12 * N, "union sizing");
-    static_assert(18 * N * 8 >= sizeof(ScenarioSmem), "union sizing");
+    static_assert(12 * N * 8 >= sizeof(ScenarioSmem), "union sizing");
 };
 
 #define RIC_TI(r, c) ((r) * ((r) + 1) / 2 + (c))
