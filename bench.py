@@ -183,7 +183,7 @@ def flops_stagewise_sweep(N=N_STEPS):
     assemble_p = 21 * 2 + 36 * 2 + 21 * 5 + 12 * 3
     stage = chol + t_g + rows + wpart + assemble_p
     feet = 4 * N
-    e_beta = feet * (21 * 6 + 27 + 18 + 12)          # lever block, B Z columns, 21 entries, impulse of pf
+    e_beta = feet * (18 + 8 + 45 + 66 + 15)          # lever block, S = Z R^-1 Z', A S, the 21 entries, impulse of pf
     forward = N * (12 * 2 + 6 * 13 * 2 + 6)
     costate = N * 6 * 6
     per_foot = feet * (18 + 18 + 12 + 12 + 20)       # lever block, Bv' lam, face solve, gradient, guard
