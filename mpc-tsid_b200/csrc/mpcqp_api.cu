@@ -78,18 +78,19 @@ namespace mpcqp {
 #define RIC_DECL(N)                                                                                                   \
     cudaError_t ric_configure_##N(int* ctas_per_sm);                                                                  \
     void ric_launch_##N(int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,      \
-                        const double* dx, const double* df, double* ws, int first, int off, int n_inst);
+                        const double* dx, const double* df, double* ws, int* ctr, int first, int off, int n_inst);
 RIC_DECL(16) RIC_DECL(32) RIC_DECL(64)
 #undef RIC_DECL
 }  // namespace mpcqp
 
 void launch_stagewise(int N, int n_inst, int max_ctas, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
-                      const double* dx, const double* df, double* ws, int first, int off) {
+                      const double* dx, const double* df, double* ws, int* ctr, int first, int off) {
     int grid = (n_inst + RIC_PER_CTA - 1) / RIC_PER_CTA;
     if (grid > max_ctas) grid = max_ctas;                      // persistent: one workspace slot per resident half-warp
-    if (N == 16) ric_launch_16(grid, s, dp, st, sc, dx, df, ws, first, off, n_inst);
-    else if (N == 32) ric_launch_32(grid, s, dp, st, sc, dx, df, ws, first, off, n_inst);
-    else ric_launch_64(grid, s, dp, st, sc, dx, df, ws, first, off, n_inst);
+    cudaMemsetAsync(ctr, 0, sizeof(int), s);                   // the kernel's work counter (pairs of robots beyond the first per warp)
+    if (N == 16) ric_launch_16(grid, s, dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
+    else if (N == 32) ric_launch_32(grid, s, dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
+    else ric_launch_64(grid, s, dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
 }
 
 template <int N>
@@ -133,8 +134,9 @@ struct mpcqp_handle {
         if (!admm && (p.mode & MPCQP_MODE_STAGEWISE)) {
             // active-set stage on the stage-wise factorisation: half a warp per robot, persistent grid; every stream
             // that may run it concurrently has its own gain workspace
-            double* ws = d_ric_ws + (size_t)(s == side[0] ? 1 : (s == side[1] ? 2 : 0)) * ric_ws_doubles;
-            launch_stagewise(p.n_steps, n, ric_max_ctas, s, dp, st, use, dx, df, ws, first, off);
+            const int lane_of_stream = s == side[0] ? 1 : (s == side[1] ? 2 : 0);
+            double* ws = d_ric_ws + (size_t)lane_of_stream * ric_ws_doubles;
+            launch_stagewise(p.n_steps, n, ric_max_ctas, s, dp, st, use, dx, df, ws, st.fb_count + 1 + lane_of_stream, first, off);
         } else if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         else launch_solve<32>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         ++launches;

@@ -32,16 +32,16 @@ cudaError_t RIC_CAT(ric_configure_, RIC_N)(int* ctas_per_sm) {
 
 // N = 64 builds the instance with the stage-wise ADMM stage only (build time); the stage itself is a run-time flag
 void RIC_CAT(ric_launch_, RIC_N)(int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc, const double* dx,
-                                 const double* df, double* ws, int first, int off, int n_inst) {
+                                 const double* df, double* ws, int* ctr, int first, int off, int n_inst) {
     constexpr int N = RIC_N;
     const size_t smem = RIC_PER_CTA * sizeof(RicInst<N>);
 #if RIC_N != 64
     if (!(dp.mode & 8)) {
-        riccati_kernel<N, false><<<grid, 32 * RIC_WARPS, smem, s>>>(dp, st, sc, dx, df, ws, first, off, n_inst);
+        riccati_kernel<N, false><<<grid, 32 * RIC_WARPS, smem, s>>>(dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
         return;
     }
 #endif
-    riccati_kernel<N, true><<<grid, 32 * RIC_WARPS, smem, s>>>(dp, st, sc, dx, df, ws, first, off, n_inst);
+    riccati_kernel<N, true><<<grid, 32 * RIC_WARPS, smem, s>>>(dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
 }
 
 }  // namespace mpcqp

@@ -697,6 +697,7 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
     }
 }
 
+// `work_ctr` must be zero at launch.
 // The active-set stage, stage-wise factorisation (SWADMM: with the stage-wise ADMM stage compiled in; the default mode runs the
 // instance without it, whose code is a quarter of the size).  Persistent grid: the two robots 2 m, 2 m + 1 of the launch are
 // solved by the two halves of warp (m mod warps), warps = RIC_WARPS * gridDim.x; `ws` holds RIC_GAIN * N doubles per
@@ -705,7 +706,7 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
 template <int N, bool SWADMM>
 __global__ void __launch_bounds__(32 * RIC_WARPS)
 riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g,
-               double* __restrict__ ws_g, int first_tick, int inst_offset, int inst_count) {
+               double* __restrict__ ws_g, int* __restrict__ work_ctr, int first_tick, int inst_offset, int inst_count) {
     using S = RicInst<N>;
     constexpr int NF = S::NF, ROUNDS = S::ROUNDS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -717,7 +718,10 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
     if (hl == 0) mbar_init(&sm.mbar, 1);
     __syncwarp();
     unsigned int phase = 0;
-    for (int w0 = gwarp * 2; w0 < inst_count; w0 += gridDim.x * RIC_PER_CTA) {
+    // Work distribution: every warp takes its first pair of robots by position and every further pair from a counter, so a
+    // warp whose robots needed a second sweep does not also hold up the robots a static schedule would queue behind them.
+    for (int w0 = gwarp * 2; w0 < inst_count;
+         w0 = gridDim.x * RIC_PER_CTA + __shfl_sync(RIC_FULL, lane == 0 ? atomicAdd(work_ctr, 2) : 0, 0)) {
         const bool valid = w0 + sub < inst_count;
         const int inst = inst_offset + (valid ? w0 + sub : w0);     // an idle half shadows its neighbour, stores masked
         __syncwarp();
