@@ -377,7 +377,8 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
     // Host inputs: the batch is cut into chunks of two full waves (2 x 4 CTAs x #SM instances); chunk
     // c is copied and solved on side stream c & 1, so the H2D copy of one chunk overlaps the solve of
     // the previous one and the two solve kernels fill each other's tails.
-    const int chunk = (h->p.mode & MPCQP_MODE_STAGEWISE) ? h->wave() : 2 * h->wave();
+    int chunk = (h->p.mode & MPCQP_MODE_STAGEWISE) ? h->wave() : 2 * h->wave();
+    if (const char* e = std::getenv("MPCQP_CHUNK")) { const int c = std::atoi(e); if (c > 0) chunk = c; }      // tuning hook
     if (location == MPCQP_HOST) {
         dx = h->d_xref; df = h->d_fsteps;
         if (stageA && B > chunk) {

@@ -241,6 +241,7 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
         load_row6(rho, prow ? cin.Ppv + 6 * ri : (vrow ? cin.Pvv + 6 * ri : cin.pv));
 #pragma unroll
         for (int q = 0; q < 6; ++q) er[q] = Ek[ie[q]];
+        RPROF(17);
         spd = chol6_regs(L, Li) && spd;
         RPROF(2);
         // (2) row ri of T = E L -> shared memory;  y = rho L^-T

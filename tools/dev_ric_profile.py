@@ -22,5 +22,5 @@ for t in range(T):
     if t >= T - 3:
         print("tick %d sweeps/inst %.2f | per sweep: %s | per stage backward %.0f | per instance: load %.0f decode %.0f sweeps %.0f finish %.0f" % (
             t, info["sweeps"].mean(), "  ".join("%s %.0f" % (n, v[1 + i] / ns) for i, n in enumerate(sw)), sum(v[2:9]) / ns / N,
-            v[13] / ni, v[14] / ni, v[15] / ni, v[16] / ni))
+            v[13] / ni, v[14] / ni, v[15] / ni, v[16] / ni) + "  stage-top loads %.0f per stage" % (v[17] / ns / N))
     sc.advance(x[:, :12] + xr[:, :, 1])
