@@ -364,6 +364,19 @@ static int stage_inputs(mpcqp_handle* h, const double* xref, const double* fstep
     return MPCQP_OK;
 }
 
+// Host -> device copy of `n` gait tables (20 x 13 doubles each).  A table ends at its first row whose step count is 0
+// (MPC.py:646); the reference's tables use 2 .. 7 of the 20 rows, the rest is NaN padding.  If row 7 of every table in the
+// batch has a zero count, only rows 0..7 travel (832 of 2080 bytes per robot, one strided copy): the device never reads
+// past a table's terminator, so what an earlier tick left in rows 8..19 does not matter.  One read per robot decides.
+static cudaError_t copy_gait_tables(double* dst, const double* src, size_t n, cudaStream_t s) {
+    constexpr size_t ROW = 13, TABLE = 260, PROBE = 7;
+    bool brief = true;
+    for (size_t b = 0; b < n && brief; ++b) brief = src[b * TABLE + PROBE * ROW] == 0.0;
+    if (!brief) return cudaMemcpyAsync(dst, src, n * TABLE * sizeof(double), cudaMemcpyHostToDevice, s);
+    return cudaMemcpy2DAsync(dst, TABLE * sizeof(double), src, TABLE * sizeof(double), (PROBE + 1) * ROW * sizeof(double), n,
+                             cudaMemcpyHostToDevice, s);
+}
+
 int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fsteps, int location) {
     if (!h || !xref || !fsteps) return fail(MPCQP_ERR_INVALID, "null argument");
     if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "location must be MPCQP_HOST or MPCQP_DEVICE");
@@ -389,7 +402,7 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
                 const int n = B - off < chunk ? B - off : chunk;
                 cudaStream_t s = h->side[c & 1];
                 CU(cudaMemcpyAsync(h->d_xref + off * xs, xref + off * xs, n * xs * sizeof(double), cudaMemcpyHostToDevice, s));
-                CU(cudaMemcpyAsync(h->d_fsteps + off * fs, fsteps + off * fs, n * fs * sizeof(double), cudaMemcpyHostToDevice, s));
+                CU(copy_gait_tables(h->d_fsteps + off * fs, fsteps + off * fs, n, s));
                 h->solve(false, n, s, dx, df, first, off, n);
             }
             for (int i = 0; i < 2; ++i) {
@@ -398,7 +411,7 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
             }
         } else {
             CU(cudaMemcpyAsync(h->d_xref, xref, B * xs * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-            CU(cudaMemcpyAsync(h->d_fsteps, fsteps, B * fs * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            CU(copy_gait_tables(h->d_fsteps, fsteps, B, h->stream));
             if (stageA) h->solve(false, B, h->stream, dx, df, first, 0, B);
         }
     } else if (stageA) {

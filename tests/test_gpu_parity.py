@@ -242,6 +242,49 @@ def test_edge_cases():
     eng.close(); solo.close()
 
 
+def test_long_gait_tables_take_the_full_copy_path():
+    """Host inputs: when row 7 of every gait table is a terminator only rows 0..7 are copied to the device; a table that uses
+    more rows (here 9 phases) must switch the whole batch to the full copy.  Same answers as the oracle either way, and the
+    stale rows a long table leaves on the device must not leak into the next (short-table) tick."""
+    B = 3
+    sc = Scenario(B, gaits=["trot", "walk", "pace"], seed=8)
+    eng = mpcqp.Engine(batch=B)
+    for t in range(4):
+        xref, fsteps = sc.inputs()
+        if t in (1, 2):
+            # robot 0: cut its table into 9 single- or double-step phases with the same contacts (equivalent QP, longer table)
+            rows = []
+            for r in range(20):
+                c = int(fsteps[0, r, 0])
+                if c == 0:
+                    break
+                for _ in range(c):
+                    rows.append(fsteps[0, r, 1:].copy())
+            phases = []                                    # [count, row]: at most 1 step per phase for the first four, then 2
+            for row in rows:
+                cap = 1 if len(phases) <= 4 else 2
+                if phases and phases[-1][0] < cap and np.array_equal(np.isnan(row), np.isnan(phases[-1][1])):
+                    phases[-1][0] += 1
+                else:
+                    phases.append([1, row])
+            assert 9 <= len(phases) <= 19
+            tab = np.full((20, 13), np.nan)
+            tab[:, 0] = 0.0
+            for r, (c, row) in enumerate(phases):
+                tab[r, 0] = c
+                tab[r, 1:] = row
+            fsteps = fsteps.copy()
+            fsteps[0] = tab
+            assert fsteps[0, 7, 0] != 0.0
+        eng.run(t, xref, fsteps)
+        x, info = eng.solution(), eng.info()
+        assert (info["status"] == 1).all()
+        for b in range(B):
+            assert_certified(certify(xref[b], fsteps[b], x[b], info["y"][b], first_tick=(t == 0)), "tick %d robot %d" % (t, b))
+        sc.advance(x[:, :12] + xref[:, :, 1])
+    eng.close()
+
+
 def test_full_batch_properties():
     """BASELINE configs[1] size (4096 robots): determinism, warm-start invariance, KKT on a sample,
     friction / unilateral / fz_max feasibility everywhere, objective consistent with x."""
