@@ -9,8 +9,12 @@ from scenario import Scenario
 import torch
 mode = int(sys.argv[2]); Bt = int(sys.argv[3]) if len(sys.argv) > 3 else 4096; N = int(sys.argv[4]) if len(sys.argv) > 4 else 16
 kw = dict(n_steps=N) if N != 16 else {}
+if os.environ.get("VREF_SCALE"):
+    rng = np.random.default_rng(1); sc_ = float(os.environ["VREF_SCALE"])
+    v = np.zeros((Bt, 6)); v[:, 0] = rng.uniform(-0.5, 1.0, Bt) * sc_; v[:, 1] = rng.uniform(-0.3, 0.3, Bt) * sc_; v[:, 5] = rng.uniform(-0.4, 0.4, Bt) * sc_
+    kw["v_ref"] = v
 sc = Scenario(Bt, gaits="trot", seed=20260, **kw)
-eng = mpcqp.Engine(batch=Bt, n_steps=N, mode=mode)
+eng = mpcqp.Engine(batch=Bt, n_steps=N, mode=mode, **({"max_iter": int(os.environ["MAX_ITER"])} if os.environ.get("MAX_ITER") else {}))
 Tt = 40
 xs, fs = [], []
 for t in range(Tt):
