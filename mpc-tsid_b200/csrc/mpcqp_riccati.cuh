@@ -747,6 +747,13 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
         bool bad = false;
         unsigned conbits = 0u;
         uint8_t sg[ROUNDS], nsg[ROUNDS];
+        // warm start: the previous tick's signatures advanced by one step (MPC.py:403-406); all loads in flight at once
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int t = hl + 16 * r, k = t >> 2, j = t & 3, ks = (k + 1 < N) ? k + 1 : 0;
+            const uint8_t s8 = warm ? st.sig[(size_t)inst * NF + 4 * ks + j] : SIG_FREE;
+            sg[r] = s8 > 26 ? SIG_FREE : s8;
+        }
 #pragma unroll 1
         for (int r = 0; r < ROUNDS; ++r) {
             const int t = hl + 16 * r, k = t >> 2, j = t & 3;
@@ -755,12 +762,7 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
             decode_lever<N>(P, sm.xr, sm.fs, k, j, first_tick != 0, lv, contact, bad);
             sm.lev[t] = lv[0]; sm.lev[NF + t] = lv[1]; sm.lev[2 * NF + t] = lv[2];
             conbits |= contact ? (1u << r) : 0u;
-            sg[r] = SIG_FREE;
-            if (warm && contact) {
-                const int ks = (k + 1 < N) ? k + 1 : 0;
-                const uint8_t s8 = st.sig[(size_t)inst * NF + 4 * ks + j];
-                sg[r] = s8 > 26 ? SIG_FREE : s8;
-            }
+            if (!contact) sg[r] = SIG_FREE;
         }
         for (int k = hl; k < N; k += 16) {
             double Ii[9];
