@@ -136,7 +136,6 @@ class Engine:
             # horizons beyond 32 steps run both stages on the stage-wise factorisation (the dense ADMM stage keeps a
             # 6N x 6N factor in shared memory, which stops fitting)
             overrides.setdefault("mode", 15)
-            overrides.setdefault("max_iter", 60)     # a stage-wise ADMM iteration is a whole N-stage recursion: cap the safeguard
         self.params = default_params(batch=int(batch), n_steps=int(n_steps), device=int(device), **overrides)
         self.B, self.N = int(batch), int(n_steps)
         h = C.c_void_p()
