@@ -392,7 +392,7 @@ def main():
                 + flops_per_tick(0, tot_iters, tot_fb) - flops_per_tick(0, 0, 0))
         peak, peak_name = peaks["dfma_tflops"], "FP64 FMA"
         kernel = "riccati_kernel<16> (+ dense ADMM fallback kernel for the robots the sweeps give up on)"
-        traffic = 26.92e6 * B / 4096.0
+        traffic = 29.09e6 * B / 4096.0
         traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum of one riccati_kernel<16> launch at 4096 robots, ncu --set full "
                        "(profiles/r01_riccati_kernel_ncu_summary.txt), scaled to this batch")
         model = "engine's own count, DESIGN.md section 5: sweeps*%.0f + %.0f per solve (+ fallback work)" % (
