@@ -19,13 +19,16 @@
 //   per foot: h = Bv' lam^v_{k+1},  q = -R^-1 Z' h,  f = pf + Z q,  grad = w_f f + h   (= H f + g of the
 //   condensed problem), then the same KKT guard as the dense path (mpcqp_foot.cuh).
 // Mapping to the machine.  The path is bound by the latency of the two 6x6 pivot chains per stage, so the
-// design maximises the number of robots in flight per SM: 16 lanes per robot (two robots per warp, every
-// collective on the half-warp's own mask), 12 KB of shared memory per robot, the per-stage gains (the only
-// O(N) state of the recursion that must survive until the forward pass) in an L2-resident workspace.
+// design maximises the number of robots in flight per SM: 16 lanes per robot, two robots per warp that run
+// CONVERGED (one instruction stream, full-mask collectives of width 16, warp-uniform control flow; partial masks
+// leave the halves diverged and issue everything twice), 12 KB of shared memory per robot, the per-stage gains (the
+// only O(N) state of the recursion that must survive until the forward pass) in an L2-resident workspace.
+// Code size is part of the design: every per-foot loop is rolled (the unrolled version spent 16 % of its stall
+// samples on instruction fetch).
 // The two Cholesky factors of a stage and their inverses are computed redundantly in the REGISTERS of every
 // lane (static indices, no shuffle or memory hop on the pivot chain, a 5-instruction reciprocal square root;
 // the inverse rows are formed in the shadow of the pivots), so every product above is "one row in registers
-// times a register-resident triangular matrix" and a stage needs three half-warp barriers.
+// times a register-resident triangular matrix" and a stage needs three warp barriers.
 // Replaces MPC.update_ML / update_NK / call_solver / retrieve_result (MPC.py:316-458) like the dense path.
 #pragma once
 #include "mpcqp_device.cuh"
@@ -93,7 +96,6 @@ struct alignas(16) RicInst {
 // The two robots of a warp run CONVERGED: one instruction stream, full-mask collectives, shuffles of width 16.
 constexpr unsigned RIC_FULL = 0xffffffffu;
 __device__ __forceinline__ double hshfl_d(double v, int src) { return __shfl_sync(RIC_FULL, v, src, 16); }
-__device__ __forceinline__ double hshfl_xor_d(double v, int x) { return __shfl_xor_sync(RIC_FULL, v, x, 16); }
 // true on every lane of a half-warp iff the predicate holds on all / any of its 16 lanes
 __device__ __forceinline__ bool half_all(bool p, int sub) { return ((__ballot_sync(RIC_FULL, p) >> (16 * sub)) & 0xFFFFu) == 0xFFFFu; }
 __device__ __forceinline__ bool half_any(bool p, int sub) { return ((__ballot_sync(RIC_FULL, p) >> (16 * sub)) & 0xFFFFu) != 0u; }
@@ -184,15 +186,6 @@ __device__ __forceinline__ void foot_A(const DevParams& P, const RicInst<N>& sm,
     for (int i = 0; i < 9; ++i) Ii[i] = src[i];
     lever_block(P, Ii, r, A);
 }
-// sum a 6-vector over the four feet of a step (lanes 4k..4k+3 of the half-warp); lane j == 0 stores it
-__device__ __forceinline__ void hstep_sum_store(double (&v)[6], double* dst, int j) {
-#pragma unroll
-    for (int c = 0; c < 6; ++c) { v[c] += hshfl_xor_d(v[c], 1); }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) { v[c] += hshfl_xor_d(v[c], 2); }
-    if (j == 0) store_row6(dst, v);
-}
-
 // The LQ solve itself: backward recursion over sm.E (packed E_k) and sm.beta, forward pass, velocity costates.
 // Returns (uniform over the half-warp) false if a pivot was not positive.  On return sm.xst holds the states
 // x_1..x_N and sm.lam the velocity costates lam^v_1..lam^v_N; sm.E is dead.
