@@ -84,10 +84,12 @@ RIC_DECL(16) RIC_DECL(32) RIC_DECL(64)
 }  // namespace mpcqp
 
 void launch_stagewise(int N, int n_inst, int max_ctas, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
-                      const double* dx, const double* df, double* ws, int* ctr, int first, int off) {
+                      const double* dx, const double* df, double* ws, int* ctr, bool reset_ctr, int first, int off) {
     int grid = (n_inst + RIC_PER_CTA - 1) / RIC_PER_CTA;
     if (grid > max_ctas) grid = max_ctas;                      // persistent: one workspace slot per resident half-warp
-    cudaMemsetAsync(ctr, 0, sizeof(int), s);                   // the kernel's work counter (pairs of robots beyond the first per warp)
+    // the kernel's work counter (pairs of robots beyond the first per warp) must be zero at launch: on the handle's main stream
+    // the caller's reset of the fallback queue covers it (one 16-byte memset), on a side stream it is reset here
+    if (reset_ctr) cudaMemsetAsync(ctr, 0, sizeof(int), s);
     if (N == 16) ric_launch_16(grid, s, dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
     else if (N == 32) ric_launch_32(grid, s, dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
     else ric_launch_64(grid, s, dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
@@ -136,7 +138,7 @@ struct mpcqp_handle {
             // that may run it concurrently has its own gain workspace
             const int lane_of_stream = s == side[0] ? 1 : (s == side[1] ? 2 : 0);
             double* ws = d_ric_ws + (size_t)lane_of_stream * ric_ws_doubles;
-            launch_stagewise(p.n_steps, n, ric_max_ctas, s, dp, st, use, dx, df, ws, st.fb_count + 1 + lane_of_stream, first, off);
+            launch_stagewise(p.n_steps, n, ric_max_ctas, s, dp, st, use, dx, df, ws, st.fb_count + 1 + lane_of_stream, lane_of_stream != 0, first, off);
         } else if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         else launch_solve<32>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         ++launches;
@@ -384,7 +386,7 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
     const int B = h->p.batch, N = h->p.n_steps;
     const int first = (k == 0.0) ? 1 : 0;                       // MPC.py:491, 413: only k == 0 vs k > 0 matters
     const size_t xs = (size_t)12 * (N + 1), fs = 260;
-    CU(cudaMemsetAsync(h->st.fb_count, 0, sizeof(int32_t), h->stream));
+    CU(cudaMemsetAsync(h->st.fb_count, 0, 4 * sizeof(int32_t), h->stream));     // fallback queue length + the stage-wise kernel's work counters
     const bool stageA = (h->p.mode & MPCQP_MODE_ACTIVE_SET) != 0;
     const double *dx = xref, *df = fsteps;
     // Host inputs: the batch is cut into chunks of two full waves (2 x 4 CTAs x #SM instances); chunk
@@ -640,7 +642,7 @@ int mpcqp_scenario_run(mpcqp_handle* h, int ticks, int emit_inputs) {
     for (int t = 0; t < ticks; ++t) {
         h->sc.tick = h->scen_tick;
         const int first = h->scen_tick == 0 ? 1 : 0;
-        CU(cudaMemsetAsync(h->st.fb_count, 0, sizeof(int32_t), h->stream));
+        CU(cudaMemsetAsync(h->st.fb_count, 0, 4 * sizeof(int32_t), h->stream));     // fallback queue length + the stage-wise kernel's work counters
         h->solve(false, B, h->stream, nullptr, nullptr, first, 0, B, true);
         if ((h->p.mode & MPCQP_MODE_ADMM) && !(h->p.mode & MPCQP_MODE_ADMM_STAGEWISE)) {
             const int slots = h->ctas_per_sm(true) * h->sms;
