@@ -11,6 +11,8 @@
 //       L L' = Pvv+,   G = I + L' E_k L = M M',   Gamma = (I + E_k Pvv+)^-1 E_k = L^-T (I - G^-1) L^-1
 //       every row rho of [Ppv+; Pvv+; pv+'] (13 rows, one per lane) goes through the same four products
 //           y = rho L^-T,  v = y G^-1 = (y M^-T) M^-1,  rho (I - Gamma Pvv+) = v L',  rho Gamma = (y - v) L^-1
+//       (computed square-root free: Pvv+ = U D U', H = D^-1 + U' E_k U = W Delta W' with U, W unit lower triangular, so
+//        that with yt = rho U^-T and e = ((yt D^-1) W^-T Delta^-1) W^-1:  rho (I - Gamma Pvv+) = e U',  rho Gamma = ((yt - e) D^-1) U^-1)
 //       which yields Pt = (P+^-1 + [0 0; 0 E])^-1 (its [:, v] block), the closed-loop gain [Ppv; Pvv] Gamma and
 //       Gamma pv; the [:, p] block follows from  Pt[:, p] = P+[:, p] - (rho Gamma) Pvp+.
 //       P_k = Q + A' Pt A,   p_k = -Q xref_k + A'(Pt[:,v] beta_k + pt)
@@ -25,9 +27,9 @@
 // only O(N) state of the recursion that must survive until the forward pass) in an L2-resident workspace.
 // Code size is part of the design: every per-foot loop is rolled (the unrolled version spent 16 % of its stall
 // samples on instruction fetch).
-// The two Cholesky factors of a stage and their inverses are computed redundantly in the REGISTERS of every
-// lane (static indices, no shuffle or memory hop on the pivot chain, a 5-instruction reciprocal square root;
-// the inverse rows are formed in the shadow of the pivots), so every product above is "one row in registers
+// The two factorisations of a stage and the inverses of their unit triangular factors are computed redundantly in the
+// REGISTERS of every lane (static indices, no shuffle or memory hop on the pivot chain; pivot to pivot is a 4-instruction
+// reciprocal and one fused multiply-add; the inverse rows are formed in the shadow of the pivots), so every product above is "one row in registers
 // times a register-resident triangular matrix" and a stage needs three warp barriers.
 // Replaces MPC.update_ML / update_NK / call_solver / retrieve_result (MPC.py:316-458) like the dense path.
 #pragma once
@@ -100,68 +102,70 @@ __device__ __forceinline__ double hshfl_d(double v, int src) { return __shfl_syn
 __device__ __forceinline__ bool half_all(bool p, int sub) { return ((__ballot_sync(RIC_FULL, p) >> (16 * sub)) & 0xFFFFu) == 0xFFFFu; }
 __device__ __forceinline__ bool half_any(bool p, int sub) { return ((__ballot_sync(RIC_FULL, p) >> (16 * sub)) & 0xFFFFu) != 0u; }
 
-// 1 / sqrt(d): hardware seed (relative error ~2^-21) and one third-order correction, five dependent instructions.
-// d <= 0 or non-finite gives a non-finite result; the caller tests d separately.
-__device__ __forceinline__ double rsqrt_fast(double d) {
+// 1 / d: hardware seed (relative error ~2^-22) and one third-order correction, three dependent instructions after the seed.
+// d <= 0 or non-finite gives garbage; the caller tests d separately.
+__device__ __forceinline__ double rcp_fast(double d) {
     double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    const double t = d * y;
-    const double e = fma(-t, y, 1.0);
-    const double p = fma(0.375, e, 0.5);
-    const double ye = y * e;
-    return fma(ye, p, y);
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
 }
 
-// Cholesky a = L L' of a 6x6 SPD matrix held as packed lower triangle in registers, in place, fused with the
-// inversion of L (li = inv(L), packed lower triangle).  Row j of the inverse needs only rows < j of it and row j
-// of L up to a final scaling by 1 / l_jj, so its sums are formed before the pivot is known: the inverse adds one
-// multiply to the pivot chain.  All indices are static.
-__device__ __forceinline__ bool chol6_regs(double (&a)[21], double (&li)[21]) {
+// Square-root-free factorisation a = U D U' of a 6x6 SPD matrix held as packed lower triangle in registers, in place
+// (U unit lower triangular: its strict lower part replaces a's, the diagonal of `a` is left as garbage), with
+// dinv = 1 / D and ui = inv(U) (unit lower, strict part only is meaningful).  The pivot-to-pivot dependency is
+// 1 / d_j (seed + 3) and ONE fused multiply-add: the next pivot is updated from the unscaled column, whose square is ready
+// before the reciprocal is.  Row j of the inverse needs only rows < j of it and row j of U, so it is formed in the shadow
+// of the pivots.  All indices are static.
+__device__ __forceinline__ bool ldl6_regs(double (&a)[21], double (&dinv)[6], double (&ui)[21]) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-        double s[6];
-#pragma unroll
-        for (int c = 0; c < j; ++c) {
-            double t = 0.0;
-#pragma unroll
-            for (int k = c; k < j; ++k) t = fma(a[RIC_TI(j, k)], li[RIC_TI(k, c)], t);
-            s[c] = t;
-        }
         const double d = a[RIC_TI(j, j)];
         ok = ok && (d > 1e-300) && (d < 1e300);
-        const double inv = rsqrt_fast(d);
-        a[RIC_TI(j, j)] = d * inv;
-        li[RIC_TI(j, j)] = inv;
+        double sq = 0.0;
+        if (j + 1 < 6) sq = a[RIC_TI(j + 1, j)] * a[RIC_TI(j + 1, j)];
+        const double r = rcp_fast(d);
+        dinv[j] = r;
+        if (j + 1 < 6) a[RIC_TI(j + 1, j + 1)] = fma(-sq, r, a[RIC_TI(j + 1, j + 1)]);       // the pivot chain
+        double t[6];                                                                      // unscaled column j
 #pragma unroll
-        for (int c = 0; c < j; ++c) li[RIC_TI(j, c)] = -inv * s[c];
-#pragma unroll
-        for (int i = j + 1; i < 6; ++i) a[RIC_TI(i, j)] *= inv;
+        for (int i = j + 1; i < 6; ++i) { t[i] = a[RIC_TI(i, j)]; a[RIC_TI(i, j)] = t[i] * r; }
 #pragma unroll
         for (int i = j + 1; i < 6; ++i)
 #pragma unroll
-            for (int c = j + 1; c <= i; ++c) a[RIC_TI(i, c)] = fma(-a[RIC_TI(i, j)], a[RIC_TI(c, j)], a[RIC_TI(i, c)]);
+            for (int c = j + 1; c <= i; ++c)
+                if (!(i == j + 1 && c == j + 1)) a[RIC_TI(i, c)] = fma(-a[RIC_TI(i, j)], t[c], a[RIC_TI(i, c)]);
+        // row j of inv(U):  ui[j][c] = -(u[j][c] + sum_{c < k < j} u[j][k] ui[k][c])
+#pragma unroll
+        for (int c = 0; c < j; ++c) {
+            double acc = a[RIC_TI(j, c)];
+#pragma unroll
+            for (int k = c + 1; k < j; ++k) acc = fma(a[RIC_TI(j, k)], ui[RIC_TI(k, c)], acc);
+            ui[RIC_TI(j, c)] = -acc;
+        }
     }
     return ok;
 }
 
-// out = in * m   (m lower triangular, packed):  out[c] = sum_{r >= c} in[r] m[r][c]
-__device__ __forceinline__ void row_mul(double (&out)[6], const double (&in)[6], const double (&m)[21]) {
+// out = in * m   (m UNIT lower triangular, packed; its diagonal entries are not read):  out[c] = in[c] + sum_{r > c} in[r] m[r][c]
+__device__ __forceinline__ void row_mul1(double (&out)[6], const double (&in)[6], const double (&m)[21]) {
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-        double t = in[c] * m[RIC_TI(c, c)];
+        double t = in[c];
 #pragma unroll
         for (int r = c + 1; r < 6; ++r) t = fma(in[r], m[RIC_TI(r, c)], t);
         out[c] = t;
     }
 }
-// out = in * m'  (m lower triangular, packed):  out[c] = sum_{r <= c} in[r] m[c][r]
-__device__ __forceinline__ void row_mulT(double (&out)[6], const double (&in)[6], const double (&m)[21]) {
+// out = in * m'  (m UNIT lower triangular, packed):  out[c] = in[c] + sum_{r < c} in[r] m[c][r]
+__device__ __forceinline__ void row_mul1T(double (&out)[6], const double (&in)[6], const double (&m)[21]) {
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-        double t = in[0] * m[RIC_TI(c, 0)];
+        double t = in[c];
 #pragma unroll
-        for (int r = 1; r <= c; ++r) t = fma(in[r], m[RIC_TI(c, r)], t);
+        for (int r = 0; r < c; ++r) t = fma(in[r], m[RIC_TI(c, r)], t);
         out[c] = t;
     }
 }
@@ -224,8 +228,8 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
         const RicCost& cin = sm.cost[k & 1];
         RicCost& cout = sm.cost[(k & 1) ^ 1];
         const double* Ek = sm.E + 21 * k;
-        // (1) L L' = Pvv, li = inv(L): every lane, in registers
-        double L[21], Li[21];
+        // (1) U D U' = Pvv, Ui = inv(U): every lane, in registers (square-root free: L = U D^1/2 never appears)
+        double L[21], Li[21], dinv[6];
 #pragma unroll
         for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -234,18 +238,17 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
         load_row6(rho, prow ? cin.Ppv + 6 * ri : (vrow ? cin.Pvv + 6 * ri : cin.pv));
 #pragma unroll
         for (int q = 0; q < 6; ++q) er[q] = Ek[ie[q]];
-        RPROF(17);
-        spd = chol6_regs(L, Li) && spd;
+        spd = ldl6_regs(L, dinv, Li) && spd;
         RPROF(2);
-        // (2) row ri of T = E L -> shared memory;  y = rho L^-T
+        // (2) row ri of T = E U -> shared memory;  y = rho U^-T  (so that rho L^-T = y D^-1/2)
         double tr[6], y[6];
-        row_mul(tr, er, L);
+        row_mul1(tr, er, L);
         if (prow) store_row6(sm.T + 6 * ri, tr);
-        row_mulT(y, rho, Li);
+        row_mul1T(y, rho, Li);
         __syncwarp();
         RPROF(3);
-        // (3) G = I + L' T (every lane), M M' = G, mi = inv(M)
-        double G[21], Mi[21];
+        // (3) H = D^-1 + U' T  (every lane; G = I + L'EL = D^1/2 H D^1/2),  H = W Delta W',  Wi = inv(W)
+        double G[21], Mi[21], einv[6];
         {
             double Tl[21];
 #pragma unroll
@@ -256,25 +259,30 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
             for (int a = 0; a < 6; ++a)
 #pragma unroll
                 for (int c = 0; c <= a; ++c) {
-                    double t = (a == c) ? 1.0 : 0.0;
+                    double t = Tl[RIC_TI(a, c)] + ((a == c) ? dinv[a] : 0.0);       // r = a term: U[a][a] = 1
 #pragma unroll
-                    for (int r = a; r < 6; ++r) t = fma(L[RIC_TI(r, a)], Tl[RIC_TI(r, c)], t);
+                    for (int r = a + 1; r < 6; ++r) t = fma(L[RIC_TI(r, a)], Tl[RIC_TI(r, c)], t);
                     G[RIC_TI(a, c)] = t;
                 }
         }
         RPROF(4);
-        spd = chol6_regs(G, Mi) && spd;
+        spd = ldl6_regs(G, einv, Mi) && spd;
         RPROF(5);
-        // (4) v = y G^-1,  t = v L' (row of Pt[:, v]),  kr = (y - v) L^-1 (row of [Ppv; Pvv; pv'] Gamma)
+        // (4) with e = ((y D^-1) W^-T Delta^-1) W^-1:   t = e U' (row of Pt[:, v]),   kr = ((y - e) D^-1) U^-1 (row of
+        //     [Ppv; Pvv; pv'] Gamma)
         double v[6], kr[6];
         {
-            double y2[6], dr[6];
-            row_mulT(y2, y, Mi);
-            row_mul(v, y2, Mi);
+            double a1[6], b1[6], dr[6];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) dr[q] = y[q] - v[q];
-            row_mulT(tr, v, L);
-            row_mul(kr, dr, Li);
+            for (int q = 0; q < 6; ++q) a1[q] = y[q] * dinv[q];
+            row_mul1T(b1, a1, Mi);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) b1[q] *= einv[q];
+            row_mul1(v, b1, Mi);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) dr[q] = (y[q] - v[q]) * dinv[q];
+            row_mul1T(tr, v, L);
+            row_mul1(kr, dr, Li);
         }
         if (hl < 13) {
             double* g = ws + (size_t)RIC_GAIN * k + rid;                // gain of impulse component o: coefficient rid
