@@ -803,11 +803,6 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
         for (int s = 0; s < P.max_sweeps; ++s) {
             const bool need = !done && !stop;
             if (!__any_sync(RIC_FULL, need)) break;
-            const unsigned long long h = sig_hash(sg);
-            __syncwarp();
-            if (need && hl == 0 && nhist < 16) sm.hist[nhist] = h;
-            if (need) nhist = (nhist < 16) ? nhist + 1 : nhist;
-            __syncwarp();
             const int rc = ric_sweep<N>(P, sm, ws, sub, hl, conbits, sg, nsg);
             bool search = false;
             if (need) {
@@ -816,8 +811,15 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
                 else if (rc > 0) { done = true; status = 1; }
                 else search = true;
             }
-            // ---- next signature.  First choice: every foot adopts its proposal (primal-dual active-set step).  If that
-            // signature was already tried the iteration would cycle: from then on one foot changes per sweep, in index order.
+            if (!__any_sync(RIC_FULL, search)) continue;      // the common case: nothing to hash, nothing to choose
+            // ---- next signature.  The one just tried goes into the history; first choice: every foot adopts its proposal
+            // (primal-dual active-set step).  If that signature was already tried the iteration would cycle: from then on one
+            // foot changes per sweep, in index order.
+            const unsigned long long h = sig_hash(sg);
+            __syncwarp();
+            if (search && hl == 0 && nhist < 16) sm.hist[nhist] = h;
+            if (search) nhist = (nhist < 16) ? nhist + 1 : nhist;
+            __syncwarp();
             auto seen = [&](unsigned long long q) {
                 bool f = false;
                 for (int i = 0; i < nhist; ++i) f = f || (sm.hist[i] == q);
