@@ -374,13 +374,13 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
                     a0 = fma(g[d][i].x, z[2 * i], a0); a1 = fma(g[d][i].y, z[2 * i + 1], a1);
                     a2 = fma(g[d][i + 1].x, z[2 * i + 2], a2); a3 = fma(g[d][i + 1].y, z[2 * i + 3], a3);
                 }
-                const double w = -((a0 + a1) + (a2 + a3));
+                const double w = (a0 + a1) + (a2 + a3);          // minus the impulse correction of component o
                 if (k + RIC_DEPTH < N) {
 #pragma unroll
                     for (int i = 0; i < 7; ++i) g[d][i] = __ldcg(reinterpret_cast<const double2*>(gcol + (size_t)RIC_GAIN * (k + RIC_DEPTH)) + i);
                 }
 #pragma unroll
-                for (int c = 0; c < 6; ++c) { x[c] = z[c]; x[6 + c] = z[6 + c] + hshfl_d(w, c); }
+                for (int c = 0; c < 6; ++c) { x[c] = z[c]; x[6 + c] = z[6 + c] - hshfl_d(w, c); }
                 if (hl == 0) {
                     double* xs = sm.xst + 12 * k;
 #pragma unroll
