@@ -118,7 +118,12 @@ __device__ __forceinline__ double rcp_fast(double d) {
 // 1 / d_j (seed + 3) and ONE fused multiply-add: the next pivot is updated from the unscaled column, whose square is ready
 // before the reciprocal is.  Row j of the inverse needs only rows < j of it and row j of U, so it is formed in the shadow
 // of the pivots.  All indices are static.
-__device__ __forceinline__ bool ldl6_regs(double (&a)[21], double (&dinv)[6], double (&ui)[21]) {
+// Two row vectors ride along in the shadow of the pivots: `fs` is overwritten by fs U^-T (forward substitution: entry
+// j + 1 needs row j + 1 of U up to column j, final right after pivot j) and, if COLP, `cp_out` receives cp U (entry j needs
+// column j of U, final at the same moment) -- so both are complete one multiply-add after the last pivot.
+template <bool COLP>
+__device__ __forceinline__ bool ldl6_regs(double (&a)[21], double (&dinv)[6], double (&ui)[21], double (&fs)[6], const double (&cp)[6],
+                                          double (&cp_out)[6]) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
@@ -144,6 +149,19 @@ __device__ __forceinline__ bool ldl6_regs(double (&a)[21], double (&dinv)[6], do
 #pragma unroll
             for (int k = c + 1; k < j; ++k) acc = fma(a[RIC_TI(j, k)], ui[RIC_TI(k, c)], acc);
             ui[RIC_TI(j, c)] = -acc;
+        }
+        // the carried rows
+        if (j + 1 < 6) {
+            double acc = fs[j + 1];
+#pragma unroll
+            for (int r = 0; r <= j; ++r) acc = fma(-fs[r], a[RIC_TI(j + 1, r)], acc);
+            fs[j + 1] = acc;
+        }
+        if (COLP) {
+            double acc = cp[j];
+#pragma unroll
+            for (int r = j + 1; r < 6; ++r) acc = fma(cp[r], a[RIC_TI(r, j)], acc);
+            cp_out[j] = acc;
         }
     }
     return ok;
@@ -238,13 +256,14 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
         load_row6(rho, prow ? cin.Ppv + 6 * ri : (vrow ? cin.Pvv + 6 * ri : cin.pv));
 #pragma unroll
         for (int q = 0; q < 6; ++q) er[q] = Ek[ie[q]];
-        spd = ldl6_regs(L, dinv, Li) && spd;
-        RPROF(2);
-        // (2) row ri of T = E U -> shared memory;  y = rho U^-T  (so that rho L^-T = y D^-1/2)
+        // ... carrying along  y = rho U^-T  (so that rho L^-T = y D^-1/2)  and row ri of T = E U
         double tr[6], y[6];
-        row_mul1(tr, er, L);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) y[q] = rho[q];
+        spd = ldl6_regs<true>(L, dinv, Li, y, er, tr) && spd;
+        RPROF(2);
+        // (2) the rows of T -> shared memory
         if (prow) store_row6(sm.T + 6 * ri, tr);
-        row_mul1T(y, rho, Li);
         __syncwarp();
         RPROF(3);
         // (3) H = D^-1 + U' T  (every lane; G = I + L'EL = D^1/2 H D^1/2),  H = W Delta W',  Wi = inv(W)
@@ -266,16 +285,17 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
                 }
         }
         RPROF(4);
-        spd = ldl6_regs(G, einv, Mi) && spd;
+        // ... carrying along  b1 = (y D^-1) W^-T
+        double b1[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) b1[q] = y[q] * dinv[q];
+        spd = ldl6_regs<false>(G, einv, Mi, b1, b1, b1) && spd;
         RPROF(5);
         // (4) with e = ((y D^-1) W^-T Delta^-1) W^-1:   t = e U' (row of Pt[:, v]),   kr = ((y - e) D^-1) U^-1 (row of
         //     [Ppv; Pvv; pv'] Gamma)
         double v[6], kr[6];
         {
-            double a1[6], b1[6], dr[6];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) a1[q] = y[q] * dinv[q];
-            row_mul1T(b1, a1, Mi);
+            double dr[6];
 #pragma unroll
             for (int q = 0; q < 6; ++q) b1[q] *= einv[q];
             row_mul1(v, b1, Mi);
