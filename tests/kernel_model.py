@@ -532,3 +532,27 @@ def riccati_solve(p, xref, Bv, contact, sig):
                 f[k, j] = pf[k, j] + Z[k, j] @ q
                 grad[k, j] = p.w_force * f[k, j] + Bv[k, j].T @ lam[k]
     return f, grad, Xs
+
+
+def riccati_stage_ldl(Ppp, Ppv, Pvv, pp, pv, E):
+    """One backward stage in the square-root-free form the kernel uses (mpcqp_riccati.cuh: ldl6_regs + the row products):
+    Pvv = U D U', H = D^-1 + U'EU = W Delta W'; for every row rho of [Ppv; Pvv; pv'] with yt = rho U^-T and
+    e = ((yt D^-1) W^-T Delta^-1) W^-1:  rho (I - Gamma Pvv) = e U',  rho Gamma = ((yt - e) D^-1) U^-1.
+    Returns (Pt[:, v] rows (13 x 6), [Ppv; Pvv; pv'] Gamma rows (13 x 6))."""
+    def ldl(a):
+        a = a.copy()
+        n = a.shape[0]
+        U = np.eye(n)
+        d = np.zeros(n)
+        for j in range(n):
+            d[j] = a[j, j]
+            U[j + 1:, j] = a[j + 1:, j] / d[j]
+            a[j + 1:, j + 1:] -= np.outer(U[j + 1:, j], a[j + 1:, j])
+        return U, d
+    U, d = ldl(Pvv)
+    H = np.diag(1.0 / d) + U.T @ E @ U
+    W, dl = ldl(H)
+    rows = np.vstack([Ppv, Pvv, pv[None, :]])
+    yt = rows @ np.linalg.inv(U).T
+    e = ((yt / d) @ np.linalg.inv(W).T / dl) @ np.linalg.inv(W)
+    return e @ U.T, ((yt - e) / d) @ np.linalg.inv(U)

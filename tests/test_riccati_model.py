@@ -65,3 +65,22 @@ def test_riccati_matches_dense_polish_on_arbitrary_faces():
             np.testing.assert_allclose(f, fq, rtol=0, atol=1e-7)
             gd = eng._hess_apply(Bv, contact, fq) + gg
             np.testing.assert_allclose(grad, gd * contact[:, :, None], rtol=0, atol=1e-8)
+
+
+def test_square_root_free_stage_equals_the_cholesky_form():
+    """The kernel factors Pvv = U D U' and H = D^-1 + U'EU = W Delta W' (no square roots on the pivot chain); the rows it
+    forms must be those of the Cholesky form the recursion is written in: Pt[:, v] = P[:, v] (I - Gamma Pvv) and P[:, v] Gamma
+    with Gamma = (I + E Pvv)^-1 E."""
+    rng = np.random.default_rng(2)
+    for trial in range(5):
+        A = rng.normal(size=(12, 12))
+        P = A @ A.T + 0.1 * np.eye(12)
+        Ppp, Ppv, Pvv = P[:6, :6], P[:6, 6:], P[6:, 6:]
+        pp, pv = rng.normal(size=6), rng.normal(size=6)
+        F = rng.normal(size=(6, 4 if trial % 2 else 7)) * (10.0 ** rng.integers(-1, 3))
+        E = F @ F.T                                         # PSD, rank-deficient every other trial
+        tr, kr = km.riccati_stage_ldl(Ppp, Ppv, Pvv, pp, pv, E)
+        Gam = np.linalg.solve(np.eye(6) + E @ Pvv, E)
+        rows = np.vstack([Ppv, Pvv, pv[None, :]])
+        np.testing.assert_allclose(kr, rows @ Gam, rtol=1e-9, atol=1e-9 * np.abs(rows @ Gam).max())
+        np.testing.assert_allclose(tr, rows @ (np.eye(6) - Gam @ Pvv), rtol=1e-9, atol=1e-9 * np.abs(rows).max())
