@@ -285,6 +285,40 @@ def test_long_gait_tables_take_the_full_copy_path():
     eng.close()
 
 
+@pytest.mark.parametrize("B,gaits", [(5, ["trot", "walk", "pace", "bound"]), (2500, "trot")], ids=["ragged-mixed", "two-waves"])
+def test_pinned_and_pageable_host_inputs_agree(B, gaits):
+    """Host inputs reach the device by asynchronous copies from page-locked buffers (what torch's pin_memory gives; 2500 robots
+    take the two-chunk path whose copies overlap the other chunk's solve) or by the driver's staged copies from pageable numpy
+    arrays.  Same robots, same ticks, both ways: every output must agree bit for bit, including a tick on which one gait table
+    runs past row 7 and the whole batch switches from the rows-0..7 copy to the full-table copy."""
+    import torch
+    staged, inplace = mpcqp.Engine(batch=B), mpcqp.Engine(batch=B)
+    sc = Scenario(B, gaits=gaits, seed=31)
+    px = torch.empty((B, 12, N + 1), dtype=torch.float64, pin_memory=True).numpy()
+    pf = torch.empty((B, 20, 13), dtype=torch.float64, pin_memory=True).numpy()
+    for t in range(6):
+        xref, fsteps = sc.inputs()
+        if t == 3:                                          # robot 0: one table row per step (16 rows, same QP)
+            cnt = fsteps[0, :, 0].astype(int)
+            tab = np.full((20, 13), np.nan); tab[:, 0] = 0.0
+            tab[:cnt.sum()] = np.repeat(fsteps[0], cnt, axis=0)
+            tab[:cnt.sum(), 0] = 1.0
+            fsteps = fsteps.copy(); fsteps[0] = tab
+            assert cnt.sum() == N and fsteps[0, 7, 0] != 0.0
+        px[...] = xref; pf[...] = fsteps
+        staged.run(t, xref, fsteps)
+        inplace.run(t, px, pf)
+        xs, xi = staged.solution(), inplace.solution()
+        a, b = staged.info(), inplace.info()
+        assert (a["status"] == 1).all()
+        np.testing.assert_array_equal(xi, xs)
+        np.testing.assert_array_equal(inplace.forces(), staged.forces())
+        for key in ("status", "sweeps", "iters", "obj", "contact", "active", "y"):
+            np.testing.assert_array_equal(b[key], a[key], err_msg=key)
+        sc.advance(xs[:, :12] + xref[:, :, 1])
+    staged.close(); inplace.close()
+
+
 def test_full_batch_properties():
     """BASELINE configs[1] size (4096 robots): determinism, warm-start invariance, KKT on a sample,
     friction / unilateral / fz_max feasibility everywhere, objective consistent with x."""
