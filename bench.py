@@ -256,6 +256,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="robots per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="leave the process on whatever cores the launcher gave it")
     ap.add_argument("--mode", type=int, default=7, help="solver stages (include/mpcqp.h MPCQP_MODE_*): 7 = stage-wise active set + ADMM fallback (default), 3 = dense")
     ap.add_argument("--cpu-ticks", type=int, default=100)
     ap.add_argument("--workload", default="trot", choices=["trot", "sweep", "mixed-sweep"],
@@ -278,6 +279,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    affinity = mpcqp.bind_near_gpu(local_rank) if not args.no_bind else {"off": True}    # before any pinned allocation
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -434,6 +437,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)                 # the CPU arm gets every host core back
         cpu, _ = cpu_arm(args.cpu_ticks, 3)
 
     if rank == 0:
@@ -443,6 +447,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD % B,
                        "instances_per_gpu": B, "parallelism": "instances sharded by index, no collective",
+                       "cpu_affinity": affinity,
                        "settle_ticks": max(args.settle, 0),
                        "tick_window": "ticks %d..%d of the closed loop are timed (steady operation; the first %d ticks after "
                                       "release from rest run untimed before the %d warm-up ticks)" % (W, T - 1, max(args.settle, 0), max(args.warmup, 3)),

@@ -127,6 +127,24 @@ def _host_f64(a, shape):
     return a
 
 
+def bind_near_gpu(device=0):
+    """Pin the calling thread (and the threads it starts later) to the CPU cores NVML reports as local to CUDA device
+    `device`, so that the page-locked input / output buffers it allocates afterwards land on that GPU's NUMA node and the
+    per-tick copies do not cross the socket interconnect.  One process per GPU: call it first thing in each process.
+    Returns {"cpus": n, "first": i, "last": j} or {"error": "..."} (never raises: containers may forbid it)."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(int(device)).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return {"cpus": len(cpus), "first": cpus[0], "last": cpus[-1]}
+    except Exception as e:          # noqa: BLE001 -- best effort by design
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 class Engine:
     """One libmpcqp handle: a batch of `batch` independent MPC instances on one GPU."""
 
