@@ -98,7 +98,17 @@ void launch_stagewise(int N, int n_inst, int max_ctas, cudaStream_t s, const Dev
 template <int N>
 void launch_solve(bool admm, int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
                   const double* dx, const double* df, int first, int off, int n) {
-    if (admm) solve_kernel<N, true><<<grid, 32 * Cfg<N>::NW, sizeof(Smem<N, true>), s>>>(dp, st, sc, dx, df, first, off, n);
+    if (admm) {
+        // fallback stage: programmatic dependent launch behind the active-set kernel of the same stream (the kernel blocks in
+        // griddepcontrol.wait before it reads the queue); behind anything else the attribute is an ordinary launch
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * Cfg<N>::NW); cfg.dynamicSmemBytes = sizeof(Smem<N, true>); cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, solve_kernel<N, true>, dp, st, sc, dx, df, first, off, n);
+    }
     else solve_kernel<N, false><<<grid, 32 * Cfg<N>::NW, sizeof(Smem<N, false>), s>>>(dp, st, sc, dx, df, first, off, n);
 }
 
@@ -117,6 +127,10 @@ struct mpcqp_handle {
     size_t block_bytes = 0;
     int aw = 0, cw = 0;             // words per instance of the active / contact masks
     bool ran = false;
+    int32_t* ctr_base = nullptr;    // two copies of {fallback queue length, three work counters}, 8 ints apart, alternating by tick
+    int ctr_parity = 0;
+    bool ctr_clean = false;         // this tick's copy was zeroed by the previous tick's stage-wise launch
+    bool zero_next = false;         // set by solve(): a main-stream stage-wise launch of this tick zeroes the next tick's copy
     int64_t launches = 0;
     int sms = 0;
 
@@ -138,7 +152,9 @@ struct mpcqp_handle {
             // that may run it concurrently has its own gain workspace
             const int lane_of_stream = s == side[0] ? 1 : (s == side[1] ? 2 : 0);
             double* ws = d_ric_ws + (size_t)lane_of_stream * ric_ws_doubles;
-            launch_stagewise(p.n_steps, n, ric_max_ctas, s, dp, st, use, dx, df, ws, st.fb_count + 1 + lane_of_stream, lane_of_stream != 0, first, off);
+            DevState stl = st;
+            if (lane_of_stream == 0) { stl.fb_next = ctr_base + 8 * (ctr_parity ^ 1); zero_next = true; }
+            launch_stagewise(p.n_steps, n, ric_max_ctas, s, dp, stl, use, dx, df, ws, st.fb_count + 1 + lane_of_stream, lane_of_stream != 0, first, off);
         } else if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         else launch_solve<32>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         ++launches;
@@ -334,6 +350,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     h->st.status = (int32_t*)(base + o_status); h->st.sweeps = (int32_t*)(base + o_sweeps); h->st.iters = (int32_t*)(base + o_iters);
     h->st.contact = (uint32_t*)(base + o_contact); h->st.active = (uint32_t*)(base + o_active);
     h->st.fb_list = (int32_t*)(base + o_list); h->st.fb_count = (int32_t*)(base + o_count);
+    h->ctr_base = h->st.fb_count; h->st.fb_next = nullptr;
     h->st.sig = (uint8_t*)(base + o_sig);
     CUH(cudaMemset(h->st.sig, SIG_FREE, (size_t)B * 4 * N));
     int ric_per_sm = 0;
@@ -349,6 +366,18 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
 #undef CUH
     *out = h;
     return MPCQP_OK;
+}
+
+// Start of a tick: switch to the other copy of the counters (fallback queue length + the stage-wise kernel's work counters).  It is
+// already zero when the previous tick ran a stage-wise launch on the main stream (that kernel clears the copy it does not use);
+// otherwise one 16-byte memset.
+static cudaError_t begin_tick(mpcqp_handle* h) {
+    h->ctr_parity ^= 1;
+    h->st.fb_count = h->ctr_base + 8 * h->ctr_parity;
+    h->st.fb_next = nullptr;
+    const bool clean = h->ctr_clean && h->zero_next;
+    h->ctr_clean = true; h->zero_next = false;
+    return clean ? cudaSuccess : cudaMemsetAsync(h->st.fb_count, 0, 4 * sizeof(int32_t), h->stream);
 }
 
 static int stage_inputs(mpcqp_handle* h, const double* xref, const double* fsteps, int location,
@@ -386,7 +415,7 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
     const int B = h->p.batch, N = h->p.n_steps;
     const int first = (k == 0.0) ? 1 : 0;                       // MPC.py:491, 413: only k == 0 vs k > 0 matters
     const size_t xs = (size_t)12 * (N + 1), fs = 260;
-    CU(cudaMemsetAsync(h->st.fb_count, 0, 4 * sizeof(int32_t), h->stream));     // fallback queue length + the stage-wise kernel's work counters
+    CU(begin_tick(h));
     const bool stageA = (h->p.mode & MPCQP_MODE_ACTIVE_SET) != 0;
     const double *dx = xref, *df = fsteps;
     // Host inputs: the batch is cut into chunks of two full waves (2 x 4 CTAs x #SM instances); chunk
@@ -642,7 +671,7 @@ int mpcqp_scenario_run(mpcqp_handle* h, int ticks, int emit_inputs) {
     for (int t = 0; t < ticks; ++t) {
         h->sc.tick = h->scen_tick;
         const int first = h->scen_tick == 0 ? 1 : 0;
-        CU(cudaMemsetAsync(h->st.fb_count, 0, 4 * sizeof(int32_t), h->stream));     // fallback queue length + the stage-wise kernel's work counters
+        CU(begin_tick(h));
         h->solve(false, B, h->stream, nullptr, nullptr, first, 0, B, true);
         if ((h->p.mode & MPCQP_MODE_ADMM) && !(h->p.mode & MPCQP_MODE_ADMM_STAGEWISE)) {
             const int slots = h->ctas_per_sm(true) * h->sms;

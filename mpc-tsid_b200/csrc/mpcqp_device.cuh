@@ -60,6 +60,7 @@ struct DevState {
     uint32_t* active;   // B x ceil(20N/32)
     int32_t* fb_list;   // fallback queue (instance ids)
     int32_t* fb_count;  // its length
+    int32_t* fb_next;   // the next tick's copy of {fb_count, three work counters}: zeroed by this tick's stage-wise launch on the main stream (null: not this launch)
 };
 
 __host__ __device__ constexpr int tile_index(int I, int J) { return I * (I + 1) / 2 + J; }

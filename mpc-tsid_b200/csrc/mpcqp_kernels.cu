@@ -385,6 +385,7 @@ solve_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict_
     for (int i = tid; i < N * N; i += blockDim.x) sm.C2[i] = __ldg(P.C2 + i);
     __syncthreads();
 
+    if (ADMM) asm volatile("griddepcontrol.wait;" ::: "memory");     // programmatically dependent on the active-set launch (no-op otherwise)
     int n_work = ADMM ? *st.fb_count : inst_count;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int inst = ADMM ? st.fb_list[w] : w + inst_offset;

@@ -738,6 +738,13 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
     S& sm = reinterpret_cast<S*>(smem_raw)[warp * 2 + sub];
     double* ws = ws_g + (size_t)(gwarp * 2 + sub) * (RIC_GAIN + 4 * RIC_ADM) * N;      // per half-warp: stage gains, then ADMM state
     if (hl == 0) mbar_init(&sm.mbar, 1);
+    // the fallback kernel behind this one is launched programmatically dependent: let it become resident (its prologue runs, then it
+    // blocks in griddepcontrol.wait) as the CTAs of this persistent grid retire, instead of after the grid has drained
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (st.fb_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        // counters are double-buffered by tick: nobody uses the other copy during this tick
+        *reinterpret_cast<int4*>(st.fb_next) = make_int4(0, 0, 0, 0);
+    }
     __syncwarp();
     unsigned int phase = 0;
     // Work distribution: every warp takes its first pair of robots by position and every further pair from a counter, so a
