@@ -13,7 +13,9 @@ if os.environ.get("VREF_SCALE"):
     rng = np.random.default_rng(1); sc_ = float(os.environ["VREF_SCALE"])
     v = np.zeros((Bt, 6)); v[:, 0] = rng.uniform(-0.5, 1.0, Bt) * sc_; v[:, 1] = rng.uniform(-0.3, 0.3, Bt) * sc_; v[:, 5] = rng.uniform(-0.4, 0.4, Bt) * sc_
     kw["v_ref"] = v
-sc = Scenario(Bt, gaits="trot", seed=20260, **kw)
+if os.environ.get("NOISE") == "0":
+    kw["noise"] = (0.0, 0.0, 0.0, 0.0)
+sc = Scenario(Bt, gaits=os.environ.get("GAITS", "trot").split(","), seed=20260, **kw)
 eng = mpcqp.Engine(batch=Bt, n_steps=N, mode=mode, **({"max_iter": int(os.environ["MAX_ITER"])} if os.environ.get("MAX_ITER") else {}))
 Tt = 40
 xs, fs = [], []
