@@ -319,6 +319,46 @@ def test_pinned_and_pageable_host_inputs_agree(B, gaits):
     staged.close(); inplace.close()
 
 
+def test_engine_against_an_independent_solver():
+    """The engine against HiGHS' QP solver (bundled in scipy; see test_oracle_independent.py) on the QP the reference would have
+    built for seeded closed-loop robots of every gait: the engine's point is feasible for that QP, its objective is never above
+    HiGHS' and within HiGHS' accuracy of it.  No code of this repository's oracle solver is involved in the comparison."""
+    from oracle import mpc_build
+    from test_oracle_independent import hc, solve_highs
+    B, T = 12, 3
+    eng = mpcqp.Engine(batch=B)
+    sc = Scenario(B, gaits=["trot", "pace", "bound", "walk"], seed=4242)
+    par = mpc_build.Params(n_steps=N)
+    compared, abstained = 0, []
+    for t in range(T):
+        xref, fsteps = sc.inputs()
+        eng.run(t, xref, fsteps)
+        x, info = eng.solution(), eng.info(with_y=False)
+        assert (info["status"] == 1).all()
+        for b in range(B):
+            Pd, A, l, u, _ = mpc_build.build_qp(xref[b], fsteps[b], par, first_tick=(t == 0))
+            Ax = A @ x[b]
+            assert (Ax >= l - 1e-8).all() and (Ax <= u + 1e-8).all(), "tick %d robot %d: infeasible for the reference QP" % (t, b)
+            obj = 0.5 * float((Pd * x[b] * x[b]).sum())
+            assert abs(obj - info["obj"][b]) <= 1e-12 * max(1.0, abs(obj))
+            # HiGHS' QP solver gives up on some instances (kSolveError); it is a witness that may abstain, at two accuracies
+            for tol, gate in ((1e-10, 5e-6), (1e-7, 1e-4)):
+                xh, status = solve_highs(Pd, A, l, u, tol)
+                if status == hc.HighsModelStatus.kOptimal:
+                    break
+            else:
+                abstained.append((t, b, sc.kinds[b]))
+                continue
+            ref = 0.5 * float((Pd * xh * xh).sum())
+            slack = 10.0 * tol * float(np.abs(Pd * xh).sum())                 # what HiGHS' own infeasibility can buy it
+            assert obj <= ref + 1e-9 * abs(ref) + slack + 1e-13, (t, b, obj, ref)
+            assert ref - obj <= gate * abs(ref) + 1e-12, (t, b, obj, ref)
+            compared += 1
+        sc.advance(x[:, :12] + xref[:, :, 1])
+    assert compared >= (3 * B * T) // 4, "HiGHS abstained on %s" % abstained
+    eng.close()
+
+
 def test_full_batch_properties():
     """BASELINE configs[1] size (4096 robots): determinism, warm-start invariance, KKT on a sample,
     friction / unilateral / fz_max feasibility everywhere, objective consistent with x."""

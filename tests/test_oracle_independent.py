@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "solve_*.npz")) if "_N" not in os.path.basename(p))
 
 
-def solve_highs(Pd, A, l, u):
+def solve_highs(Pd, A, l, u, tol=1e-10):
     """min 1/2 x' diag(Pd) x  s.t.  l <= A x <= u  with HiGHS; returns (x, model status)."""
     n, m = len(Pd), A.shape[0]
     A = sp.csc_matrix(A)
@@ -41,8 +41,8 @@ def solve_highs(Pd, A, l, u):
     hs.start_, hs.index_, hs.value_ = np.arange(n + 1, dtype=np.int32), np.arange(n, dtype=np.int32), np.asarray(Pd, dtype=np.float64)
     h = hc._Highs()
     h.setOptionValue("output_flag", False)
-    h.setOptionValue("primal_feasibility_tolerance", 1e-10)
-    h.setOptionValue("dual_feasibility_tolerance", 1e-10)
+    h.setOptionValue("primal_feasibility_tolerance", tol)
+    h.setOptionValue("dual_feasibility_tolerance", tol)
     h.passModel(model)
     h.run()
     return np.array(h.getSolution().col_value), h.getModelStatus()
