@@ -1,3 +1,4 @@
+"""Second sweeps in steady trot: rate by gait phase, persistence from tick to tick, which step of the horizon changed."""
 import sys
 import numpy as np
 sys.path.insert(0, "/root/repo/mpc-tsid_b200"); sys.path.insert(0, "/root/repo")
