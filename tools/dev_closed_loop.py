@@ -1,4 +1,4 @@
-"""Closed loop of B robots on the engine, tick by tick against the numpy kernel model and the oracle certificate:\npython dev_closed_loop.py [B] [T] [gait,gait,...] [mode]"""
+"""Closed loop of B robots on the engine, tick by tick against the numpy kernel model and the oracle certificate: python dev_closed_loop.py [B] [T] [gait,gait,...] [mode]"""
 import sys, time
 import numpy as np
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/mpc-tsid_b200"); sys.path.insert(0, "/root/repo/tests")
