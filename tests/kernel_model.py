@@ -461,8 +461,9 @@ def riccati_faces(p, contact, sig):
     return Z, pf, dinv
 
 
-def riccati_solve(p, xref, Bv, contact, sig):
-    """-> f (N,4,3), grad (N,4,3) = H f + g of the condensed problem, X (N,12) states 1..N."""
+def riccati_solve(p, xref, Bv, contact, sig, keep=False):
+    """-> f (N,4,3), grad (N,4,3) = H f + g of the condensed problem, X (N,12) states 1..N.
+    keep=True also returns the per-stage blocks a one-direction update on this factorisation needs (riccati_one_direction)."""
     N, dt = p.N, p.dt
     Z, pf, dinv = riccati_faces(p, contact, sig)
     Qp, Qv = p.w_state[0:6], p.w_state[6:12]
@@ -493,9 +494,9 @@ def riccati_solve(p, xref, Bv, contact, sig):
         Y = Ppv @ Linv.T                   # Ppv L^-T
         Y2 = Y @ Minv.T
         Gam = Linv.T @ (I6 - Minv.T @ Minv) @ Linv
-        store[k] = (Ppv.copy(), Pvv.copy(), pv.copy(), Gam)
         Ptvv = X @ X.T
         Ptpv = Y2 @ X.T
+        store[k] = (Ppv.copy(), Pvv.copy(), pv.copy(), Gam, Ptpv, Ptvv)
         Ptpp = Ppp - Y @ Y.T + Y2 @ Y2.T
         gp = Gam @ pv
         ptp = pp - Ppv @ gp
@@ -514,7 +515,7 @@ def riccati_solve(p, xref, Bv, contact, sig):
     Xs = np.zeros((N, 12))
     lam = np.zeros((N, 6))
     for k in range(N):
-        Ppv_, Pvv_, pv_, Gam = store[k]
+        Ppv_, Pvv_, pv_, Gam = store[k][:4]
         zp = xp + dt * xv
         zv = xv + beta[k]
         l0 = Ppv_.T @ zp + Pvv_ @ zv + pv_
@@ -531,7 +532,79 @@ def riccati_solve(p, xref, Bv, contact, sig):
                 q = -dinv[k, j] * (Bq.T @ lam[k])
                 f[k, j] = pf[k, j] + Z[k, j] @ q
                 grad[k, j] = p.w_force * f[k, j] + Bv[k, j].T @ lam[k]
+    if keep:
+        return f, grad, Xs, dict(store=store, Z=Z, dinv=dinv)
     return f, grad, Xs
+
+
+def riccati_one_direction(p, Bv, contact, kept, ks, js, e):
+    """Response of the equality-constrained optimum to moving foot-step (ks, js) by a unit along direction e (3-vector in
+    force space), every face and every 6x6 factorisation of the kept solve unchanged: the impulse offset of stage ks grows by
+    Bv e and nothing else does, so only the *vector* half of the recursion runs -- backward from ks to 1 (no matrix
+    recursion, no factorisation), forward over the whole horizon.  -> df (N,4,3) on the kept faces (the e itself not
+    included), dgrad (N,4,3), dX (N,12).  Round-2 plan of DESIGN.md 9.1: a second sweep at a quarter of the cost."""
+    N, dt = p.N, p.dt
+    store, Z, dinv = kept["store"], kept["Z"], kept["dinv"]
+    dbeta = Bv[ks, js] @ e
+    # backward, vector only: above ks nothing changes
+    dpv_in = [np.zeros(6) for _ in range(N)]                  # change of the p-vector (v half) each stage's forward step reads
+    dpp_in = [np.zeros(6) for _ in range(N)]
+    pp, pv = np.zeros(6), np.zeros(6)
+    for k in range(ks, 0, -1):
+        Ppv, Pvv, _, Gam, Ptpv, Ptvv = store[k]
+        gp = Gam @ pv
+        ptp, ptv = pp - Ppv @ gp, pv - Pvv @ gp
+        b = dbeta if k == ks else np.zeros(6)
+        hp, hv = Ptpv @ b + ptp, Ptvv @ b + ptv
+        pp, pv = hp, dt * hp + hv
+        dpp_in[k - 1], dpv_in[k - 1] = pp, pv
+    # forward from a fixed initial state
+    xp, xv = np.zeros(6), np.zeros(6)
+    dX = np.zeros((N, 12))
+    dlam = np.zeros((N, 6))
+    for k in range(N):
+        Ppv, Pvv, _, Gam = store[k][:4]
+        zp = xp + dt * xv
+        zv = xv + (dbeta if k == ks else 0.0)
+        l0 = Ppv.T @ zp + Pvv @ zv + dpv_in[k]
+        w = -Gam @ l0
+        xp, xv = zp, zv + w
+        dlam[k] = l0 + Pvv @ w
+        dX[k, 0:6], dX[k, 6:12] = xp, xv
+    df = np.zeros((N, 4, 3))
+    dgrad = np.zeros((N, 4, 3))
+    for k in range(N):
+        for j in range(4):
+            if contact[k, j]:
+                Bq = Bv[k, j] @ Z[k, j]
+                df[k, j] = Z[k, j] @ (-dinv[k, j] * (Bq.T @ dlam[k]))
+                dgrad[k, j] = p.w_force * df[k, j] + Bv[k, j].T @ dlam[k]
+    return df, dgrad, dX
+
+
+def riccati_change_one_row(p, Bv, contact, kept, f, grad, X, ks, js, release=None, activate=None):
+    """The optimum on a face that differs from the kept one in ONE row of foot-step (ks, js), from the kept solve plus one
+    riccati_one_direction.  release = d (3,): a force direction that becomes free (its component orthogonal to the kept face is
+    used; the step length follows from stationarity along it).  activate = (c (3,), b): a row c'f = b that becomes active (the
+    step runs along the component of c inside the kept face; its length follows from feasibility)."""
+    Zk = kept["Z"][ks, js]
+    zz = np.sum(Zk * Zk, axis=0)
+    proj = lambda v: Zk @ (np.where(zz > 0, (Zk.T @ v) / np.where(zz > 0, zz, 1.0), 0.0))      # Z'Z is diagonal
+    if release is not None:
+        e = release - proj(release)
+        df, dgrad, dX = riccati_one_direction(p, Bv, contact, kept, ks, js, e)
+        g0 = e @ grad[ks, js]
+        g1 = e @ (dgrad[ks, js] + p.w_force * e)             # grad(step)[ks, js] = grad + step (dgrad + w_f e)
+        step = -g0 / g1
+    else:
+        c, b = activate
+        e = proj(c)
+        df, dgrad, dX = riccati_one_direction(p, Bv, contact, kept, ks, js, e)
+        step = (b - c @ f[ks, js]) / (c @ (df[ks, js] + e))
+    f2, g2 = f + step * df, grad + step * dgrad
+    f2[ks, js] += step * e
+    g2[ks, js] += step * p.w_force * e
+    return f2, g2, X + step * dX
 
 
 def riccati_stage_ldl(Ppp, Ppv, Pvv, pp, pv, E):

@@ -84,3 +84,47 @@ def test_square_root_free_stage_equals_the_cholesky_form():
         rows = np.vstack([Ppv, Pvv, pv[None, :]])
         np.testing.assert_allclose(kr, rows @ Gam, rtol=1e-9, atol=1e-9 * np.abs(rows @ Gam).max())
         np.testing.assert_allclose(tr, rows @ (np.eye(6) - Gam @ Pvv), rtol=1e-9, atol=1e-9 * np.abs(rows).max())
+
+
+def test_one_row_change_on_the_kept_factorisation_equals_a_full_resolve():
+    """Round-2 groundwork: when the guard rejects a sweep because ONE friction row of ONE foot-step is on the
+    wrong side (99.7 % of the rejected first sweeps in steady trot), the optimum on the corrected face follows from the kept
+    factorisation by one vector-only pass and a scalar step -- no new 6x6 factorisations.  Checked here on the numpy model in both
+    directions (a row that must be released, a row that must become active) against solving the corrected face from scratch."""
+    p = km.ModelParams()
+    mu = p.mu
+    checked = {"release": 0, "activate": 0}
+    for name, t in (("trot", 1), ("trot", 7), ("aggressive", 2), ("pace", 3), ("bound", 2)):
+        g = np.load([q for q in GOLD if q.endswith("solve_%s.npz" % name)][0])
+        xref, fsteps = g["xref"][t], g["fsteps"][t]
+        contact, Bv = km.decode(p, xref, fsteps)
+        fstar = g["x"][t][12 * p.N:].reshape(p.N, 4, 3)
+        sig_opt = _sig_from_forces(p, fstar, contact)
+        f_ref, grad_ref, X_ref = km.riccati_solve(p, xref, Bv, contact, sig_opt)
+        for ks in range(p.N):
+            for js in range(4):
+                if not contact[ks, js] or sig_opt[ks, js, 2] != 0:
+                    continue
+                for axis in (0, 1):
+                    wrong = sig_opt.copy()
+                    unit = np.eye(3)[axis]
+                    if sig_opt[ks, js, axis] == 0:
+                        # the first sweep wrongly held the row (+1 side) active: release it
+                        wrong[ks, js, axis] = 1
+                        f0, g0, X0, kept = km.riccati_solve(p, xref, Bv, contact, wrong, keep=True)
+                        f1, g1, X1 = km.riccati_change_one_row(p, Bv, contact, kept, f0, g0, X0, ks, js, release=unit)
+                        checked["release"] += 1
+                    else:
+                        # the first sweep wrongly left the row free: activate it
+                        sgn = float(sig_opt[ks, js, axis])
+                        wrong[ks, js, axis] = 0
+                        c = sgn * unit - np.array([0.0, 0.0, mu])
+                        f0, g0, X0, kept = km.riccati_solve(p, xref, Bv, contact, wrong, keep=True)
+                        f1, g1, X1 = km.riccati_change_one_row(p, Bv, contact, kept, f0, g0, X0, ks, js, activate=(c, 0.0))
+                        checked["activate"] += 1
+                    np.testing.assert_allclose(f1, f_ref, rtol=0, atol=1e-8)
+                    np.testing.assert_allclose(X1, X_ref, rtol=0, atol=1e-9)
+                    live = contact[:, :, None] & np.ones(3, bool)
+                    live[ks, js] = False                      # at the changed foot-step the two faces define grad on different rows
+                    np.testing.assert_allclose(g1[live], grad_ref[live], rtol=0, atol=1e-8)
+    assert checked["release"] > 50 and checked["activate"] > 3, checked
