@@ -41,7 +41,8 @@ extern "C" {
 /* per-instance status written by mpcqp_run */
 #define MPCQP_STATUS_UNSOLVED 0
 #define MPCQP_STATUS_SOLVED 1          /* active-set polished, KKT-verified (exact to rounding) */
-#define MPCQP_STATUS_MAX_ITER 2        /* ADMM iterate returned at max_iter, not polished */
+#define MPCQP_STATUS_MAX_ITER 2        /* the fallback stage ran out of iterations: a feasible (inside the friction pyramid), uncertified
+                                          iterate is returned, x[:12N] is the roll-out of exactly these forces */
 #define MPCQP_STATUS_BAD_INPUT 3       /* non-finite state / malformed gait table; forces are 0 */
 
 /* solver stages that may run (bit mask in mpcqp_params.mode) */
@@ -49,8 +50,9 @@ extern "C" {
 #define MPCQP_MODE_ADMM 2           /* fixed-rho ADMM + guarded polish (globally convergent)    */
 #define MPCQP_MODE_STAGEWISE 4      /* active-set stage factorises stage by stage (Riccati recursion over the horizon, one warp per
                                        robot, O(N)) instead of the dense 6N x 6N condensed system (one CTA per robot, O(N^3))      */
-#define MPCQP_MODE_ADMM_STAGEWISE 8 /* the ADMM stage iterates on the stage-wise factorisation too, inside the active-set kernel (no
-                                       second kernel, any horizon; slower per iteration than the dense ADMM stage for N <= 32)     */
+#define MPCQP_MODE_IPM 8            /* fallback stage of the stage-wise path: primal-dual interior-point iterations on the stage-wise
+                                       factorisation (any horizon, ~20 factorisations whatever the active set), then active-set
+                                       sweeps from the rows it identifies; takes precedence over MPCQP_MODE_ADMM when both are set   */
 
 typedef struct mpcqp_handle mpcqp_handle;
 
@@ -58,7 +60,7 @@ typedef struct mpcqp_handle mpcqp_handle;
  * mpcqp_default_params() first, then override. */
 typedef struct mpcqp_params {
     int32_t struct_size;        /* = sizeof(mpcqp_params), ABI check */
-    int32_t n_steps;            /* horizon N            (MPC.py:42)   */
+    int32_t n_steps;            /* horizon N, 1 .. 64   (MPC.py:42; main.py:23: n_periods * T_gait / dt); the dense stages: 16, 32 */
     int32_t batch;              /* B independent robots               */
     int32_t device;             /* CUDA device ordinal                */
     double dt;                  /* MPC.py:25 */
@@ -72,8 +74,8 @@ typedef struct mpcqp_params {
     double w_state[12];         /* diagonal state weights    (MPC.py:255-275) */
     double w_force;             /* force weight              (MPC.py:282-284) */
     /* solver */
-    int32_t mode;               /* MPCQP_MODE_* mask, default ACTIVE_SET | ADMM | STAGEWISE */
-    int32_t max_sweeps;         /* active-set sweeps before falling back to ADMM */
+    int32_t mode;               /* MPCQP_MODE_* mask, default ACTIVE_SET | STAGEWISE | IPM */
+    int32_t max_sweeps;         /* active-set sweeps before the fallback stage takes over */
     int32_t max_iter;           /* ADMM iteration cap */
     int32_t min_iter;           /* ADMM iterations before the first polish attempt */
     int32_t check_every;        /* ADMM iterations between active-set stability checks */
@@ -84,7 +86,7 @@ typedef struct mpcqp_params {
     double feas_tol;            /* primal feasibility tolerance of the KKT guard [N] */
     double dual_tol;            /* multiplier sign tolerance of the KKT guard */
     int32_t refine;             /* iterative-refinement passes per equality-constrained solve (0 or 1) */
-    int32_t reserved;
+    int32_t ipm_max_iter;       /* interior-point iterations per round (two rounds: gap 1e-8, then 1e-11) */
 } mpcqp_params;
 
 /* Reference constants of MPC.py:22-82 for the Solo trot configuration (dt 0.02, N 16, T_gait 0.32). */
@@ -107,14 +109,14 @@ int mpcqp_get_latest_result(mpcqp_handle* h, double* forces, int location);
 int mpcqp_get_solution(mpcqp_handle* h, double* x, int location);
 
 /* Per-instance diagnostics the reference never exposes (it ignores sol.info.status, MPC.py:427):
- * any pointer may be NULL.  status[B], sweeps[B] (active-set factorizations), iters[B] (ADMM
- * iterations), obj[B] (1/2 x'Px), contact[B*ceil(4N/32)] (4N bits: bit 4k+j = foot j in stance at step k),
+ * any pointer may be NULL.  status[B], sweeps[B] (active-set factorizations), iters[B] (iterations of the
+ * fallback stage: interior-point or ADMM), obj[B] (1/2 x'Px), contact[B*ceil(4N/32)] (4N bits: bit 4k+j = foot j in stance at step k),
  * active[B*ceil(20N/32)] (bit 20k+5j+r = pyramid row r of foot j at step k holds with equality),
  * y[B*20N] multipliers of the pyramid rows (rows of L in MPC.py:136-148). */
 int mpcqp_get_info(mpcqp_handle* h, int32_t* status, int32_t* sweeps, int32_t* iters, double* obj,
                    uint32_t* contact, uint32_t* active, double* y, int location);
 
-/* Number of instances the last run sent to the ADMM stage (host int). */
+/* Number of instances the last run sent to the fallback stage (host int). */
 int mpcqp_get_fallback_count(mpcqp_handle* h, int32_t* count);
 
 /* Forget the carried solution (what a fresh osqp.OSQP() + k == 0 does in the reference). */

@@ -78,21 +78,37 @@ namespace mpcqp {
 #define RIC_DECL(N)                                                                                                   \
     cudaError_t ric_configure_##N(int* ctas_per_sm);                                                                  \
     void ric_launch_##N(int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,      \
-                        const double* dx, const double* df, double* ws, int* ctr, int first, int off, int n_inst);
+                        const double* dx, const double* df, double* ws, int* ctr, int first, int off, int n_inst);     \
+    void ipm_launch_##N(int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,      \
+                        const double* dx, const double* df, double* ws, int first);
 RIC_DECL(16) RIC_DECL(32) RIC_DECL(64)
 #undef RIC_DECL
 }  // namespace mpcqp
 
-void launch_stagewise(int N, int n_inst, int max_ctas, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
-                      const double* dx, const double* df, double* ws, int* ctr, bool reset_ctr, int first, int off) {
+// the capacity class (compiled instantiation) that holds a horizon of n steps
+static int ric_capacity(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : 64); }
+
+cudaError_t launch_stagewise(int cap, int n_inst, int max_ctas, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
+                             const double* dx, const double* df, double* ws, int* ctr, bool reset_ctr, int first, int off) {
     int grid = (n_inst + RIC_PER_CTA - 1) / RIC_PER_CTA;
     if (grid > max_ctas) grid = max_ctas;                      // persistent: one workspace slot per resident half-warp
     // the kernel's work counter (pairs of robots beyond the first per warp) must be zero at launch: on the handle's main stream
     // the caller's reset of the fallback queue covers it (one 16-byte memset), on a side stream it is reset here
-    if (reset_ctr) cudaMemsetAsync(ctr, 0, sizeof(int), s);
-    if (N == 16) ric_launch_16(grid, s, dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
-    else if (N == 32) ric_launch_32(grid, s, dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
+    if (reset_ctr) {
+        const cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(int), s);
+        if (e != cudaSuccess) return e;
+    }
+    if (cap == 16) ric_launch_16(grid, s, dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
+    else if (cap == 32) ric_launch_32(grid, s, dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
     else ric_launch_64(grid, s, dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
+    return cudaSuccess;
+}
+
+void launch_ipm(int cap, int max_ctas, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
+                const double* dx, const double* df, double* ws, int first) {
+    if (cap == 16) ipm_launch_16(max_ctas, s, dp, st, sc, dx, df, ws, first);
+    else if (cap == 32) ipm_launch_32(max_ctas, s, dp, st, sc, dx, df, ws, first);
+    else ipm_launch_64(max_ctas, s, dp, st, sc, dx, df, ws, first);
 }
 
 template <int N>
@@ -143,18 +159,29 @@ struct mpcqp_handle {
     int scen_tick = 0;
     bool scen_ready = false;
 
+    cudaError_t launch_err = cudaSuccess;           // first error of a launch helper since the last check
+
+    // fallback stage of this tick for the robots in the queue: the interior-point kernel (stage-wise path) or the dense ADMM kernel
+    bool fallback_is_ipm() const { return (p.mode & MPCQP_MODE_STAGEWISE) && (p.mode & MPCQP_MODE_IPM); }
+    bool has_fallback() const { return fallback_is_ipm() || (p.mode & MPCQP_MODE_ADMM); }
+
     void solve(bool admm, int grid, cudaStream_t s, const double* dx, const double* df, int first, int off, int n,
                bool closed_loop = false) {
         DevScenario use = sc;
         use.enabled = closed_loop ? 1 : 0;
-        if (!admm && (p.mode & MPCQP_MODE_STAGEWISE)) {
+        if (admm && fallback_is_ipm()) {
+            // the main stream's workspace: every active-set launch of this tick has been joined into `s` by now
+            launch_ipm(ric_capacity(p.n_steps), ric_max_ctas, s, dp, st, use, dx, df, d_ric_ws, first);
+        } else if (!admm && (p.mode & MPCQP_MODE_STAGEWISE)) {
             // active-set stage on the stage-wise factorisation: half a warp per robot, persistent grid; every stream
             // that may run it concurrently has its own gain workspace
             const int lane_of_stream = s == side[0] ? 1 : (s == side[1] ? 2 : 0);
             double* ws = d_ric_ws + (size_t)lane_of_stream * ric_ws_doubles;
             DevState stl = st;
             if (lane_of_stream == 0) { stl.fb_next = ctr_base + 8 * (ctr_parity ^ 1); zero_next = true; }
-            launch_stagewise(p.n_steps, n, ric_max_ctas, s, dp, stl, use, dx, df, ws, st.fb_count + 1 + lane_of_stream, lane_of_stream != 0, first, off);
+            const cudaError_t e = launch_stagewise(ric_capacity(p.n_steps), n, ric_max_ctas, s, dp, stl, use, dx, df, ws,
+                                                   st.fb_count + 1 + lane_of_stream, lane_of_stream != 0, first, off);
+            if (e != cudaSuccess && launch_err == cudaSuccess) launch_err = e;
         } else if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         else launch_solve<32>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         ++launches;
@@ -162,6 +189,18 @@ struct mpcqp_handle {
     int ctas_per_sm(bool admm) const { return p.n_steps == 16 ? (admm ? 2 : 4) : 1; }
     // robots of the active-set stage that are resident at once (one wave)
     int wave(void) const { return (p.mode & MPCQP_MODE_STAGEWISE) ? ric_max_ctas * RIC_PER_CTA : ctas_per_sm(false) * sms; }
+
+    int32_t* d_all = nullptr;       // ADMM-only mode: 0 .. B-1, then B (the queue that holds every robot)
+    double* d_scratch = nullptr;    // device staging of the diagnostics that are computed on request (export_build, cost components)
+    size_t scratch_bytes = 0;
+    cudaError_t scratch(size_t bytes) {
+        if (bytes <= scratch_bytes) return cudaSuccess;
+        if (d_scratch) cudaFree(d_scratch);
+        d_scratch = nullptr; scratch_bytes = 0;
+        const cudaError_t e = cudaMalloc(&d_scratch, bytes);
+        if (e == cudaSuccess) scratch_bytes = bytes;
+        return e;
+    }
 
     double* d_ric_ws = nullptr;     // stage-wise path: per-stage gains of the resident robots, x3 (main + two side streams)
     size_t ric_ws_doubles = 0;
@@ -199,8 +238,8 @@ void mpcqp_default_params(mpcqp_params* p) {
     for (int i = 0; i < 3; ++i) p->w_state[6 + i] = 2.0 * std::sqrt(p->w_state[i]);
     for (int i = 0; i < 3; ++i) p->w_state[9 + i] = 0.05 * std::sqrt(p->w_state[3 + i]);
     p->w_force = 1e-5;                                      // MPC.py:282-284
-    p->mode = MPCQP_MODE_ACTIVE_SET | MPCQP_MODE_ADMM | MPCQP_MODE_STAGEWISE;
-    p->max_sweeps = 12;
+    p->mode = MPCQP_MODE_ACTIVE_SET | MPCQP_MODE_STAGEWISE | MPCQP_MODE_IPM;
+    p->max_sweeps = 16;
     p->max_iter = 1000;
     p->min_iter = 10;
     p->check_every = 5;
@@ -211,6 +250,7 @@ void mpcqp_default_params(mpcqp_params* p) {
     p->feas_tol = 1e-9;
     p->dual_tol = 1e-12;
     p->refine = 0;
+    p->ipm_max_iter = 60;
 }
 
 int mpcqp_destroy(mpcqp_handle* h) {
@@ -224,6 +264,8 @@ int mpcqp_destroy(mpcqp_handle* h) {
     cudaFree(h->d_block);
     cudaFree(h->d_scen);
     cudaFree(h->d_ric_ws);
+    cudaFree(h->d_all);
+    cudaFree(h->d_scratch);
     for (int i = 0; i < 2; ++i) {
         if (h->pin[i]) cudaFreeHost(h->pin[i]);
         if (h->ev_pin[i]) cudaEventDestroy(h->ev_pin[i]);
@@ -242,12 +284,16 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     if (!p || !out) return fail(MPCQP_ERR_INVALID, "null argument");
     *out = nullptr;
     if (p->struct_size != (int32_t)sizeof(mpcqp_params)) return fail(MPCQP_ERR_INVALID, "mpcqp_params.struct_size mismatch");
-    if (p->n_steps != 16 && p->n_steps != 32 && p->n_steps != 64)
-        return fail(MPCQP_ERR_INVALID, "n_steps: this build supports horizons of 16, 32 and 64 steps");
-    if (p->n_steps == 64 && (!(p->mode & MPCQP_MODE_STAGEWISE) || ((p->mode & MPCQP_MODE_ADMM) && !(p->mode & MPCQP_MODE_ADMM_STAGEWISE))))
-        return fail(MPCQP_ERR_INVALID, "n_steps = 64 needs the stage-wise stages: MPCQP_MODE_STAGEWISE, and MPCQP_MODE_ADMM_STAGEWISE with MPCQP_MODE_ADMM");
-    if ((p->mode & MPCQP_MODE_ADMM_STAGEWISE) && (p->mode & (MPCQP_MODE_STAGEWISE | MPCQP_MODE_ADMM)) != (MPCQP_MODE_STAGEWISE | MPCQP_MODE_ADMM))
-        return fail(MPCQP_ERR_INVALID, "MPCQP_MODE_ADMM_STAGEWISE runs inside the stage-wise active-set kernel: set MPCQP_MODE_STAGEWISE and MPCQP_MODE_ADMM too");
+    if (p->n_steps < 1 || p->n_steps > 64)
+        return fail(MPCQP_ERR_INVALID, "n_steps: horizons of 1 .. 64 steps are supported");
+    // the dense kernels (MPCQP_MODE_ACTIVE_SET without MPCQP_MODE_STAGEWISE, and the MPCQP_MODE_ADMM stage) exist for N = 16 and 32 only
+    const bool dense_ok = p->n_steps == 16 || p->n_steps == 32;
+    const bool ipm_fallback = (p->mode & MPCQP_MODE_STAGEWISE) && (p->mode & MPCQP_MODE_IPM);
+    const bool needs_dense = !(p->mode & MPCQP_MODE_STAGEWISE) || ((p->mode & MPCQP_MODE_ADMM) && !ipm_fallback);
+    if (needs_dense && !dense_ok)
+        return fail(MPCQP_ERR_INVALID, "the dense stages exist for n_steps = 16 and 32 only: use MPCQP_MODE_ACTIVE_SET | MPCQP_MODE_STAGEWISE | MPCQP_MODE_IPM");
+    if ((p->mode & MPCQP_MODE_IPM) && !(p->mode & MPCQP_MODE_STAGEWISE))
+        return fail(MPCQP_ERR_INVALID, "MPCQP_MODE_IPM is the fallback stage of the stage-wise path: set MPCQP_MODE_STAGEWISE too");
     if ((p->mode & MPCQP_MODE_STAGEWISE) && !(p->mode & MPCQP_MODE_ACTIVE_SET))
         return fail(MPCQP_ERR_INVALID, "MPCQP_MODE_STAGEWISE selects the factorisation of the active-set stage: set MPCQP_MODE_ACTIVE_SET too");
     if (p->batch < 1) return fail(MPCQP_ERR_INVALID, "batch must be >= 1");
@@ -290,12 +336,14 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     d.max_sweeps = p->max_sweeps; d.max_iter = p->max_iter; d.min_iter = p->min_iter > 0 ? p->min_iter : 1;
     d.check_every = p->check_every > 0 ? p->check_every : 1;
     d.warm_start = p->warm_start; d.mode = p->mode; d.refine = p->refine > 0 ? 1 : 0;
+    d.ipm_max_iter = p->ipm_max_iter > 0 ? p->ipm_max_iter : 60;
 
     // Gram matrices of the double-integrator response and their inverses (constant per handle)
     //   M_c[k,l] = sum_{i >= max(k,l)} ( dt^2 Qp_c (i-k)(i-l) + Qv_c ),  i = 0..N-1
-    const int n = 6 * N, NT = n / 8, NTILES = NT * (NT + 1) / 2;
+    // (dense kernels only: 6 N must fill whole 8 x 8 tiles)
+    const int n = 6 * N, NT = (n + 7) / 8, NTILES = NT * (NT + 1) / 2;
     std::vector<double> C2((size_t)N * N), Mt((size_t)NTILES * 64, 0.0);
-    for (int c = 0; c < 6; ++c) {
+    for (int c = 0; c < 6 && dense_ok; ++c) {
         std::vector<long double> m((size_t)N * N);
         for (int k = 0; k < N; ++k)
             for (int l = 0; l < N; ++l) {
@@ -354,14 +402,23 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     h->st.sig = (uint8_t*)(base + o_sig);
     CUH(cudaMemset(h->st.sig, SIG_FREE, (size_t)B * 4 * N));
     int ric_per_sm = 0;
-    if (N == 16) { CUH(configure_kernels<16>()); CUH(ric_configure_16(&ric_per_sm)); }
-    else if (N == 32) { CUH(configure_kernels<32>()); CUH(ric_configure_32(&ric_per_sm)); }
-    else { CUH(ric_configure_64(&ric_per_sm)); }
+    const int cap = ric_capacity(N);
+    if (N == 16) CUH(configure_kernels<16>());
+    else if (N == 32) CUH(configure_kernels<32>());
+    if (cap == 16) CUH(ric_configure_16(&ric_per_sm));
+    else if (cap == 32) CUH(ric_configure_32(&ric_per_sm));
+    else CUH(ric_configure_64(&ric_per_sm));
     if (p->mode & MPCQP_MODE_STAGEWISE) {
         if (ric_per_sm < 1) return bail(fail(MPCQP_ERR_CUDA, "the stage-wise kernel does not fit on this device"));
         h->ric_max_ctas = ric_per_sm * h->sms;
-        h->ric_ws_doubles = (size_t)h->ric_max_ctas * RIC_PER_CTA * (RIC_GAIN + 4 * RIC_ADM) * N;
+        h->ric_ws_doubles = (size_t)h->ric_max_ctas * RIC_PER_CTA * (RIC_GAIN + 4 * RIC_ADM) * cap;
         CUH(cudaMalloc(&h->d_ric_ws, 3 * h->ric_ws_doubles * sizeof(double)));
+    }
+    if (!(p->mode & MPCQP_MODE_ACTIVE_SET)) {
+        std::vector<int32_t> all((size_t)B + 1);
+        for (int i = 0; i <= B; ++i) all[i] = i;
+        CUH(cudaMalloc(&h->d_all, all.size() * 4));
+        CUH(cudaMemcpy(h->d_all, all.data(), all.size() * 4, cudaMemcpyHostToDevice));
     }
 #undef CUH
     *out = h;
@@ -449,17 +506,15 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
         h->solve(false, B, h->stream, dx, df, first, 0, B);
     }
     if (!stageA) {
-        // ADMM only: queue every instance
-        std::vector<int32_t> all(B);
-        for (int i = 0; i < B; ++i) all[i] = i;
-        CU(cudaMemcpyAsync(h->st.fb_list, all.data(), (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemcpyAsync(h->st.fb_count, &B, 4, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+        // ADMM only: queue every instance (the identity list and its length were uploaded once, at creation)
+        CU(cudaMemcpyAsync(h->st.fb_list, h->d_all, (size_t)B * 4, cudaMemcpyDeviceToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->st.fb_count, h->d_all + B, 4, cudaMemcpyDeviceToDevice, h->stream));
     }
-    if ((h->p.mode & MPCQP_MODE_ADMM) && !(h->p.mode & MPCQP_MODE_ADMM_STAGEWISE)) {
+    if (h->has_fallback()) {
         const int slots = h->ctas_per_sm(true) * h->sms;
         h->solve(true, B < slots ? B : slots, h->stream, dx, df, first, 0, B);
     }
+    CU(h->launch_err);
     CU(cudaGetLastError());
     h->ran = true;
     return MPCQP_OK;
@@ -558,13 +613,12 @@ int mpcqp_export_build(mpcqp_handle* h, double k, const double* xref, const doub
     double *dB, *dS, *dN;
     const bool host = location == MPCQP_HOST;
     if (host) {
-        CU(cudaMalloc(&dB, B * 48 * N * 8)); CU(cudaMalloc(&dS, B * 12 * N * 8)); CU(cudaMalloc(&dN, B * 12 * N * 8));
+        CU(h->scratch(B * 72 * N * 8));
+        dB = h->d_scratch; dS = dB + B * 48 * N; dN = dS + B * 12 * N;
     } else {
         dB = B_vals; dS = S_vals; dN = NK;
     }
-    if (N == 16) export_build_kernel<16><<<(int)B, 128, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
-    else if (N == 32) export_build_kernel<32><<<(int)B, 128, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
-    else export_build_kernel<64><<<(int)B, 256, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
+    export_build_kernel<<<(int)B, N > 32 ? 256 : 128, 0, h->stream>>>(h->dp, dx, df, k == 0.0 ? 1 : 0, dB, dS, dN);
     ++h->launches;
     CU(cudaGetLastError());
     if (host) {
@@ -573,7 +627,6 @@ int mpcqp_export_build(mpcqp_handle* h, double k, const double* xref, const doub
         CU(cudaMemcpyAsync(NK, dN, B * 12 * N * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     CU(cudaStreamSynchronize(h->stream));
-    if (host) { cudaFree(dB); cudaFree(dS); cudaFree(dN); }
     return MPCQP_OK;
 }
 
@@ -621,7 +674,10 @@ int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* pha
     if (!h || !seq || !phase || !vref || !state || !sigma4) return fail(MPCQP_ERR_INVALID, "null argument");
     const size_t B = h->p.batch;
     const int N = h->p.n_steps;
-    if (std::fabs(h->p.T_gait / h->p.dt - 16.0) > 1e-9) return fail(MPCQP_ERR_INVALID, "closed loop needs a 16-step gait period (T_gait / dt)");
+    // the gait period is T_gait / dt steps (FootstepPlanner.py:52-63); `seq` holds 4 bits per step, so up to 16 steps
+    const int period = (int)std::lround(h->p.T_gait / h->p.dt);
+    if (period < 1 || period > 16 || std::fabs(h->p.T_gait / h->p.dt - period) > 1e-9)
+        return fail(MPCQP_ERR_INVALID, "closed loop needs a gait period T_gait / dt of 1 .. 16 whole steps");
     CU(cudaSetDevice(h->p.device));
     CU(cudaStreamSynchronize(h->stream));
     size_t off = 0;
@@ -649,10 +705,11 @@ int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* pha
     // numpy.linspace(start, stop, N): start + i * step with the last element set to stop exactly
     const double a0 = 0.0, a1 = h->p.T_gait - h->p.dt, b0 = h->p.dt, b1 = h->p.T_gait;
     for (int i = 0; i < N; ++i) {
-        s.lin_a[i] = (i == N - 1) ? a1 : a0 + i * ((a1 - a0) / (N - 1));
-        s.lin_b[i] = (i == N - 1) ? b1 : b0 + i * ((b1 - b0) / (N - 1));
+        s.lin_a[i] = (N == 1) ? a0 : ((i == N - 1) ? a1 : a0 + i * ((a1 - a0) / (N - 1)));
+        s.lin_b[i] = (N == 1) ? b0 : ((i == N - 1) ? b1 : b0 + i * ((b1 - b0) / (N - 1)));
     }
     s.seed = seed;
+    s.period = period;
     h->scen_tick = 0;
     h->scen_ready = true;
     CU(mpcqp_reset_warm_start(h) == 0 ? cudaSuccess : cudaErrorUnknown);
@@ -673,7 +730,7 @@ int mpcqp_scenario_run(mpcqp_handle* h, int ticks, int emit_inputs) {
         const int first = h->scen_tick == 0 ? 1 : 0;
         CU(begin_tick(h));
         h->solve(false, B, h->stream, nullptr, nullptr, first, 0, B, true);
-        if ((h->p.mode & MPCQP_MODE_ADMM) && !(h->p.mode & MPCQP_MODE_ADMM_STAGEWISE)) {
+        if (h->has_fallback()) {
             const int slots = h->ctas_per_sm(true) * h->sms;
             h->solve(true, B < slots ? B : slots, h->stream, nullptr, nullptr, first, 0, B, true);
         }
@@ -714,14 +771,13 @@ int mpcqp_get_cost_components(mpcqp_handle* h, double* cost, int location) {
     CU(cudaSetDevice(h->p.device));
     const size_t B = h->p.batch, bytes = B * 13 * sizeof(double);
     double* d = cost;
-    if (location == MPCQP_HOST) CU(cudaMalloc(&d, bytes));
+    if (location == MPCQP_HOST) { CU(h->scratch(bytes)); d = h->d_scratch; }
     cost_components_kernel<<<(int)((B + 3) / 4), 128, 0, h->stream>>>(h->dp, h->st, h->p.n_steps, d);
     ++h->launches;
     CU(cudaGetLastError());
     if (location == MPCQP_HOST) {
         CU(cudaMemcpyAsync(cost, d, bytes, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        cudaFree(d);
     }
     return MPCQP_OK;
 }

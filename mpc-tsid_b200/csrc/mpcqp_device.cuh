@@ -40,7 +40,7 @@ struct DevParams {
     double footholds[12];   // 3 x 4 row major
     double wp[6], wv[6];    // state weights: position-like (x y z roll pitch yaw) and velocity-like
     double rho, sigma, alpha, feas_tol, dual_tol;
-    int max_sweeps, max_iter, min_iter, check_every, warm_start, mode, refine;
+    int max_sweeps, max_iter, min_iter, check_every, warm_start, mode, refine, ipm_max_iter;
     const double* Minv_tiled;   // lower block triangle of M^-1 in the smem tile layout
     const double* C2;           // N x N: C2[k,l] = sum_{i >= max(k,l)} (i-k)(i-l)   (C0[k,l] = N - max(k,l))
 };

@@ -67,8 +67,8 @@ __device__ __forceinline__ void step_sum_store(double v[6], double* dst, int j) 
 // -------------------------------------------------------------------------------------------------
 // decode: contact flag, foothold, lever arm block for (step k, foot j)      [MPC.py:316-360, 635-652]
 // -------------------------------------------------------------------------------------------------
-template <int N>
-__device__ __forceinline__ void decode_foot(const DevParams& P, const double* xr, const double* fs, int k, int j,
+// N is the horizon (xref is 12 x (N + 1)); the dense kernels pass their compile-time horizon
+__device__ __forceinline__ void decode_foot(const DevParams& P, const double* xr, const double* fs, const int N, int k, int j,
                                             bool first_tick, double A[9], bool& contact, bool& bad) {
     int row = -1;
     double cum = 0.0;
@@ -119,8 +119,8 @@ __device__ __forceinline__ void decode_foot(const DevParams& P, const double* xr
 // The same decode split in two, for the stage-wise path (it keeps the lever arm and the per-step inertia
 // block instead of the 3x3 product, and forms  A = dt inv(R gI) [r]x  on demand with decode_foot's arithmetic):
 //   contact flag + lever arm r = foothold - xref[0:3, k] of (step k, foot j)            [MPC.py:327, 343, 635-652]
-template <int N>
-__device__ __forceinline__ void decode_lever(const DevParams& P, const double* xr, const double* fs, int k, int j, bool first_tick,
+// `n` is the run-time horizon: xref is 12 x (n + 1).
+__device__ __forceinline__ void decode_lever(const DevParams& P, const double* xr, const double* fs, int n, int k, int j, bool first_tick,
                                              double r[3], bool& contact, bool& bad) {
     int row = -1;
     double cum = 0.0;
@@ -147,7 +147,7 @@ __device__ __forceinline__ void decode_lever(const DevParams& P, const double* x
         for (int c = 0; c < 3; ++c) foot[c] = P.footholds[c * 4 + j];
     }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) r[c] = foot[c] - xr[c * (N + 1) + k];
+    for (int c = 0; c < 3; ++c) r[c] = foot[c] - xr[c * (n + 1) + k];
 }
 //   inv(R_z(yaw) gI) = gI^-1 R'                                                          [MPC.py:330, 339-340]
 __device__ __forceinline__ void step_inertia(const DevParams& P, double yaw, double Ii[9]) {

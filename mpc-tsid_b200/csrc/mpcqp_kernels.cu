@@ -396,7 +396,7 @@ solve_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict_
         PROF_T0();
         if (SC.enabled) {
             // ---- device-resident closed loop: the planner runs here, inputs never touch HBM
-            scenario_inputs<N>(P, SC, sm.sc, inst, sm.xr, sm.fs);
+            scenario_inputs<0>(P, SC, sm.sc, inst, sm.xr, sm.fs, N);
         } else {
             // ---- stage inputs in shared memory: two bulk async copies (16-byte aligned blocks per instance)
             if (tid == 0) {
@@ -411,7 +411,7 @@ solve_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict_
         bool bad = false, contact = false;
         uint8_t sig = SIG_FREE;
         double A0[9];
-        if (foot_thread) decode_foot<N>(P, sm.xr, sm.fs, k, j, first_tick != 0, A0, contact, bad);
+        if (foot_thread) decode_foot(P, sm.xr, sm.fs, N, k, j, first_tick != 0, A0, contact, bad);
         for (int i = tid; i < 12 * (N + 1); i += blockDim.x) bad = bad || !isfinite(sm.xr[i]);
         free_response<N>(P, sm.xr, sm.gam);
         const int any_bad = __syncthreads_or(bad ? 1 : 0);       // also: every thread is done reading fs
@@ -591,20 +591,20 @@ solve_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict_
 // Build-half parity hook: the coefficients MPC.update_ML / update_NK write each tick, in the
 // reference's own order (MPC.py:154-166, 349, 355-358, 362-378).
 // -------------------------------------------------------------------------------------------------
-template <int N>
 __global__ void export_build_kernel(DevParams P, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g,
                                     int first_tick, double* __restrict__ Bv, double* __restrict__ Sv, double* __restrict__ NK) {
-    __shared__ double xr[12 * (N + 1)];
+    __shared__ double xr[12 * 65];
     __shared__ double fs[260];
+    const int N = P.N;                                   // any horizon up to 64
     const int inst = blockIdx.x, tid = threadIdx.x;
     for (int i = tid; i < 12 * (N + 1); i += blockDim.x) xr[i] = xref_g[(size_t)inst * 12 * (N + 1) + i];
     for (int i = tid; i < 260; i += blockDim.x) fs[i] = fsteps_g[(size_t)inst * 260 + i];
     __syncthreads();
-    if (tid < 4 * N) {
-        const int k = tid >> 2, j = tid & 3;
+    for (int t = tid; t < 4 * N; t += blockDim.x) {
+        const int k = t >> 2, j = t & 3;
         double A[9];
         bool bad = false, contact = false;
-        decode_foot<N>(P, xr, fs, k, j, first_tick != 0, A, contact, bad);
+        decode_foot(P, xr, fs, N, k, j, first_tick != 0, A, contact, bad);
         double* b = Bv + (size_t)inst * 48 * N + 48 * k + 12 * j;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {

@@ -2,7 +2,7 @@
 #pragma once
 namespace mpcqp {
 constexpr int RIC_GAIN = 84;        // workspace doubles per stage: 6 impulse components x 14 (13 coefficients + pad)
-constexpr int RIC_ADM = 13;         // workspace doubles of ADMM state per foot-step (struct of arrays): f (3), z (5), y (5)
+constexpr int RIC_ADM = 18;         // workspace doubles of interior-point state per foot-step (struct of arrays): f (3), y (6), step df (3), dy (6)
 #ifndef MPCQP_RIC_WARPS
 #define MPCQP_RIC_WARPS 1
 #endif

@@ -32,6 +32,18 @@
 // reciprocal and one fused multiply-add; the inverse rows are formed in the shadow of the pivots), so every product above is "one row in registers
 // times a register-resident triangular matrix" and a stage needs three warp barriers.
 // Replaces MPC.update_ML / update_NK / call_solver / retrieve_result (MPC.py:316-458) like the dense path.
+//
+// Horizons: the kernels are compiled for three CAPACITIES NC = 16, 32, 64 (array sizes, lanes per robot, feet per lane); the
+// horizon itself, n = P.N <= NC, is a run-time value (any n_steps = n_periods T_gait / dt of the reference, main.py:20-23,
+// FootstepPlanner.py:52-63): xref is 12 x (n + 1), foot-steps t >= 4 n do not exist, the recursion runs over n stages.
+//
+// Robots the warm-started sweeps do not certify (cycling signatures: cold starts of long horizons, nearly degenerate faces)
+// go to a second kernel, ipm_kernel, that runs a primal-dual INTERIOR-POINT iteration on the same stage-wise factorisation:
+// per foot the barrier adds  C' diag(y / s) C  (a full symmetric 3 x 3) to the force weight, whose inverse S is exactly the
+// 3 x 3 the stage assembly consumes, so one iteration = one ric_assemble + ric_core + per-foot step rules.  About twenty
+// iterations bring the complementarity gap to 1e-8 whatever the active set looks like; the rows with y > s then seed the sweeps,
+// which certify the optimum exactly as on the fast path (same KKT guard).  This is the globally convergent stage of the
+// stage-wise path, the role OSQP's ADMM iteration has in the reference (MPC.py:414-428).
 #pragma once
 #include "mpcqp_device.cuh"
 #include "mpcqp_foot.cuh"
@@ -60,7 +72,7 @@ struct alignas(16) RicCost {
     double Ppp[36], Ppv[36], Pvv[36], pp[6], pv[6];
 };
 
-template <int N>
+template <int N>                        // N = capacity (16, 32, 64); the run-time horizon n <= N
 struct alignas(16) RicInst {
     static constexpr int NF = 4 * N;
     static constexpr int ROUNDS = NF / 16;                     // feet per lane
@@ -212,12 +224,13 @@ __device__ __forceinline__ void foot_A(const DevParams& P, const RicInst<N>& sm,
 // Returns (uniform over the half-warp) false if a pivot was not positive.  On return sm.xst holds the states
 // x_1..x_N and sm.lam the velocity costates lam^v_1..lam^v_N; sm.E is dead.
 template <int N>
-__device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl) {
+__device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl, const int n) {
     const double dt = P.dt;
+    const int ld = n + 1;                                        // leading dimension of xref
     RPROF_T0();
     // ---- terminal cost-to-go: P_N = Q, p_N = -Q xref_N
     {
-        RicCost& c0 = sm.cost[(N - 1) & 1];
+        RicCost& c0 = sm.cost[(n - 1) & 1];
         for (int i = hl; i < 36; i += 16) {
             const int rr = i / 6, dg = (i - 6 * rr) == rr;
             c0.Ppp[i] = dg ? P.wp[rr] : 0.0;
@@ -225,8 +238,8 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
             c0.Ppv[i] = 0.0;
         }
         if (hl < 6) {
-            c0.pp[hl] = -P.wp[hl] * sm.xr[hl * (N + 1) + N];
-            c0.pv[hl] = -P.wv[hl] * sm.xr[(6 + hl) * (N + 1) + N];
+            c0.pp[hl] = -P.wp[hl] * sm.xr[hl * ld + n];
+            c0.pv[hl] = -P.wv[hl] * sm.xr[(6 + hl) * ld + n];
         }
     }
     __syncwarp();
@@ -242,7 +255,7 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
     for (int q = 0; q < 6; ++q) ie[q] = (ri >= q) ? ri * (ri + 1) / 2 + q : q * (q + 1) / 2 + ri;
 
     bool spd = true;
-    for (int k = N - 1; k >= 0; --k) {
+    for (int k = n - 1; k >= 0; --k) {
         const RicCost& cin = sm.cost[k & 1];
         RicCost& cout = sm.cost[(k & 1) ^ 1];
         const double* Ek = sm.E + 21 * k;
@@ -348,7 +361,7 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
                 store_row6(cout.Ppp + 6 * ri, npp);
                 store_row6(cout.Ppv + 6 * ri, npv);
                 sm.hp[ri] = hb;
-                cout.pp[ri] = hb - P.wp[ri] * sm.xr[ri * (N + 1) + k];
+                cout.pp[ri] = hb - P.wp[ri] * sm.xr[ri * ld + k];
             }
             __syncwarp();
             if (vrow) {
@@ -357,7 +370,7 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
 #pragma unroll
                 for (int c = 0; c < 6; ++c) nvv[c] = fma(dt, npv[c] + wr[c], tr[c]) + ((c == ri) ? P.wv[ri] : 0.0);
                 store_row6(cout.Pvv + 6 * ri, nvv);
-                cout.pv[ri] = fma(dt, sm.hp[ri], hb) - P.wv[ri] * sm.xr[(6 + ri) * (N + 1) + k];
+                cout.pv[ri] = fma(dt, sm.hp[ri], hb) - P.wv[ri] * sm.xr[(6 + ri) * ld + k];
             }
             __syncwarp();
             RPROF(8);
@@ -372,7 +385,7 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
     {
         double x[12];
 #pragma unroll
-        for (int c = 0; c < 12; ++c) x[c] = sm.xr[c * (N + 1)];
+        for (int c = 0; c < 12; ++c) x[c] = sm.xr[c * ld];
         const int o = hl % 6;
         const double* gcol = ws + 14 * o;
         double2 g[RIC_DEPTH][7];
@@ -380,10 +393,11 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
         for (int d = 0; d < RIC_DEPTH; ++d)
 #pragma unroll
             for (int i = 0; i < 7; ++i) g[d][i] = __ldcg(reinterpret_cast<const double2*>(gcol + (size_t)RIC_GAIN * d) + i);
-        for (int k0 = 0; k0 < N; k0 += RIC_DEPTH) {
+        for (int k0 = 0; k0 < n; k0 += RIC_DEPTH) {
 #pragma unroll
             for (int d = 0; d < RIC_DEPTH; ++d) {
                 const int k = k0 + d;
+                if (k >= n) break;                               // uniform over the warp (n is)
                 double bk[6], z[12];
                 load_row6(bk, sm.beta + 6 * k);
 #pragma unroll
@@ -395,7 +409,7 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
                     a2 = fma(g[d][i + 1].x, z[2 * i + 2], a2); a3 = fma(g[d][i + 1].y, z[2 * i + 3], a3);
                 }
                 const double w = (a0 + a1) + (a2 + a3);          // minus the impulse correction of component o
-                if (k + RIC_DEPTH < N) {
+                if (k + RIC_DEPTH < n) {
 #pragma unroll
                     for (int i = 0; i < 7; ++i) g[d][i] = __ldcg(reinterpret_cast<const double2*>(gcol + (size_t)RIC_GAIN * (k + RIC_DEPTH)) + i);
                 }
@@ -417,9 +431,9 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
         const double wpc = P.wp[c], wvc = P.wv[c];
         double lp = 0.0, lv = 0.0;
 #pragma unroll 8
-        for (int s = N; s >= 1; --s) {
+        for (int s = n; s >= 1; --s) {
             const double* xs = sm.xst + 12 * (s - 1);
-            const double ep = xs[c] - sm.xr[c * (N + 1) + s], ev = xs[6 + c] - sm.xr[(6 + c) * (N + 1) + s];
+            const double ep = xs[c] - sm.xr[c * ld + s], ev = xs[6 + c] - sm.xr[(6 + c) * ld + s];
             lv = fma(wvc, ev, fma(dt, lp, lv));
             lp = fma(wpc, ep, lp);
             sm.lam[6 * (s - 1) + c] = lv;
@@ -430,15 +444,16 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
     return spd_all;
 }
 
-// E_k = sum_j (Bv Z) R^-1 (Bv Z)' (packed lower triangle) and beta_k = g + sum_j Bv pf for every step.  One lane per step
-// (lane hl owns steps hl, hl + 16, ...), the four feet of a step in sequence, no shuffles: with S = Z R^-1 Z' (3x3, a
-// closed form of the face) and Bv = [lin I; A],  E = [[lin^2 S, lin (A S)'], [lin A S, A S A']].
-// face_of(t, fc) describes foot-step t; it must not depend on which lane asks.
-template <int N, class FaceFn>
-__device__ __forceinline__ void ric_assemble(const DevParams& P, RicInst<N>& sm, int hl, FaceFn face_of) {
+// E_k = sum_j Bv S Bv' (packed lower triangle) and beta_k = g + sum_j Bv pf for every step, where foot-step t contributes the
+// symmetric 3 x 3 S_t (inverse of its force weight on the directions it may move in: Z R^-1 Z' of a face, the full inverse of
+// w_f I + C' D C of an interior-point iterate) and the offset pf_t.  One lane per step (lane hl owns steps hl, hl + 16, ...),
+// the four feet of a step in sequence, no shuffles: with Bv = [lin I; A],  E = [[lin^2 S, lin (A S)'], [lin A S, A S A']].
+// foot_of(t, S, pf) describes foot-step t (S as S00, S10, S11, S20, S21, S22); it must not depend on which lane asks.
+template <int N, class FootFn>
+__device__ __forceinline__ void ric_assemble(const DevParams& P, RicInst<N>& sm, int hl, const int n, FootFn foot_of) {
     const double lin = P.dt / P.mass, lin2 = lin * lin;
 #pragma unroll 1
-    for (int k = hl; k < N; k += 16) {
+    for (int k = hl; k < n; k += 16) {
         double e[21], ub[6];
 #pragma unroll
         for (int i = 0; i < 21; ++i) e[i] = 0.0;
@@ -448,12 +463,10 @@ __device__ __forceinline__ void ric_assemble(const DevParams& P, RicInst<N>& sm,
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             const int t = 4 * k + j;
-            Face fc;
-            face_of(t, fc);
+            double S[6], pf[3];
+            foot_of(t, S, pf);
             double A[9];
             foot_A<N>(P, sm, t, A);
-            const double S[6] = {fc.dx + fc.dz * fc.czx * fc.czx, fc.dz * fc.czx * fc.czy, fc.dy + fc.dz * fc.czy * fc.czy,
-                                 fc.dz * fc.czx, fc.dz * fc.czy, fc.dz};      // S00, S10, S11, S20, S21, S22
             double M[9];                                       // M = A S
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
@@ -476,7 +489,7 @@ __device__ __forceinline__ void ric_assemble(const DevParams& P, RicInst<N>& sm,
                     e[RIC_TI(3 + q, 3 + c)] += M[3 * q] * A[3 * c] + M[3 * q + 1] * A[3 * c + 1] + M[3 * q + 2] * A[3 * c + 2];
             }
             double u6[6];
-            bv_apply(A, lin, fc.pf, u6);
+            bv_apply(A, lin, pf, u6);
 #pragma unroll
             for (int i = 0; i < 6; ++i) ub[i] += u6[i];
         }
@@ -485,16 +498,26 @@ __device__ __forceinline__ void ric_assemble(const DevParams& P, RicInst<N>& sm,
         store_row6(sm.beta + 6 * k, ub);
     }
 }
+// S = Z R^-1 Z' of a face (closed form)
+__device__ __forceinline__ void face_S(const Face& fc, double (&S)[6]) {
+    S[0] = fc.dx + fc.dz * fc.czx * fc.czx; S[1] = fc.dz * fc.czx * fc.czy; S[2] = fc.dy + fc.dz * fc.czy * fc.czy;
+    S[3] = fc.dz * fc.czx; S[4] = fc.dz * fc.czy; S[5] = fc.dz;
+}
+
+constexpr uint8_t SIG_PIN = 27;    // not a face: the foot-step's force is held at a given value (roll-out of a feasible iterate)
 
 // One equality-constrained solve on the faces `sg` selects + KKT guard.  The 16 lanes of the robot call it.
 // Returns (uniform over the half-warp) 1 if every foot passes the guard, 0 if not, -1 if a pivot was not positive.
 // Both halves of the warp must call it together (full-mask collectives inside).
 // On return sm.E holds the forces (3 per foot, foot-major), sm.xst the states, sm.lam the velocity costates.
+// A foot-step whose signature is SIG_PIN is held at the force pin[c * NF + t] (c = 0..2) and skips the guard: with every
+// stance foot pinned the sweep is the forward roll-out of those forces (E_k = 0), which is how an iterate that was not
+// certified still leaves with states that belong to its forces.
 template <int N>
-__device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl, unsigned conbits,
-                         const uint8_t (&sg)[RicInst<N>::ROUNDS], uint8_t (&nsg)[RicInst<N>::ROUNDS]) {
+__device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl, const int n, unsigned conbits,
+                         const uint8_t (&sg)[RicInst<N>::ROUNDS], uint8_t (&nsg)[RicInst<N>::ROUNDS], const double* __restrict__ pin = nullptr) {
     using S = RicInst<N>;
-    constexpr int ROUNDS = S::ROUNDS;
+    constexpr int ROUNDS = S::ROUNDS, NF = S::NF;
     const double lin = P.dt / P.mass;
     RPROF_T0();
     RPROF_COUNT(0);
@@ -502,10 +525,18 @@ __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict_
 #pragma unroll 1
     for (int r = 0; r < ROUNDS; ++r) sm.sigb[hl + 16 * r] = (uint8_t)(sg[r] | (((conbits >> r) & 1u) << 7));
     __syncwarp();
-    ric_assemble<N>(P, sm, hl, [&](int t, Face& fc) { const uint8_t sb = sm.sigb[t]; make_face(P, (sb >> 7) != 0, sb & 127, fc); });
+    ric_assemble<N>(P, sm, hl, n, [&](int t, double (&S6)[6], double (&pf)[3]) {
+        const uint8_t sb = sm.sigb[t];
+        Face fc;
+        const bool pinned = (sb & 127) == SIG_PIN;
+        make_face(P, (sb >> 7) != 0 && !pinned, sb & 127, fc);
+        face_S(fc, S6);
+        pf[0] = fc.pf[0]; pf[1] = fc.pf[1]; pf[2] = fc.pf[2];
+        if (pinned && (sb >> 7) && pin != nullptr) { pf[0] = pin[t]; pf[1] = pin[NF + t]; pf[2] = pin[2 * NF + t]; }
+    });
     __syncwarp();
     RPROF(1);
-    const bool spd_all = ric_core<N>(P, sm, ws, sub, hl);
+    const bool spd_all = ric_core<N>(P, sm, ws, sub, hl, n);
     // ---- per foot: forces on the face, gradient, KKT guard
     bool ok = true;
 #pragma unroll 1
@@ -514,7 +545,9 @@ __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict_
         const bool contact = (conbits >> r) & 1u;
         double f[3] = {0.0, 0.0, 0.0};
         nsg[r] = sg[r];
-        if (contact) {
+        if (contact && sg[r] == SIG_PIN) {
+            if (pin != nullptr) { f[0] = pin[t]; f[1] = pin[NF + t]; f[2] = pin[2 * NF + t]; }
+        } else if (contact) {
             Face fc;
             make_face(P, true, sg[r], fc);
             double A[9], h[3];
@@ -537,103 +570,279 @@ __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict_
     return !spd_all ? -1 : (all_ok ? 1 : 0);
 }
 
-
-// One iteration of the ADMM stage in stage-wise form (same splitting as the dense ADMM stage in mpcqp_kernels.cu: OSQP's
-// iteration on the condensed QP  l <= C f <= u  with fixed rho, sigma, alpha).  The x-update
-//     (H + sigma I + rho C'C) ft = sigma f - g + C'(rho z - y),      C'C = diag(2, 2, 4 mu^2 + 1) per foot,
-// is the same LQ problem as a sweep with every stance force free, R = w_f + sigma + rho C'C on the diagonal and the
-// offset pf = R^-1 (sigma f + C'(rho z - y)):  ft = pf - R^-1 Bv' lam.  Then OSQP's relaxed z / y updates per foot.
-// `cur` receives the active set the iterate suggests (OSQP's polish rule).  Returns false if a pivot failed.
+// The active-set iteration: up to max_s sweeps from the signatures `sg`, every failed sweep followed by the primal-dual
+// update (every foot adopts the guard's proposal).  A proposal that was tried before would cycle; then, if `careful`, one
+// foot changes per sweep in index order (the stage's own safeguard), otherwise the iteration stops (the interior-point
+// stage takes over).  `want` says whether this half-warp takes part; both halves call it together.
+// done / status / sweeps are updated for the halves that take part; on return with done the results of the accepted
+// sweep sit in shared memory ONLY IF the other half did not go on sweeping -- callers that need them re-run one sweep.
 template <int N>
-__device__ bool ric_admm_iter(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, double* __restrict__ adm, int sub, int hl,
-                              unsigned conbits, uint8_t (&cur)[RicInst<N>::ROUNDS]) {
-    constexpr int NF = RicInst<N>::NF, ROUNDS = RicInst<N>::ROUNDS;
-    const double rho = P.rho, sigma = P.sigma, alpha = P.alpha, mu = P.mu, lin = P.dt / P.mass;
-    const double ddx = 1.0 / (P.w_force + sigma + 2.0 * rho), ddz = 1.0 / (P.w_force + sigma + rho * (4.0 * mu * mu + 1.0));
-    auto offset = [&](int t, double (&pf)[3]) {
-        double f[3], z[5], y[5];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) f[c] = adm[c * NF + t];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) { z[q] = adm[(3 + q) * NF + t]; y[q] = adm[(8 + q) * NF + t]; }
-        const double v0 = rho * z[0] - y[0], v1 = rho * z[1] - y[1], v2 = rho * z[2] - y[2], v3 = rho * z[3] - y[3], v4 = rho * z[4] - y[4];
-        pf[0] = ddx * (sigma * f[0] + (v0 - v1));
-        pf[1] = ddx * (sigma * f[1] + (v2 - v3));
-        pf[2] = ddz * (sigma * f[2] - mu * (v0 + v1 + v2 + v3) - v4);
-    };
+__device__ __forceinline__ void ric_active_set(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl, const int n,
+                                               unsigned conbits, uint8_t (&sg)[RicInst<N>::ROUNDS], uint8_t (&nsg)[RicInst<N>::ROUNDS],
+                                               bool want, int max_s, bool allow_careful, int& sweeps, bool& done, int& status) {
+    constexpr int ROUNDS = RicInst<N>::ROUNDS;
+    // order-sensitive hash of a signature, uniform over the half-warp (cycle detection)
+    auto sig_hash = [&](const uint8_t (&g)[ROUNDS]) {
+        unsigned long long h = 0ull;
 #pragma unroll 1
-    for (int r = 0; r < ROUNDS; ++r) sm.sigb[hl + 16 * r] = (uint8_t)(((conbits >> r) & 1u) << 7);
-    __syncwarp();
-    ric_assemble<N>(P, sm, hl, [&](int t, Face& fc) {
-        const bool live = (sm.sigb[t] >> 7) != 0;
-        fc.zx = fc.zy = fc.zz = live;
-        fc.czx = 0.0; fc.czy = 0.0;
-        fc.dx = live ? ddx : 0.0; fc.dy = fc.dx; fc.dz = live ? ddz : 0.0;
-        fc.pf[0] = fc.pf[1] = fc.pf[2] = 0.0;
-        if (live) offset(t, fc.pf);
-    });
-    __syncwarp();
-    const bool spd_all = ric_core<N>(P, sm, ws, sub, hl);
-#pragma unroll 1
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int t = hl + 16 * r, k = t >> 2;
-        cur[r] = SIG_FREE;
-        if ((conbits >> r) & 1u) {
-            double A[9], h[3], pf[3], f[3], z[5], y[5];
-            foot_A<N>(P, sm, t, A);
-            bvT_apply(A, lin, sm.lam + 6 * k, h);
-            offset(t, pf);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) f[c] = adm[c * NF + t];
-#pragma unroll
-            for (int q = 0; q < 5; ++q) { z[q] = adm[(3 + q) * NF + t]; y[q] = adm[(8 + q) * NF + t]; }
-            const double ftx = pf[0] - ddx * h[0], fty = pf[1] - ddx * h[1], ftz = pf[2] - ddz * h[2];
-            const double zt[5] = {ftx - mu * ftz, -ftx - mu * ftz, fty - mu * ftz, -fty - mu * ftz, -ftz};
-            f[0] = alpha * ftx + (1.0 - alpha) * f[0];
-            f[1] = alpha * fty + (1.0 - alpha) * f[1];
-            f[2] = alpha * ftz + (1.0 - alpha) * f[2];
-            bool upp[5], low4 = false;
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                const double zr = alpha * zt[q] + (1.0 - alpha) * z[q];
-                double zn = fmin(zr + y[q] / rho, 0.0);
-                if (q == 4) zn = fmax(zn, -P.fz_max);
-                y[q] += rho * (zr - zn);
-                z[q] = zn;
-                upp[q] = (0.0 - zn) < y[q];                    // OSQP's polish rule
-                if (q == 4) low4 = (zn + P.fz_max) < -y[q];
+        for (int r = 0; r < ROUNDS; ++r) {
+            if ((conbits >> r) & 1u) {
+                unsigned long long q = (unsigned long long)(g[r] + 1) * 0x9E3779B97F4A7C15ull;
+                q ^= q >> 29; q *= (2ull * (hl + 16 * r) + 0xBF58476D1CE4E5B9ull); q ^= q >> 32;
+                h += q;
             }
-            const int sx = (upp[0] ? 1 : 0) - (upp[1] ? 1 : 0), sy = (upp[2] ? 1 : 0) - (upp[3] ? 1 : 0);
-            const bool apex = upp[4] || (upp[0] && upp[1]) || (upp[2] && upp[3]);
-            cur[r] = sig_pack(sx, sy, apex ? 1 : (low4 ? 2 : 0));
+        }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) adm[c * NF + t] = f[c];
+        for (int o = 8; o > 0; o >>= 1) h += __shfl_xor_sync(RIC_FULL, h, o, 16);
+        return h;
+    };
+    int nhist = 0;
+    bool careful = false;       // set once the full primal-dual update proposed a signature that was tried before
+    bool stop = !want;
+    for (int s = 0; s < max_s; ++s) {
+        const bool need = !done && !stop;
+        if (!__any_sync(RIC_FULL, need)) break;
+        const int rc = ric_sweep<N>(P, sm, ws, sub, hl, n, conbits, sg, nsg);
+        bool search = false;
+        if (need) {
+            ++sweeps;
+            if (rc < 0) stop = true;
+            else if (rc > 0) { done = true; status = 1; }
+            else search = true;
+        }
+        if (!__any_sync(RIC_FULL, search)) continue;      // the common case: nothing to hash, nothing to choose
+        // ---- next signature.  The one just tried goes into the history; first choice: every foot adopts its proposal
+        // (primal-dual active-set step).
+        const unsigned long long h = sig_hash(sg);
+        __syncwarp();
+        if (search && hl == 0 && nhist < 16) sm.hist[nhist] = h;
+        if (search) nhist = (nhist < 16) ? nhist + 1 : nhist;
+        __syncwarp();
+        auto seen = [&](unsigned long long q) {
+            bool f = false;
+            for (int i = 0; i < nhist; ++i) f = f || (sm.hist[i] == q);
+            return f;
+        };
+        const unsigned long long hfull = sig_hash(nsg);
+        if (search && !careful) {
+            if (seen(hfull)) {
+                careful = true;
+                if (!allow_careful) { stop = true; search = false; }
+            } else {
+#pragma unroll 1
+                for (int r = 0; r < ROUNDS; ++r) sg[r] = nsg[r];
+                search = false;
+            }
+        }
+        int tlast = -1;
+        while (__any_sync(RIC_FULL, search)) {
+            int tm = 0x7fffffff;
+#pragma unroll 1
+            for (int r = 0; r < ROUNDS; ++r) {
+                const int t = hl + 16 * r;
+                if (nsg[r] != sg[r] && t > tlast && t < tm) tm = t;
+            }
 #pragma unroll
-            for (int q = 0; q < 5; ++q) { adm[(3 + q) * NF + t] = z[q]; adm[(8 + q) * NF + t] = y[q]; }
+            for (int o = 8; o > 0; o >>= 1) { const int q = __shfl_xor_sync(RIC_FULL, tm, o, 16); tm = q < tm ? q : tm; }
+            uint8_t cand[ROUNDS];
+#pragma unroll 1
+            for (int r = 0; r < ROUNDS; ++r) cand[r] = (hl + 16 * r == tm) ? nsg[r] : sg[r];
+            const unsigned long long hc = sig_hash(cand);
+            if (search) {
+                if (tm == 0x7fffffff) { stop = true; search = false; }            // every single change was tried before
+                else if (!seen(hc)) {
+#pragma unroll 1
+                    for (int r = 0; r < ROUNDS; ++r) sg[r] = cand[r];
+                    search = false;
+                } else tlast = tm;
+            }
         }
     }
-    __syncwarp();
-    return spd_all;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Interior-point stage.  Per stance foot-step the six rows  C6 f <= h6  (the five pyramid rows of MPC.py:136-148 with the
+// two-sided fz row split in two):  fx - mu fz, -fx - mu fz, fy - mu fz, -fy - mu fz, -fz <= 0,  fz <= fz_max.
+// State per foot-step in the workspace (struct of arrays, stride NF): f (3), y (6); scratch: target fp (3), dy (6).
+// One iteration, written for the NEW iterate instead of the step (so that the linear terms of the tracking problem stay
+// where ric_core expects them):  with s = h6 - C6 f, D = y / s,
+//     (H + C6' D C6) f+ = -g - C6' (y - D h6 + sigma mu / s)
+// is the stage-wise LQ problem with per-foot force weight R = w_f I + C6' D C6 and linear term c = C6' (...):  S = R^-1,
+// pf = -S c, f+ = pf - S Bv' lam.  Then ds = -C6 (f+ - f), dy = sigma mu / s - y - D ds, separate primal and dual step
+// lengths to the boundary (0.995), sigma chosen from the length of the previous step.
+// ---------------------------------------------------------------------------------------------------------------------
+struct IpmFoot {
+    double S[6], c[3], s[6], D[6];
+};
+__device__ __forceinline__ void ipm_foot(const DevParams& P, const double (&f)[3], const double (&y)[6], double sigmu, IpmFoot& o) {
+    const double mu = P.mu, w = P.w_force;
+    o.s[0] = mu * f[2] - f[0]; o.s[1] = mu * f[2] + f[0]; o.s[2] = mu * f[2] - f[1]; o.s[3] = mu * f[2] + f[1];
+    o.s[4] = f[2]; o.s[5] = P.fz_max - f[2];
+    double v[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double is = 1.0 / o.s[i];
+        o.D[i] = y[i] * is;
+        v[i] = fma(sigmu, is, y[i]);
+    }
+    v[5] -= o.D[5] * P.fz_max;
+    const double a = w + o.D[0] + o.D[1], b = w + o.D[2] + o.D[3];
+    const double p = mu * (o.D[1] - o.D[0]), q = mu * (o.D[3] - o.D[2]);
+    const double ia = 1.0 / a, ib = 1.0 / b;
+    // Schur complement of the fz row, cancellation free:  mu^2 [(D0 + D1) - (D1 - D0)^2 / a] = mu^2 [w (D0 + D1) + 4 D0 D1] / a
+    const double cz = w + o.D[4] + o.D[5] + mu * mu * ((w * (o.D[0] + o.D[1]) + 4.0 * o.D[0] * o.D[1]) * ia +
+                                                        (w * (o.D[2] + o.D[3]) + 4.0 * o.D[2] * o.D[3]) * ib);
+    const double iz = 1.0 / cz, pa = p * ia, qb = q * ib;
+    o.S[5] = iz; o.S[3] = -pa * iz; o.S[4] = -qb * iz;
+    o.S[0] = fma(pa * pa, iz, ia); o.S[2] = fma(qb * qb, iz, ib); o.S[1] = pa * qb * iz;
+    o.c[0] = v[0] - v[1]; o.c[1] = v[2] - v[3]; o.c[2] = -mu * ((v[0] + v[1]) + (v[2] + v[3])) - v[4] + v[5];
+}
+__device__ __forceinline__ void sym3_apply(const double (&S)[6], const double (&x)[3], double (&o)[3]) {
+    o[0] = S[0] * x[0] + S[1] * x[1] + S[3] * x[2];
+    o[1] = S[1] * x[0] + S[2] * x[1] + S[4] * x[2];
+    o[2] = S[3] * x[0] + S[4] * x[1] + S[5] * x[2];
+}
+
+// Interior-point iterations of one robot until the complementarity gap mu_gap = y's / rows falls below `target` or `budget`
+// iterations are spent.  `gap` / `sigma` carry over between calls.  Returns false on a numerical breakdown.
+template <int N>
+__device__ bool ric_ipm(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, double* __restrict__ adm, int sub, int hl, const int n,
+                        unsigned conbits, bool want, double target, int budget, double& gap, double& sigma, int& iters) {
+    constexpr int NF = RicInst<N>::NF, ROUNDS = RicInst<N>::ROUNDS;
+    const double lin = P.dt / P.mass, tau = 0.995;
+    int rows = 0;
+#pragma unroll 1
+    for (int r = 0; r < ROUNDS; ++r) rows += ((conbits >> r) & 1u) ? 6 : 0;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) rows += __shfl_xor_sync(RIC_FULL, rows, o, 16);
+    const double inv_rows = rows > 0 ? 1.0 / (double)rows : 0.0;
+    bool ok = true;
+    bool live = want && rows > 0;
+    for (int it = 0; it < budget; ++it) {
+        const bool need = live && ok && gap > target;
+        if (!__any_sync(RIC_FULL, need)) break;
+        const double sigmu = sigma * gap;
+#pragma unroll 1
+        for (int r = 0; r < ROUNDS; ++r) sm.sigb[hl + 16 * r] = (uint8_t)(((conbits >> r) & 1u) << 7);
+        __syncwarp();
+        ric_assemble<N>(P, sm, hl, n, [&](int t, double (&S6)[6], double (&pf)[3]) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) S6[i] = 0.0;
+            pf[0] = pf[1] = pf[2] = 0.0;
+            if (sm.sigb[t] >> 7) {
+                double f[3], y[6];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) f[c] = adm[c * NF + t];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) y[q] = adm[(3 + q) * NF + t];
+                IpmFoot ft;
+                ipm_foot(P, f, y, sigmu, ft);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) S6[i] = ft.S[i];
+                double sc[3];
+                sym3_apply(ft.S, ft.c, sc);
+                pf[0] = -sc[0]; pf[1] = -sc[1]; pf[2] = -sc[2];
+            }
+        });
+        __syncwarp();
+        const bool spd = ric_core<N>(P, sm, ws, sub, hl, n);
+        // ---- per foot: target, steps, lengths to the boundary
+        double ap = 1.0, ad = 1.0;
+#pragma unroll 1
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int t = hl + 16 * r, k = t >> 2;
+            if ((conbits >> r) & 1u) {
+                double f[3], y[6], A[9], h[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) f[c] = adm[c * NF + t];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) y[q] = adm[(3 + q) * NF + t];
+                IpmFoot ft;
+                ipm_foot(P, f, y, sigmu, ft);
+                foot_A<N>(P, sm, t, A);
+                bvT_apply(A, lin, sm.lam + 6 * k, h);
+                const double ch[3] = {ft.c[0] + h[0], ft.c[1] + h[1], ft.c[2] + h[2]};
+                double fp[3];
+                sym3_apply(ft.S, ch, fp);
+                const double df[3] = {-fp[0] - f[0], -fp[1] - f[1], -fp[2] - f[2]};
+                const double mz = P.mu * df[2];
+                const double ds[6] = {mz - df[0], mz + df[0], mz - df[1], mz + df[1], df[2], -df[2]};
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const double dy = sigmu / ft.s[q] - y[q] - ft.D[q] * ds[q];
+                    if (ds[q] < 0.0) ap = fmin(ap, -tau * ft.s[q] / ds[q]);
+                    if (dy < 0.0) ad = fmin(ad, -tau * y[q] / dy);
+                    adm[(12 + q) * NF + t] = dy;
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) adm[(9 + c) * NF + t] = df[c];
+            }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            ap = fmin(ap, __shfl_xor_sync(RIC_FULL, ap, o, 16));
+            ad = fmin(ad, __shfl_xor_sync(RIC_FULL, ad, o, 16));
+        }
+        // ---- apply, new gap
+        double part = 0.0;
+        const bool sane = spd && (ap > 0.0) && (ad > 0.0) && isfinite(ap) && isfinite(ad);
+#pragma unroll 1
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int t = hl + 16 * r;
+            if ((conbits >> r) & 1u) {
+                double f[3], y[6];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) f[c] = adm[c * NF + t];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) y[q] = adm[(3 + q) * NF + t];
+                if (need && sane) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { f[c] = fma(ap, adm[(9 + c) * NF + t], f[c]); adm[c * NF + t] = f[c]; }
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) { y[q] = fma(ad, adm[(12 + q) * NF + t], y[q]); adm[(3 + q) * NF + t] = y[q]; }
+                }
+                const double mz = P.mu * f[2];
+                const double s6[6] = {mz - f[0], mz + f[0], mz - f[1], mz + f[1], f[2], P.fz_max - f[2]};
+#pragma unroll
+                for (int q = 0; q < 6; ++q) part = fma(y[q], s6[q], part);
+            }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(RIC_FULL, part, o, 16);
+        if (need) {
+            ++iters;
+            if (!sane) ok = false;
+            else {
+                gap = part * inv_rows;
+                const double a = fmin(ap, ad);
+                sigma = a > 0.9 ? 0.05 : (a > 0.6 ? 0.15 : (a > 0.3 ? 0.3 : 0.5));
+            }
+        }
+        __syncwarp();
+    }
+    return ok;
 }
 
 // Outputs of one robot (the half-warp version of finish() in mpcqp_kernels.cu)                 [MPC.py:432-458]
-// The states are those of the accepted sweep's forward pass (sm.xst), i.e. the dynamics driven by exactly the
-// impulses of the forces returned.
+// The states are those of the last sweep's forward pass (sm.xst), i.e. the dynamics driven by exactly the impulses of the
+// forces returned (sm.E) -- also for a robot that leaves uncertified (status MPCQP_STATUS_MAX_ITER): its last sweep was the
+// roll-out of its feasible interior-point iterate (SIG_PIN), `ymax` then points at that iterate's multipliers.
 template <int N>
-__device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>& sm, const DevState& st, int inst, int sub, int hl,
+__device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>& sm, const DevState& st, int inst, int sub, int hl, const int n,
                            unsigned conbits, const uint8_t (&sg)[RicInst<N>::ROUNDS], bool solved, int status, int sweeps, int iters,
-                           const double* __restrict__ adm, bool commit) {
+                           const double* __restrict__ ymax, bool commit) {
     using S = RicInst<N>;
-    constexpr int NF = S::NF, ROUNDS = S::ROUNDS, AW = S::AW, CW = S::CW;
+    constexpr int NF = S::NF, ROUNDS = S::ROUNDS, AWC = S::AW, CWC = S::CW;
+    const int AW = (20 * n + 31) / 32, CW = (4 * n + 31) / 32, ld = n + 1;
     const double lin = P.dt / P.mass;
-    for (int i = hl; i < AW + CW; i += 16) sm.amask[i] = 0u;
+    for (int i = hl; i < AWC + CWC; i += 16) sm.amask[i] = 0u;
     if (!solved) {
         // no forces: the states are the free response  p_{s+1} = p_s + dt v_s, v_{s+1} = v_s + g   (MPC.py:110-111, 200-205)
         if (hl < 6) {
             const int c = hl;
-            double p = sm.xr[c * (N + 1)], v = sm.xr[(6 + c) * (N + 1)];
+            double p = sm.xr[c * ld], v = sm.xr[(6 + c) * ld];
             const double gc = (c == 2) ? -P.gravity * P.dt : 0.0;
-            for (int s = 0; s < N; ++s) {
+            for (int s = 0; s < n; ++s) {
                 const double pn = p + P.dt * v;
                 v += gc; p = pn;
                 sm.xst[12 * s + c] = p; sm.xst[12 * s + 6 + c] = v;
@@ -642,10 +851,10 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
     }
     __syncwarp();
     double part = 0.0;
-    double* xs = st.xs + (size_t)inst * 12 * N;
-    for (int i = hl; i < 12 * N; i += 16) {
+    double* xs = st.xs + (size_t)inst * 12 * n;
+    for (int i = hl; i < 12 * n; i += 16) {
         const int s = i / 12, c = i - 12 * s;
-        const double e = sm.xst[i] - sm.xr[c * (N + 1) + s + 1];
+        const double e = sm.xst[i] - sm.xr[c * ld + s + 1];
         const double ee = isfinite(e) ? e : 0.0;                                             // malformed input: never NaN out
         if (commit) xs[i] = ee;                                                              // MPC.x[:12N] (MPC.py:428)
         part = fma(0.5 * (c < 6 ? P.wp[c] : P.wv[c - 6]) * ee, ee, part);
@@ -654,39 +863,37 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
 #pragma unroll 1
     for (int r = 0; r < ROUNDS; ++r) {
         const int t = hl + 16 * r, k = t >> 2, j = t & 3;
+        const bool exists = t < 4 * n;
         const bool contact = (conbits >> r) & 1u;
         double f[3] = {0.0, 0.0, 0.0};
         FootSol sol;
 #pragma unroll
         for (int q = 0; q < 5; ++q) sol.y[q] = 0.0;
-        if (adm != nullptr && contact) {
-            // ADMM ran out of iterations: its iterate, unpolished (status MPCQP_STATUS_MAX_ITER)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) f[c] = adm[c * NF + t];
-#pragma unroll
-            for (int q = 0; q < 5; ++q) sol.y[q] = adm[(8 + q) * NF + t];
-            // ... clipped into the friction pyramid, so that even a flagged answer is a force the robot can apply
-            f[2] = fmin(fmax(f[2], 0.0), P.fz_max);
-            f[0] = fmin(fmax(f[0], -P.mu * f[2]), P.mu * f[2]);
-            f[1] = fmin(fmax(f[1], -P.mu * f[2]), P.mu * f[2]);
-        } else if (solved && contact) {
-            // multipliers: the guard's closed form on the gradient of the accepted sweep
+        if (solved && contact) {
             f[0] = sm.E[3 * t]; f[1] = sm.E[3 * t + 1]; f[2] = sm.E[3 * t + 2];
-            double A[9], h[3];
-            foot_A<N>(P, sm, t, A);
-            bvT_apply(A, lin, sm.lam + 6 * k, h);
-            const double grad[3] = {fma(P.w_force, f[0], h[0]), fma(P.w_force, f[1], h[1]), fma(P.w_force, f[2], h[2])};
-            uint8_t dummy;
-            kkt_guard(P, sg[r], f, grad, sol, dummy);
+            if (ymax != nullptr) {
+                // uncertified interior-point iterate: its own multipliers (the two fz rows share the reference's fifth row)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sol.y[q] = ymax[(3 + q) * NF + t];
+                sol.y[4] = ymax[7 * NF + t] - ymax[8 * NF + t];
+            } else {
+                // multipliers: the guard's closed form on the gradient of the accepted sweep
+                double A[9], h[3];
+                foot_A<N>(P, sm, t, A);
+                bvT_apply(A, lin, sm.lam + 6 * k, h);
+                const double grad[3] = {fma(P.w_force, f[0], h[0]), fma(P.w_force, f[1], h[1]), fma(P.w_force, f[2], h[2])};
+                uint8_t dummy;
+                kkt_guard(P, sg[r], f, grad, sol, dummy);
+            }
         }
         part += 0.5 * P.w_force * (f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
-        if (commit) {
-            double* fo = st.f + (size_t)inst * 12 * N + 3 * t;
+        if (commit && exists) {
+            double* fo = st.f + (size_t)inst * 12 * n + 3 * t;
             fo[0] = f[0]; fo[1] = f[1]; fo[2] = f[2];
-            double* yo = st.y + (size_t)inst * 20 * N + 5 * t;
+            double* yo = st.y + (size_t)inst * 20 * n + 5 * t;
 #pragma unroll
             for (int q = 0; q < 5; ++q) yo[q] = sol.y[q];
-            st.sig[(size_t)inst * NF + t] = sg[r];
+            st.sig[(size_t)inst * 4 * n + t] = sg[r] > 26 ? SIG_FREE : sg[r];
             if (k == 0) {
                 double* f0 = st.f0 + (size_t)inst * 12 + 3 * j;
                 f0[0] = f[0]; f0[1] = f[1]; f0[2] = f[2];
@@ -696,20 +903,22 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
         const double mu = P.mu, tol = 1e-9;
         const double row[5] = {f[0] - mu * f[2], -f[0] - mu * f[2], f[1] - mu * f[2], -f[1] - mu * f[2], -f[2]};
         const int b0 = 5 * t;
+        if (exists) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            const bool act = (fabs(row[q]) <= tol) || (q == 4 && fabs(row[4] + P.fz_max) <= tol);
-            if (act) atomicOr(&sm.amask[(b0 + q) >> 5], 1u << ((b0 + q) & 31));
+            for (int q = 0; q < 5; ++q) {
+                const bool act = (fabs(row[q]) <= tol) || (q == 4 && fabs(row[4] + P.fz_max) <= tol);
+                if (act) atomicOr(&sm.amask[(b0 + q) >> 5], 1u << ((b0 + q) & 31));
+            }
         }
         const unsigned cb = (__ballot_sync(RIC_FULL, contact) >> (16 * sub)) & 0xFFFFu;      // feet 16 r .. 16 r + 15
-        if (hl == 0 && cb) atomicOr(&sm.amask[AW + (r >> 1)], cb << (16 * (r & 1)));
+        if (hl == 0 && cb) atomicOr(&sm.amask[AWC + (r >> 1)], cb << (16 * (r & 1)));
     }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(RIC_FULL, part, o, 16);
     __syncwarp();
     if (!commit) return;
     for (int i = hl; i < AW; i += 16) st.active[(size_t)inst * AW + i] = sm.amask[i];
-    for (int i = hl; i < CW; i += 16) st.contact[(size_t)inst * CW + i] = sm.amask[AW + i];
+    for (int i = hl; i < CW; i += 16) st.contact[(size_t)inst * CW + i] = sm.amask[AWC + i];
     if (hl == 0) {
         st.obj[inst] = part;
         st.status[inst] = status;
@@ -719,24 +928,73 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
     }
 }
 
+// Inputs of one robot -> shared memory, then the decode: contact flags, lever arms, inertia blocks  [MPC.py:316-360, 635-652].
+// Both halves of the warp call it together.  Returns (uniform over the half-warp) true if the inputs are malformed.
+template <int N>
+__device__ __forceinline__ bool ric_load_decode(const DevParams& P, const DevScenario& SC, RicInst<N>& sm, const double* __restrict__ xref_g,
+                                                const double* __restrict__ fsteps_g, int inst, bool valid, int first_tick, int sub, int hl,
+                                                const int n, unsigned int& phase, unsigned& conbits) {
+    constexpr int NF = RicInst<N>::NF, ROUNDS = RicInst<N>::ROUNDS;
+    if (SC.enabled) {
+        scenario_inputs<16>(P, SC, sm.sc, inst, sm.xr, sm.fs, n, valid);
+    } else {
+        if (hl == 0) {
+            fence_async_smem();
+            mbar_expect_tx(&sm.mbar, (12 * (n + 1) + 260) * 8);
+            bulk_g2s(sm.xr, xref_g + (size_t)inst * 12 * (n + 1), 12 * (n + 1) * 8, &sm.mbar);
+            bulk_g2s(sm.fs, fsteps_g + (size_t)inst * 260, 260 * 8, &sm.mbar);
+        }
+        mbar_wait(&sm.mbar, phase);
+        phase ^= 1u;
+        __syncwarp();
+    }
+    RPROF_T0();
+    RPROF(13);
+    bool bad = false;
+    conbits = 0u;
+#pragma unroll 1
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int t = hl + 16 * r, k = t >> 2, j = t & 3;
+        double lv[3] = {0.0, 0.0, 0.0};
+        bool contact = false;
+        if (t < 4 * n) decode_lever(P, sm.xr, sm.fs, n, k, j, first_tick != 0, lv, contact, bad);
+        sm.lev[t] = lv[0]; sm.lev[NF + t] = lv[1]; sm.lev[2 * NF + t] = lv[2];
+        conbits |= contact ? (1u << r) : 0u;
+    }
+    for (int k = hl; k < n; k += 16) {
+        double Ii[9];
+        step_inertia(P, sm.xr[5 * (n + 1) + k], Ii);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sm.Ii[9 * k + i] = Ii[i];
+    }
+    for (int i = hl; i < 12 * (n + 1); i += 16) bad = bad || !isfinite(sm.xr[i]);
+    const bool any_bad = half_any(bad, sub);
+    __syncwarp();                                            // fs is dead from here on (E overwrites it)
+    RPROF(14);
+    return any_bad;
+}
+
 // `work_ctr` must be zero at launch.
-// The active-set stage, stage-wise factorisation (SWADMM: with the stage-wise ADMM stage compiled in; the default mode runs the
-// instance without it, whose code is a quarter of the size).  Persistent grid: the two robots 2 m, 2 m + 1 of the launch are
+// The active-set stage, stage-wise factorisation.  Persistent grid: the two robots 2 m, 2 m + 1 of the launch are
 // solved by the two halves of warp (m mod warps), warps = RIC_WARPS * gridDim.x; `ws` holds RIC_GAIN * N doubles per
 // half-warp.  The halves share one instruction stream: control flow is warp-uniform, a half that has nothing (left)
-// to do shadows the computation with its stores masked.
-template <int N, bool SWADMM>
+// to do shadows the computation with its stores masked.  Robots the sweeps do not certify are queued (st.fb_list) for the
+// fallback stage the mode selects: ipm_kernel below (MPCQP_MODE_IPM) or the dense ADMM kernel (MPCQP_MODE_ADMM, N <= 32).
+// FULL: the horizon fills the capacity (n = N is a compile-time constant: the headline horizons 16, 32, 64 keep static index
+// arithmetic); otherwise n = P.N < N at run time.
+template <int N, bool FULL>
 __global__ void __launch_bounds__(32 * RIC_WARPS)
 riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g,
                double* __restrict__ ws_g, int* __restrict__ work_ctr, int first_tick, int inst_offset, int inst_count) {
     using S = RicInst<N>;
-    constexpr int NF = S::NF, ROUNDS = S::ROUNDS;
+    constexpr int ROUNDS = S::ROUNDS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = FULL ? N : P.N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane >> 4, hl = lane & 15;
     const int gwarp = blockIdx.x * RIC_WARPS + warp;
     S& sm = reinterpret_cast<S*>(smem_raw)[warp * 2 + sub];
-    double* ws = ws_g + (size_t)(gwarp * 2 + sub) * (RIC_GAIN + 4 * RIC_ADM) * N;      // per half-warp: stage gains, then ADMM state
+    double* ws = ws_g + (size_t)(gwarp * 2 + sub) * (RIC_GAIN + 4 * RIC_ADM) * N;      // per half-warp: stage gains, then interior-point state
     if (hl == 0) mbar_init(&sm.mbar, 1);
     // the fallback kernel behind this one is launched programmatically dependent: let it become resident (its prologue runs, then it
     // blocks in griddepcontrol.wait) as the CTAs of this persistent grid retire, instead of after the grid has drained
@@ -747,6 +1005,7 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
     }
     __syncwarp();
     unsigned int phase = 0;
+    const bool has_fallback = (P.mode & (2 | 8)) != 0;
     // Work distribution: every warp takes its first pair of robots by position and every further pair from a counter, so a
     // warp whose robots needed a second sweep does not also hold up the robots a static schedule would queue behind them.
     for (int w0 = gwarp * 2; w0 < inst_count;
@@ -756,215 +1015,127 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
         __syncwarp();
         RPROF_T0();
         RPROF_COUNT(12);
-        if (SC.enabled) {
-            scenario_inputs<N, 16>(P, SC, sm.sc, inst, sm.xr, sm.fs, valid);
-        } else {
-            if (hl == 0) {
-                fence_async_smem();
-                mbar_expect_tx(&sm.mbar, (12 * (N + 1) + 260) * 8);
-                bulk_g2s(sm.xr, xref_g + (size_t)inst * 12 * (N + 1), 12 * (N + 1) * 8, &sm.mbar);
-                bulk_g2s(sm.fs, fsteps_g + (size_t)inst * 260, 260 * 8, &sm.mbar);
-            }
-            mbar_wait(&sm.mbar, phase);
-            phase ^= 1u;
-            __syncwarp();
-        }
-        RPROF(13);
-        // ---- decode: contact flags, lever arms, inertia blocks, warm-start signature   [MPC.py:316-360, 403-406, 635-652]
         const bool warm = P.warm_start && !first_tick;
-        bool bad = false;
-        unsigned conbits = 0u;
         uint8_t sg[ROUNDS], nsg[ROUNDS];
         // warm start: the previous tick's signatures advanced by one step (MPC.py:403-406); all loads in flight at once
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
-            const int t = hl + 16 * r, k = t >> 2, j = t & 3, ks = (k + 1 < N) ? k + 1 : 0;
-            const uint8_t s8 = warm ? st.sig[(size_t)inst * NF + 4 * ks + j] : SIG_FREE;
+            const int t = hl + 16 * r, k = t >> 2, j = t & 3, ks = (k + 1 < n) ? k + 1 : 0;
+            const uint8_t s8 = (warm && t < 4 * n) ? st.sig[(size_t)inst * 4 * n + 4 * ks + j] : SIG_FREE;
             sg[r] = s8 > 26 ? SIG_FREE : s8;
         }
+        unsigned conbits = 0u;
+        const bool any_bad = ric_load_decode<N>(P, SC, sm, xref_g, fsteps_g, inst, valid, first_tick, sub, hl, n, phase, conbits);
 #pragma unroll 1
-        for (int r = 0; r < ROUNDS; ++r) {
-            const int t = hl + 16 * r, k = t >> 2, j = t & 3;
-            double lv[3];
-            bool contact = false;
-            decode_lever<N>(P, sm.xr, sm.fs, k, j, first_tick != 0, lv, contact, bad);
-            sm.lev[t] = lv[0]; sm.lev[NF + t] = lv[1]; sm.lev[2 * NF + t] = lv[2];
-            conbits |= contact ? (1u << r) : 0u;
-            if (!contact) sg[r] = SIG_FREE;
-        }
-        for (int k = hl; k < N; k += 16) {
-            double Ii[9];
-            step_inertia(P, sm.xr[5 * (N + 1) + k], Ii);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) sm.Ii[9 * k + i] = Ii[i];
-        }
-        for (int i = hl; i < 12 * (N + 1); i += 16) bad = bad || !isfinite(sm.xr[i]);
-        const bool any_bad = half_any(bad, sub);
-        __syncwarp();                                            // fs is dead from here on (E overwrites it)
+        for (int r = 0; r < ROUNDS; ++r)
+            if (!((conbits >> r) & 1u)) sg[r] = SIG_FREE;
         int sweeps = 0, status = 0;
-        bool done = false, stop = any_bad || !valid;
-        RPROF(14);
+        bool done = false;
         if (any_bad) {
             status = 3;
             conbits = 0u;
 #pragma unroll 1
             for (int r = 0; r < ROUNDS; ++r) sg[r] = SIG_FREE;
         }
-        // order-sensitive hash of a signature, uniform over the half-warp (cycle detection)
-        auto sig_hash = [&](const uint8_t (&g)[ROUNDS]) {
-            unsigned long long h = 0ull;
-#pragma unroll 1
-            for (int r = 0; r < ROUNDS; ++r) {
-                if ((conbits >> r) & 1u) {
-                    unsigned long long q = (unsigned long long)(g[r] + 1) * 0x9E3779B97F4A7C15ull;
-                    q ^= q >> 29; q *= (2ull * (hl + 16 * r) + 0xBF58476D1CE4E5B9ull); q ^= q >> 32;
-                    h += q;
-                }
-            }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) h += __shfl_xor_sync(RIC_FULL, h, o, 16);
-            return h;
-        };
-        int nhist = 0;
-        bool careful = false;       // set once the full primal-dual update proposed a signature that was tried before
-        for (int s = 0; s < P.max_sweeps; ++s) {
-            const bool need = !done && !stop;
-            if (!__any_sync(RIC_FULL, need)) break;
-            const int rc = ric_sweep<N>(P, sm, ws, sub, hl, conbits, sg, nsg);
-            bool search = false;
-            if (need) {
-                ++sweeps;
-                if (rc < 0) stop = true;
-                else if (rc > 0) { done = true; status = 1; }
-                else search = true;
-            }
-            if (!__any_sync(RIC_FULL, search)) continue;      // the common case: nothing to hash, nothing to choose
-            // ---- next signature.  The one just tried goes into the history; first choice: every foot adopts its proposal
-            // (primal-dual active-set step).  If that signature was already tried the iteration would cycle: from then on one
-            // foot changes per sweep, in index order.
-            const unsigned long long h = sig_hash(sg);
-            __syncwarp();
-            if (search && hl == 0 && nhist < 16) sm.hist[nhist] = h;
-            if (search) nhist = (nhist < 16) ? nhist + 1 : nhist;
-            __syncwarp();
-            auto seen = [&](unsigned long long q) {
-                bool f = false;
-                for (int i = 0; i < nhist; ++i) f = f || (sm.hist[i] == q);
-                return f;
-            };
-            const unsigned long long hfull = sig_hash(nsg);
-            if (search && !careful) {
-                if (seen(hfull)) careful = true;
-                else {
-#pragma unroll 1
-                    for (int r = 0; r < ROUNDS; ++r) sg[r] = nsg[r];
-                    search = false;
-                }
-            }
-            int tlast = -1;
-            while (__any_sync(RIC_FULL, search)) {
-                int tm = 0x7fffffff;
-#pragma unroll 1
-                for (int r = 0; r < ROUNDS; ++r) {
-                    const int t = hl + 16 * r;
-                    if (nsg[r] != sg[r] && t > tlast && t < tm) tm = t;
-                }
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) { const int q = __shfl_xor_sync(RIC_FULL, tm, o, 16); tm = q < tm ? q : tm; }
-                uint8_t cand[ROUNDS];
-#pragma unroll 1
-                for (int r = 0; r < ROUNDS; ++r) cand[r] = (hl + 16 * r == tm) ? nsg[r] : sg[r];
-                const unsigned long long hc = sig_hash(cand);
-                if (search) {
-                    if (tm == 0x7fffffff) { stop = true; search = false; }            // every single change was tried before
-                    else if (!seen(hc)) {
-#pragma unroll 1
-                        for (int r = 0; r < ROUNDS; ++r) sg[r] = cand[r];
-                        search = false;
-                    } else tlast = tm;
-                }
-            }
-        }
-        // ---- ADMM stage, stage-wise (MPCQP_MODE_ADMM_STAGEWISE): the robots the sweeps gave up on iterate here, in the same
-        //      warp; every check_every iterations a stable active set is handed to a sweep, accepted only if its guard passes
-        int iters = 0;
-        bool admm_out = false;
-        const bool want_admm = SWADMM && (P.mode & 8) && (P.mode & 2) && valid && !done && !any_bad;
-        if (SWADMM && __any_sync(RIC_FULL, want_admm)) {
-            double* adm = ws + (size_t)RIC_GAIN * N;
-            const double mu = P.mu;
-#pragma unroll 1
-            for (int r = 0; r < ROUNDS; ++r) {
-                const int t = hl + 16 * r, k = t >> 2, j = t & 3;
-                double f[3] = {0.0, 0.0, 0.0}, z[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, y[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-                if (warm && ((conbits >> r) & 1u)) {
-                    const int ks = (k + 1 < N) ? k + 1 : 0;                   // MPC.py:403-406
-                    const double* fp = st.f + (size_t)inst * 12 * N + 12 * ks + 3 * j;
-                    const double* yp = st.y + (size_t)inst * 20 * N + 20 * ks + 5 * j;
-                    f[0] = fp[0]; f[1] = fp[1]; f[2] = fp[2];
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) y[q] = yp[q];
-                    const double cf[5] = {f[0] - mu * f[2], -f[0] - mu * f[2], f[1] - mu * f[2], -f[1] - mu * f[2], -f[2]};
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) z[q] = fmin(cf[q], 0.0);
-                    z[4] = fmax(z[4], -P.fz_max);
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) adm[c * NF + t] = f[c];
-#pragma unroll
-                for (int q = 0; q < 5; ++q) { adm[(3 + q) * NF + t] = z[q]; adm[(8 + q) * NF + t] = y[q]; }
-            }
-            uint8_t cur[ROUNDS], prev[ROUNDS];
-#pragma unroll 1
-            for (int r = 0; r < ROUNDS; ++r) prev[r] = 255;
-            bool astop = false;
-            for (int it = 1; it <= P.max_iter; ++it) {
-                const bool needa = want_admm && !done && !astop;
-                if (!__any_sync(RIC_FULL, needa)) break;
-                const bool spd = ric_admm_iter<N>(P, sm, ws, adm, sub, hl, conbits, cur);
-                if (needa) { ++iters; if (!spd) astop = true; }
-#ifdef RIC_DEBUG
-                if (hl == 0 && it < 14) printf("inst %d sub %d it %d needa %d spd %d astop %d cur0 %d f0z %g\n", inst, sub, it, (int)needa, (int)spd, (int)astop, (int)cur[0], adm[2 * NF]);
-#endif
-                if (it >= P.min_iter && (it % P.check_every) == 0) {
-                    bool same = true;
-#pragma unroll 1
-                    for (int r = 0; r < ROUNDS; ++r) { same = same && (cur[r] == prev[r]); prev[r] = cur[r]; }
-                    const bool stable = half_all(same, sub);          // a collective: evaluated by every lane, never short-circuited
-                    const bool tryp = needa && !astop && stable;
-                    if (__any_sync(RIC_FULL, tryp)) {
-                        const int rc = ric_sweep<N>(P, sm, ws, sub, hl, conbits, cur, nsg);
-                        if (tryp) {
-                            ++sweeps;
-                            if (rc > 0) {
-                                done = true; status = 1;
-#pragma unroll 1
-                                for (int r = 0; r < ROUNDS; ++r) sg[r] = cur[r];
-                            }
-                        }
-                    }
-                }
-            }
-            // The iterations above ran on both halves of the warp: a robot that was already solved (or got solved first) had
-            // its sweep results overwritten by the shadow work.  One more sweep on the accepted signatures restores them.
-            ric_sweep<N>(P, sm, ws, sub, hl, conbits, sg, nsg);
-            if (want_admm && !done) {
-                status = 2; admm_out = true;
-#pragma unroll 1
-                for (int r = 0; r < ROUNDS; ++r) sg[r] = SIG_FREE;
-            }
-        }
-        // a robot the sweeps gave up on goes to the (dense) ADMM stage with its carried state untouched
-        const bool pushed = valid && !done && !any_bad && (P.mode & 2) && !(P.mode & 8);
+        ric_active_set<N>(P, sm, ws, sub, hl, n, conbits, sg, nsg, valid && !any_bad, P.max_sweeps, !(P.mode & 8), sweeps, done, status);
+        // a robot the sweeps gave up on goes to the fallback stage with its carried state untouched
+        const bool pushed = valid && !done && !any_bad && has_fallback;
         if (pushed && hl == 0) {
             const int q = atomicAdd(st.fb_count, 1);
             st.fb_list[q] = inst;
             st.sweeps[inst] = sweeps;
         }
         RPROF(15);
-        ric_finish<N>(P, SC, sm, st, inst, sub, hl, conbits, sg, done || admm_out, status, sweeps, iters,
-                      admm_out ? ws + (size_t)RIC_GAIN * N : nullptr, valid && !pushed);
+        ric_finish<N>(P, SC, sm, st, inst, sub, hl, n, conbits, sg, done, status, sweeps, 0, nullptr, valid && !pushed);
         RPROF(16);
+    }
+}
+
+// The interior-point stage for the robots queued in st.fb_list (launched programmatically dependent on riccati_kernel: resident
+// early, reads the queue after griddepcontrol.wait).  Half a warp per robot like the active-set stage, persistent grid, static
+// striding over the queue.  Per robot: interior-point iterations to a complementarity gap of 1e-8 (then 1e-11), the rows with
+// y > s as signature, active-set sweeps from it (same guard => status SOLVED means the same thing as on the fast path).  A robot
+// that is still uncertified leaves with its strictly feasible interior-point forces, the states rolled out from exactly those
+// forces, and status MPCQP_STATUS_MAX_ITER.
+template <int N>
+__global__ void __launch_bounds__(32 * RIC_WARPS)
+ipm_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g,
+           double* __restrict__ ws_g, int first_tick) {
+    using S = RicInst<N>;
+    constexpr int NF = S::NF, ROUNDS = S::ROUNDS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = P.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane >> 4, hl = lane & 15;
+    const int gwarp = blockIdx.x * RIC_WARPS + warp;
+    S& sm = reinterpret_cast<S*>(smem_raw)[warp * 2 + sub];
+    double* ws = ws_g + (size_t)(gwarp * 2 + sub) * (RIC_GAIN + 4 * RIC_ADM) * N;
+    double* adm = ws + (size_t)RIC_GAIN * N;
+    if (hl == 0) mbar_init(&sm.mbar, 1);
+    __syncwarp();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int n_work = *st.fb_count;
+    unsigned int phase = 0;
+    for (int w0 = gwarp * 2; w0 < n_work; w0 += gridDim.x * RIC_PER_CTA) {
+        const bool valid = w0 + sub < n_work;
+        const int inst = st.fb_list[valid ? w0 + sub : w0];
+        __syncwarp();
+        unsigned conbits = 0u;
+        const bool any_bad = ric_load_decode<N>(P, SC, sm, xref_g, fsteps_g, inst, valid, first_tick, sub, hl, n, phase, conbits);
+        uint8_t sg[ROUNDS], nsg[ROUNDS];
+        int sweeps = valid ? st.sweeps[inst] : 0, status = 0, iters = 0;
+        bool done = false;
+        // ---- start: every stance force well inside its pyramid, gap 1
+#pragma unroll 1
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int t = hl + 16 * r;
+            sg[r] = SIG_FREE;
+            const double f0[3] = {0.0, 0.0, 2.0};
+            const double s0[6] = {P.mu * 2.0, P.mu * 2.0, P.mu * 2.0, P.mu * 2.0, 2.0, P.fz_max - 2.0};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) adm[c * NF + t] = f0[c];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) adm[(3 + q) * NF + t] = 1.0 / s0[q];
+        }
+        __syncwarp();
+        double gap = 1.0, sigma = 0.3;
+        bool alive = valid && !any_bad;
+        for (int round = 0; round < 2; ++round) {
+            const bool want = alive && !done;
+            if (!__any_sync(RIC_FULL, want)) break;
+            const bool ok = ric_ipm<N>(P, sm, ws, adm, sub, hl, n, conbits, want, round == 0 ? 1e-8 : 1e-11, P.ipm_max_iter, gap, sigma, iters);
+            if (want && !ok) alive = false;
+            // ---- signature of the iterate: a row is active iff its multiplier outweighs its slack
+#pragma unroll 1
+            for (int r = 0; r < ROUNDS; ++r) {
+                const int t = hl + 16 * r;
+                if (want && ((conbits >> r) & 1u)) {
+                    double f[3], y[6];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) f[c] = adm[c * NF + t];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) y[q] = adm[(3 + q) * NF + t];
+                    const double mz = P.mu * f[2];
+                    const bool a0 = y[0] > mz - f[0], a1 = y[1] > mz + f[0], a2 = y[2] > mz - f[1], a3 = y[3] > mz + f[1];
+                    const bool a4 = y[4] > f[2], a5 = y[5] > P.fz_max - f[2];
+                    const bool apex = a4 || (a0 && a1) || (a2 && a3);
+                    sg[r] = sig_pack((a0 ? 1 : 0) - (a1 ? 1 : 0), (a2 ? 1 : 0) - (a3 ? 1 : 0), apex ? 1 : (a5 ? 2 : 0));
+                }
+            }
+            ric_active_set<N>(P, sm, ws, sub, hl, n, conbits, sg, nsg, want && alive, P.max_sweeps > 8 ? P.max_sweeps : 8, false, sweeps, done, status);
+        }
+        // The sweeps above ran on both halves of the warp: a robot that got solved first had its results overwritten by the
+        // shadow work.  One more sweep restores them; an uncertified robot rolls out its interior-point forces instead.
+        const bool failed = valid && !any_bad && !done;
+        if (failed) {
+            status = 2;
+#pragma unroll 1
+            for (int r = 0; r < ROUNDS; ++r) sg[r] = SIG_PIN;
+        }
+        ric_sweep<N>(P, sm, ws, sub, hl, n, conbits, sg, nsg, adm);
+        if (any_bad) status = 3;
+        ric_finish<N>(P, SC, sm, st, inst, sub, hl, n, any_bad ? 0u : conbits, sg, (done || failed) && !any_bad, status, sweeps, iters,
+                      failed ? adm : nullptr, valid);
     }
 }
 

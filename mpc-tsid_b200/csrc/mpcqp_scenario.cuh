@@ -21,7 +21,7 @@ struct DevScenario {
     double* feet;           // B x 8   feet in the world, [x0..x3, y0..y3]
     double* target;         // B x 8   where each swinging foot is planned to land (world)
     const double* vref;     // B x 6
-    const unsigned long long* seq;   // B: bit 4 s + j = foot j in contact at step s of the 16-step gait period
+    const unsigned long long* seq;   // B: bit 4 s + j = foot j in contact at step s of the gait period (<= 16 steps)
     const int32_t* phase;   // B
     uint8_t* prevc;         // B: bits 0..3 contact of the previous tick's first step, bit 7 = valid
     double* xref_out;       // optional B x 12 x (N+1): the inputs generated this tick (parity hook), or null
@@ -31,6 +31,7 @@ struct DevScenario {
     double lin_b[64];       // numpy.linspace(dt, T_gait, N)          (FootstepPlanner.py:114)
     unsigned long long seed;
     int tick;               // closed-loop tick of this launch
+    int period;             // steps per gait period (T_gait / dt), <= 16
     int enabled;
 };
 
@@ -67,9 +68,10 @@ struct ScenarioSmem {
 
 // Build xref (12 x (N+1)) and fsteps (20 x 13) of instance `inst` in shared memory.  Called by every thread of
 // the group that owns the instance: the whole CTA (GROUP = 0), one warp (GROUP = 32) or half a warp (GROUP = 16).
-template <int N, int GROUP = 0>
+// N is the run-time horizon (xref is 12 x (N + 1)).
+template <int GROUP = 0>
 __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, ScenarioSmem& sc, int inst, double* xr, double* fs,
-                                bool commit = true) {
+                                const int N, bool commit = true) {
     constexpr bool WARP = GROUP != 0;
     const int tid = WARP ? (int)(threadIdx.x & (GROUP - 1)) : (int)threadIdx.x;
     const int nthr = WARP ? GROUP : (int)blockDim.x;
@@ -89,7 +91,7 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
         const int ph = S.phase[inst];
         int rows = 0, prev = -1;
         for (int i = 0; i < N; ++i) {
-            const int s = (S.tick + ph + i) & 15;
+            const int s = (S.tick + ph + i) % S.period;
             const int m = (int)((seq >> (4 * s)) & 15ull);
             if (m != prev) { sc.mask[rows] = m; sc.cnt[rows] = 1; ++rows; prev = m; }
             else sc.cnt[rows - 1] += 1;

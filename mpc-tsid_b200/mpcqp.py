@@ -11,7 +11,7 @@ import numpy as np
 HOST, DEVICE = 0, 1
 MODE_ACTIVE_SET, MODE_ADMM = 1, 2
 MODE_STAGEWISE = 4           # active-set stage on the stage-wise (Riccati) factorisation, half a warp per robot
-MODE_ADMM_STAGEWISE = 8      # ADMM stage on the stage-wise factorisation too (any horizon)
+MODE_IPM = 8                 # fallback stage of the stage-wise path: interior-point iterations on the same factorisation (any horizon)
 STATUS = {0: "unsolved", 1: "solved", 2: "max_iter", 3: "bad_input"}
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmpcqp.so")
@@ -38,7 +38,7 @@ class Params(C.Structure):
         ("check_every", C.c_int32), ("warm_start", C.c_int32),
         ("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
         ("feas_tol", C.c_double), ("dual_tol", C.c_double),
-        ("refine", C.c_int32), ("reserved", C.c_int32),
+        ("refine", C.c_int32), ("ipm_max_iter", C.c_int32),
     ]
 
 
@@ -150,10 +150,6 @@ class Engine:
 
     def __init__(self, batch=1, n_steps=16, device=0, **overrides):
         self.lib = load()
-        if int(n_steps) == 64:
-            # horizons beyond 32 steps run both stages on the stage-wise factorisation (the dense ADMM stage keeps a
-            # 6N x 6N factor in shared memory, which stops fitting)
-            overrides.setdefault("mode", 15)
         self.params = default_params(batch=int(batch), n_steps=int(n_steps), device=int(device), **overrides)
         self.B, self.N = int(batch), int(n_steps)
         h = C.c_void_p()

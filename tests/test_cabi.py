@@ -32,7 +32,7 @@ def test_params_layout_matches_header():
     assert (p.n_steps, p.dt, p.T_gait, p.mu, p.fz_max) == (16, 0.02, 0.32, 0.9, 25.0)
     assert abs(p.mass - 2.50000279) < 1e-15 and abs(p.gI[4] - 5.106100e-2) < 1e-18
     assert abs(p.w_state[6] - 2 * 0.1 ** 0.5) < 1e-15 and p.w_force == 1e-5
-    assert p.mode == mpcqp.MODE_ACTIVE_SET | mpcqp.MODE_ADMM | mpcqp.MODE_STAGEWISE and p.max_sweeps == 12
+    assert p.mode == mpcqp.MODE_ACTIVE_SET | mpcqp.MODE_STAGEWISE | mpcqp.MODE_IPM and p.max_sweeps == 16 and p.ipm_max_iter == 60
     assert b"sm_100a" in mpcqp.load().mpcqp_version()
 
 
@@ -55,8 +55,11 @@ def test_bad_arguments_are_rejected_before_touching_the_gpu():
     p.struct_size = 8
     assert lib.mpcqp_create(ctypes.byref(p), ctypes.byref(h)) == -1
     assert b"struct_size" in lib.mpcqp_last_error()
-    p = mpcqp.default_params(n_steps=24)            # only horizons 16 and 32 are compiled in
+    p = mpcqp.default_params(n_steps=65)            # horizons 1 .. 64
     assert lib.mpcqp_create(ctypes.byref(p), ctypes.byref(h)) == -1
+    p = mpcqp.default_params(n_steps=24, mode=3)    # the dense stages exist for 16 and 32 steps only
+    assert lib.mpcqp_create(ctypes.byref(p), ctypes.byref(h)) == -1
+    assert b"dense" in lib.mpcqp_last_error()
     p = mpcqp.default_params(batch=0)
     assert lib.mpcqp_create(ctypes.byref(p), ctypes.byref(h)) == -1
     assert lib.mpcqp_run(None, 0.0, None, None, 0) == -1

@@ -32,16 +32,18 @@ def _active_from_x(g, t, n):
     return ((np.abs(Ax - u) <= 1e-9) | (np.abs(Ax - l) <= 1e-9)).reshape(n, 4, 5)
 
 
-@pytest.mark.parametrize("mode", [7, 3, 2], ids=["stagewise+admm", "dense+admm", "admm-only"])
+@pytest.mark.parametrize("mode", [13, -13, 7, 3, 2], ids=["stagewise+ipm", "ipm-only", "stagewise+admm", "dense+admm", "admm-only"])
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[6:-4] for p in GOLD])
 def test_golden_sequences(path, mode):
-    """Replay each golden closed-loop sequence tick by tick (warm start carried like the reference)."""
+    """Replay each golden closed-loop sequence tick by tick (warm start carried like the reference).  mode 13 is the default
+    (stage-wise sweeps, interior-point fallback); "ipm-only" switches the warm-started sweeps off so that EVERY tick is solved
+    by the interior-point stage and the sweeps it seeds."""
     g = np.load(path)
     n = g["x"].shape[1] // 24                       # horizon of this fixture (16, or 32 / 64 for the long-horizon cases)
-    if n == 64:
-        if mode != 7:
-            pytest.skip("N = 64 runs on the stage-wise active-set stage only")
-        eng = mpcqp.Engine(batch=1, n_steps=n)      # the wrapper's N = 64 default: mode 15 (both stages stage-wise)
+    if n == 64 and mode in (7, 3, 2):
+        pytest.skip("the dense stages exist for N = 16 and 32")
+    if mode == -13:
+        eng = mpcqp.Engine(batch=1, n_steps=n, mode=13, max_sweeps=0)
     else:
         eng = mpcqp.Engine(batch=1, n_steps=n, mode=mode)
     for t in range(len(g["k"])):
@@ -126,7 +128,7 @@ def test_horizon_64_trot_closed_loop_certified():
     from oracle import mpc_build
     B, T, n = 16, 5, 64
     eng = mpcqp.Engine(batch=B, n_steps=n)
-    assert eng.params.mode == 15
+    assert eng.params.mode == 13
     rng = np.random.default_rng(64)
     v_ref = np.zeros((B, 6))
     v_ref[:, 0], v_ref[:, 1], v_ref[:, 5] = rng.uniform(-0.2, 0.45, B), rng.uniform(-0.15, 0.15, B), rng.uniform(-0.3, 0.3, B)
@@ -145,48 +147,102 @@ def test_horizon_64_trot_closed_loop_certified():
     eng.close()
 
 
-def test_stagewise_admm_stage_is_the_dense_admm_stage():
-    """MPCQP_MODE_ADMM_STAGEWISE runs the same splitting as the dense ADMM stage on the stage-wise factorisation: with the
-    active-set sweeps switched off (max_sweeps = 0) both engines must take the same number of ADMM iterations and polish
-    attempts, robot by robot, and land on the same optimum (cold and warm ticks, mixed gaits, odd batch)."""
+def test_interior_point_stage_alone_lands_on_the_same_optimum():
+    """The fallback stage of the stage-wise path with the warm-started sweeps switched off (max_sweeps = 0 sends every robot to
+    ipm_kernel): interior-point iterations, the signature they identify, the sweeps from it.  Same (unique) optimum as the dense
+    ADMM stage, every robot certified by the same guard, cold and warm ticks, mixed gaits, odd batch."""
     B = 9
     sc = Scenario(B, gaits=["trot", "walk", "bound"], seed=5)
-    dense, sw = mpcqp.Engine(batch=B, mode=2), mpcqp.Engine(batch=B, mode=15, max_sweeps=0)
+    dense, ipm = mpcqp.Engine(batch=B, mode=2), mpcqp.Engine(batch=B, mode=13, max_sweeps=0)
     for t in range(4):
         xref, fsteps = sc.inputs()
         dense.run(t, xref, fsteps)
-        sw.run(t, xref, fsteps)
-        xd, xs, idn, isw = dense.solution(), sw.solution(), dense.info(), sw.info()
-        assert (idn["status"] == 1).all() and (isw["status"] == 1).all()
-        np.testing.assert_array_equal(idn["iters"], isw["iters"])
-        np.testing.assert_array_equal(idn["sweeps"], isw["sweeps"])
+        ipm.run(t, xref, fsteps)
+        xd, xs, idn, iip = dense.solution(), ipm.solution(), dense.info(), ipm.info()
+        assert (idn["status"] == 1).all() and (iip["status"] == 1).all()
+        assert ipm.fallback_count() == B and (iip["iters"] > 0).all() and (iip["iters"] <= 60).all()
         assert np.abs(xd - xs).max() <= 1e-8
-        np.testing.assert_array_equal(idn["active"], isw["active"])
+        np.testing.assert_array_equal(idn["active"], iip["active"])
+        for b in (0, 4, 8):
+            assert_certified(certify(xref[b], fsteps[b], xs[b], iip["y"][b], first_tick=(t == 0)), "tick %d robot %d" % (t, b))
         sc.advance(xd[:, :12] + xref[:, :, 1])
-    dense.close(); sw.close()
+    dense.close(); ipm.close()
 
 
-def test_hard_long_horizon_instances_are_flagged_not_wrong():
-    """N = 64 released from rest with a 1 m/s command is close to bang-bang (most stance foot-steps at the apex or at fz_max,
-    degenerate multipliers): robots neither stage can certify within the iteration cap must come back flagged
-    MPCQP_STATUS_MAX_ITER with finite forces inside the friction pyramid; the certified ones must pass the oracle's check."""
+def _dynamics_residual(xref, fsteps, x, n, first_tick):
+    """max |A x - b| over the 12 n dynamics rows of the QP the reference would have built (MPC.py:98-134, 362-378)."""
+    from oracle import mpc_build
+    _, A, l, u, _ = mpc_build.build_qp(xref, fsteps, mpc_build.Params(n_steps=n), first_tick=first_tick)
+    return np.abs((A @ x)[:12 * n] - u[:12 * n]).max()
+
+
+def test_hard_long_horizon_instances_are_solved():
+    """N = 64 released from rest with a 0.7 .. 1 m/s command is close to bang-bang (two thirds of the stance foot-steps at the apex
+    or at fz_max, near-degenerate multipliers): the warm-started sweeps cycle on some of them, the interior-point stage must
+    then finish the job.  The reference's OSQP solves these (MPC.py:414-428), so must we: every robot SOLVED and certified
+    by the oracle at the default settings."""
     from oracle import mpc_build
     B, n = 8, 64
     v_ref = np.zeros((B, 6))
     v_ref[:, 0] = np.linspace(0.7, 1.0, B)
     sc = Scenario(B, n_steps=n, gaits=["trot"], seed=3, v_ref=v_ref)
-    eng = mpcqp.Engine(batch=B, n_steps=n, max_iter=60)
+    eng = mpcqp.Engine(batch=B, n_steps=n)
+    par = mpc_build.Params(n_steps=n)
+    for t in range(3):
+        xref, fsteps = sc.inputs()
+        eng.run(t, xref, fsteps)
+        x, info = eng.solution(), eng.info()
+        assert (info["status"] == 1).all(), (t, info["status"], info["sweeps"], info["iters"])
+        for b in range(B):
+            assert_certified(certify(xref[b], fsteps[b], x[b], info["y"][b], first_tick=(t == 0), params=par), "tick %d robot %d" % (t, b))
+        sc.advance(x[:, :12] + xref[:, :, 1])
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [16, 32, 64])
+def test_aggressive_cold_starts_are_solved(n):
+    """Robots of every gait released with large velocity errors and commands up to 1.5 m/s (the regime of
+    tests/golden/solve_aggressive.npz), cold start: every robot SOLVED, a sample certified by the oracle."""
+    from oracle import mpc_build
+    B = 256 if n < 64 else 64
+    rng = np.random.default_rng(1000 + n)
+    v_ref = np.zeros((B, 6))
+    v_ref[:, 0], v_ref[:, 1], v_ref[:, 5] = rng.uniform(-0.8, 1.5, B), rng.uniform(-0.5, 0.5, B), rng.uniform(-0.8, 0.8, B)
+    sc = Scenario(B, n_steps=n, gaits=["trot", "pace", "bound", "walk"], seed=100 + n, v_ref=v_ref)
+    sc.state[:, 6:12] += rng.normal(0, 0.3, (B, 6))
+    sc.state[:, 3:5] += rng.normal(0, 0.1, (B, 2))
+    eng = mpcqp.Engine(batch=B, n_steps=n)
+    par = mpc_build.Params(n_steps=n)
+    for t in range(3):
+        xref, fsteps = sc.inputs()
+        eng.run(t, xref, fsteps)
+        x, info = eng.solution(), eng.info()
+        assert (info["status"] == 1).all(), (t, np.flatnonzero(info["status"] != 1), info["sweeps"].max(), info["iters"].max())
+        for b in range(0, B, 37):
+            assert_certified(certify(xref[b], fsteps[b], x[b], info["y"][b], first_tick=(t == 0), params=par), "tick %d robot %d" % (t, b))
+        sc.advance(x[:, :12] + xref[:, :, 1])
+    eng.close()
+
+
+def test_uncertified_answers_are_feasible_and_consistent():
+    """MPCQP_STATUS_MAX_ITER contract (forced here by starving both stages of iterations): finite forces inside the friction
+    pyramid, and x[:12N] is the roll-out of exactly those forces -- the dynamics rows of the reference's QP hold."""
+    B, n = 8, 64
+    v_ref = np.zeros((B, 6))
+    v_ref[:, 0] = np.linspace(0.7, 1.0, B)
+    sc = Scenario(B, n_steps=n, gaits=["trot"], seed=3, v_ref=v_ref)
+    eng = mpcqp.Engine(batch=B, n_steps=n, max_sweeps=1, ipm_max_iter=4)
     xref, fsteps = sc.inputs()
     eng.run(0, xref, fsteps)
     x, info = eng.solution(), eng.info()
-    assert np.isfinite(x).all() and set(np.unique(info["status"])) <= {1, 2}
+    assert np.isfinite(x).all() and set(np.unique(info["status"])) <= {1, 2} and (info["status"] == 2).any()
     f = x[:, 12 * n:].reshape(B, n, 4, 3)
     mu = eng.params.mu
     assert (np.abs(f[..., 0]) <= mu * f[..., 2] + 1e-9).all() and (np.abs(f[..., 1]) <= mu * f[..., 2] + 1e-9).all()
-    assert (f[..., 2] >= 0).all() and (f[..., 2] <= 25).all() and (info["status"] == 2).any()
-    par = mpc_build.Params(n_steps=n)
-    for b in np.flatnonzero(info["status"] == 1)[:2]:
-        assert_certified(certify(xref[b], fsteps[b], x[b], info["y"][b], first_tick=True, params=par), "robot %d" % b)
+    assert (f[..., 2] >= 0).all() and (f[..., 2] <= 25).all()
+    for b in range(B):
+        assert _dynamics_residual(xref[b], fsteps[b], x[b], n, True) <= 1e-9, b
+    np.testing.assert_array_equal(eng.forces(), x[:, 12 * n:12 * n + 12])
     eng.close()
 
 

@@ -1,6 +1,6 @@
 """Small all-mode smoke (compute-sanitizer is closed on this pool; bounds are checked by the parity suite): 6 robots, mixed gaits, 4 ticks,
 default mode and the dense + ADMM modes, plus 3 ticks of the device-resident closed loop.
-python tools/dev_sanitize.py"""
+python tools/scratch/dev_sanitize.py"""
 import sys
 import numpy as np
 sys.path.insert(0, "/root/repo/mpc-tsid_b200"); sys.path.insert(0, "/root/repo")
