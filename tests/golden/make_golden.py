@@ -39,7 +39,7 @@ from scenario import Scenario, SHOULDERS, H_REF   # noqa: E402
 assert RefMPC.__file__.startswith("/root/reference"), RefMPC.__file__
 
 
-def run_case(name, scen, ticks, first_state=None):
+def run_case(name, scen, ticks, first_state=None, prefix="solve"):
     """Closed loop: scenario -> reference MPC.run -> scenario.advance(reference prediction)."""
     mpc = RefMPC.MPC(scen.dt, scen.N, scen.T_gait)
     if first_state is not None:
@@ -71,10 +71,11 @@ def run_case(name, scen, ticks, first_state=None):
     out["ML_indptr"] = mpc.ML.indptr.copy()
     out["i_update_B"] = np.asarray(mpc.i_update_B)
     out["i_update_S"] = np.asarray(mpc.i_update_S)
-    if scen.N != 16:
+    out["dt"], out["T_gait"] = np.float64(scen.dt), np.float64(scen.T_gait)
+    if scen.N != 16 or prefix != "solve":
         for key in ("ML_data", "NK", "NK_inf", "x_admm", "warm_x"):     # keep the long-horizon fixture small
             out[key] = out[key][:2]
-    np.savez_compressed(os.path.join(HERE, "solve_%s.npz" % name), **out)
+    np.savez_compressed(os.path.join(HERE, "%s_%s.npz" % (prefix, name)), **out)
     nact = int(((np.abs(out["x"][:, 12 * scen.N:].reshape(ticks, -1, 3)[:, :, 2] - 25.0) < 1e-9)).sum())
     print("wrote solve_%s.npz  (%d ticks, %d foot-steps at fz_max)" % (name, ticks, nact))
 
@@ -137,8 +138,24 @@ def long_horizon_64():
     run_case("trot_N64", s, 3)
 
 
+def general_horizons():
+    # 8. horizons other than 16 / 32 / 64 and other MPC time steps: n_steps = n_periods * T_gait / dt (main.py:20-23,
+    #    FootstepPlanner.py:52-63).  Files horizon_<case>.npz (they also carry dt and T_gait).
+    cases = (("trot_N24", dict(n_steps=24, dt=0.02, T_gait=0.48, gaits="trot"), [0.4, 0.1, 0, 0, 0, 0.2], 5),
+             ("trot_dt01", dict(n_steps=32, dt=0.01, T_gait=0.32, gaits="trot"), [0.5, -0.1, 0, 0, 0, 0.3], 7),
+             ("walk_N8", dict(n_steps=8, dt=0.04, T_gait=0.32, gaits="walk"), [0.2, 0.05, 0, 0, 0, -0.2], 1),
+             ("pace_N12", dict(n_steps=12, dt=0.02, T_gait=0.24, gaits="pace"), [0.3, 0.1, 0, 0, 0, 0.1], 4),
+             ("bound_N10", dict(n_steps=10, dt=0.02, T_gait=0.2, gaits="bound"), [0.25, 0.0, 0, 0, 0, -0.3], 2),
+             ("trot_N48", dict(n_steps=48, dt=0.02, T_gait=0.48, gaits="trot"), [0.6, 0.15, 0, 0, 0, -0.25], 9))
+    for i, (name, kw, v, ph) in enumerate(cases):
+        s = Scenario(1, v_ref=v, phase=[ph], random_commands=False, seed=30 + i, **kw)
+        run_case(name, s, 4, prefix="horizon")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "long":
+    if len(sys.argv) > 1 and sys.argv[1] == "horizons":
+        general_horizons()
+    elif len(sys.argv) > 1 and sys.argv[1] == "long":
         long_horizon()
     elif len(sys.argv) > 1 and sys.argv[1] == "long64":
         long_horizon_64()
@@ -146,3 +163,4 @@ if __name__ == "__main__":
         main()
         long_horizon()
         long_horizon_64()
+        general_horizons()
