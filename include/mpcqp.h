@@ -105,6 +105,14 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
  * B x 12 forces of the last run.  Synchronises the handle's stream when location == MPCQP_HOST. */
 int mpcqp_get_latest_result(mpcqp_handle* h, double* forces, int location);
 
+/* What a control loop reads every tick, in one call and one synchronisation: forces (B x 12, as above; may be NULL) and
+ * dev1 (B x 12; may be NULL) = X_1 - xref_1, the first predicted state minus its reference, from which MPC.q_next / v_next
+ * (MPC.py:448-450) and the dead-reckoned MPC.q_w (MPC.py:503-510) follow as dev1 + xref[:, 1]. */
+int mpcqp_get_step_result(mpcqp_handle* h, double* forces, double* dev1, int location);
+
+/* status[B] alone (MPCQP_STATUS_*): the cheap check the reference never makes (MPC.py:427 ignores sol.info.status). */
+int mpcqp_get_status(mpcqp_handle* h, int32_t* status, int location);
+
 /* MPC.x (MPC.py:428): B x 24N.  MPC.x_robot (MPC.py:437-447) is x[:12N] + xref[:,1:]. */
 int mpcqp_get_solution(mpcqp_handle* h, double* x, int location);
 

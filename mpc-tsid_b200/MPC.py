@@ -9,8 +9,12 @@ leading axis of size B.  `run(k, T_gait=..., fsteps=..., xref=...)` (the north-s
 signature) is accepted by keyword.  Differences on purpose:
   * the caller's fsteps is NOT modified (the reference overwrites its NaNs, MPC.py:327);
   * `status` / `info` report per-instance solver status (the reference never looks, MPC.py:427);
+  * results travel when they are read: `run` enqueues the tick and returns; `f_applied` / `q_next` / `v_next` / `q_w` cost one
+    small copy (24 doubles per robot, what MPC_Wrapper.py:103-114 needs), `x` / `x_robot` the full 24N per robot;
   * there is no CPU path: construction fails without the CUDA extension or without a B200.
 """
+import warnings
+
 import numpy as np
 
 import mpcqp
@@ -31,18 +35,20 @@ class MPC:
         self._w = np.concatenate([np.tile(np.array(p.w_state[:]), self.n_steps),
                                   np.full(12 * self.n_steps, p.w_force)])
         self.xref = np.zeros((12, 1 + self.n_steps))    # MPC.py:49
-        self.x = np.zeros((12 * self.n_steps * 2,))     # MPC.py:52
         self.q = np.array([[0.0, 0.0, 0.2027682, 0.0, 0.0, 0.0]]).transpose()   # MPC.py:55
-        self.q_w = self.q.copy()                        # MPC.py:58
+        self._qw0 = self.q[:, 0].copy()                 # MPC.py:58: the world pose every robot starts from
         self.v = np.zeros((6, 1))                       # MPC.py:61
         self.h_ref = self.q[2, 0]                       # MPC.py:64
-        self.f_applied = np.zeros((12,))
-        self.x_robot = np.zeros((12, self.n_steps))
-        self.q_next = np.zeros((6, 1))
-        self.v_next = np.zeros((6, 1))
-        self.status = None
         self._engine = None
-        self._batched = None
+        self._batched = False
+        self._B = 1
+        self._ran = False
+        self._pending = False                           # the last tick's dead-reckoning step has not been applied yet
+        self._qw = self._qw0[None, :].copy()            # (B, 6) dead-reckoned world poses
+        self._step = None                               # (f_applied, x_next) of the last tick once fetched
+        self._full = None                               # full solution of the last tick once fetched
+        self._status = None
+        self._xb = None
         if batch is not None:
             self._make_engine(int(batch))
 
@@ -58,59 +64,18 @@ class MPC:
 
     def _make_engine(self, batch):
         if self._engine is not None:
+            self._settle()
             self._engine.close()
         self._engine = mpcqp.Engine(batch=batch, n_steps=self.n_steps, device=self._device, dt=float(self.dt),
                                     T_gait=float(self.T_gait), **self._opts)
-        self._qw = np.tile(self.q_w[:, 0], (batch, 1))
+        if self._qw.shape[0] != batch:
+            # a new batch size is a new set of robots: they start from the initial world pose (MPC.py:58)
+            self._qw = np.tile(self._qw0, (batch, 1))
+        self._B = batch
+        self._ran = False
+        self._step = self._full = self._status = None
 
-    def run(self, k, xref=None, fsteps=None, T_gait=None):
-        if xref is None or fsteps is None:
-            raise TypeError("run(k, xref, fsteps): xref and fsteps are required")
-        xref = np.asarray(xref, dtype=np.float64)
-        fsteps = np.asarray(fsteps, dtype=np.float64)
-        batched = xref.ndim == 3
-        xb = xref if batched else xref[None]
-        fb = fsteps if batched else fsteps[None]
-        if xb.shape[1:] != (12, self.n_steps + 1) or fb.shape[1:] != (20, 13) or fb.shape[0] != xb.shape[0]:
-            raise ValueError("xref must be ([B,] 12, %d) and fsteps ([B,] 20, 13)" % (self.n_steps + 1))
-        B = xb.shape[0]
-        if self._engine is None or self._engine.B != B:
-            self._make_engine(B)
-        self._batched = batched
-        eng = self._engine
-        eng.run(float(k), xb, fb)
-        x = eng.solution()
-        f0 = eng.forces()
-        N = self.n_steps
-        # retrieve_result, MPC.py:432-450
-        x_robot = x[:, :12 * N].reshape(B, N, 12).transpose(0, 2, 1) + xb[:, :, 1:]
-        # dead-reckoned world pose, MPC.py:503-510
-        c, s = np.cos(self._qw[:, 5]), np.sin(self._qw[:, 5])
-        qn = x_robot[:, 0:6, 0]
-        self._qw[:, 0] += c * qn[:, 0] - s * qn[:, 1]
-        self._qw[:, 1] += s * qn[:, 0] + c * qn[:, 1]
-        self._qw[:, 2] = qn[:, 2]
-        self._qw[:, 3:5] = qn[:, 3:5]
-        self._qw[:, 5] += qn[:, 5]
-        self.xref = xref
-        self.x0 = xref[..., 0:1]
-        if batched:
-            self.x, self.f_applied, self.x_robot = x, f0, x_robot
-            self.q_next, self.v_next = x_robot[:, 0:6, 0:1], x_robot[:, 6:12, 0:1]
-            self.q_w = self._qw[:, :, None].copy()
-        else:
-            self.x, self.f_applied, self.x_robot = x[0], f0[0], x_robot[0]
-            self.q_next, self.v_next = x_robot[0, 0:6, 0:1], x_robot[0, 6:12, 0:1]
-            self.q_w = self._qw[0].reshape(6, 1).copy()
-            if k > 0:                                     # MPC.py:478-482
-                self.q[0:6, 0] = xref[0:6, 0]
-                self.v[0:6, 0] = xref[6:12, 0]
-        self.status = None
-        return 0
-
-    def run_async(self, k, xref, fsteps, slot):
-        """Enqueue one tick and the copy of its forces into the engine's pinned slot; returns without waiting.
-        Used by MPC_Wrapper's asynchronous mode; the caller owns xref / fsteps until the result has been collected."""
+    def _check_inputs(self, xref, fsteps):
         xref = np.asarray(xref, dtype=np.float64)
         fsteps = np.asarray(fsteps, dtype=np.float64)
         batched = xref.ndim == 3
@@ -120,9 +85,116 @@ class MPC:
             raise ValueError("xref must be ([B,] 12, %d) and fsteps ([B,] 20, 13)" % (self.n_steps + 1))
         if self._engine is None or self._engine.B != xb.shape[0]:
             self._make_engine(xb.shape[0])
+        return xref, batched, xb, fb
+
+    def run(self, k, xref=None, fsteps=None, T_gait=None):
+        if xref is None or fsteps is None:
+            raise TypeError("run(k, xref, fsteps): xref and fsteps are required")
+        xref, batched, xb, fb = self._check_inputs(xref, fsteps)
+        self._settle()                                  # the previous tick's step of the dead reckoning, if nobody asked for it
+        self._batched = batched
+        self._engine.run(float(k), xb, fb)              # asynchronous: build + solve + extract on the device
+        self._ran, self._pending = True, True
+        self._step = self._full = self._status = None
+        self._xb = xb
+        self.xref = xref                                # MPC.py:486 (aliased there too)
+        self.x0 = xref[..., 0:1]
+        if not batched and k > 0:                       # MPC.py:478-482
+            self.q[0:6, 0] = xref[0:6, 0]
+            self.v[0:6, 0] = xref[6:12, 0]
+        return 0
+
+    # ---- results, fetched when read ---------------------------------------------------------------------------
+    def _settle(self):
+        """Forces + first predicted state of the last tick (one small copy), and this tick's step of MPC.py:503-510."""
+        if not self._ran or self._step is not None:
+            return
+        f0, dev1 = self._engine.step_result()
+        xn = dev1 + self._xb[:, :, 1]                   # MPC.py:437: x_robot[:, 0]
+        self._step = (f0, xn)
+        if self._pending:
+            c, s = np.cos(self._qw[:, 5]), np.sin(self._qw[:, 5])
+            self._qw[:, 0] += c * xn[:, 0] - s * xn[:, 1]
+            self._qw[:, 1] += s * xn[:, 0] + c * xn[:, 1]
+            self._qw[:, 2] = xn[:, 2]
+            self._qw[:, 3:5] = xn[:, 3:5]
+            self._qw[:, 5] += xn[:, 5]
+            self._pending = False
+
+    def _fetch_full(self):
+        if self._full is None and self._ran:
+            self._settle()
+            self._full = self._engine.solution()
+        return self._full
+
+    @property
+    def f_applied(self):                                # MPC.py:441
+        if not self._ran:
+            return np.zeros((12,))
+        self._settle()
+        return self._step[0] if self._batched else self._step[0][0]
+
+    @property
+    def q_next(self):                                   # MPC.py:448-449
+        if not self._ran:
+            return np.zeros((6, 1))
+        self._settle()
+        xn = self._step[1]
+        return xn[:, 0:6, None] if self._batched else xn[0, 0:6, None]
+
+    @property
+    def v_next(self):                                   # MPC.py:450
+        if not self._ran:
+            return np.zeros((6, 1))
+        self._settle()
+        xn = self._step[1]
+        return xn[:, 6:12, None] if self._batched else xn[0, 6:12, None]
+
+    @property
+    def q_w(self):                                      # MPC.py:58, 503-510
+        self._settle()
+        return self._qw[:, :, None].copy() if self._batched else self._qw[0].reshape(6, 1).copy()
+
+    @property
+    def x(self):                                        # MPC.py:52, 428
+        if not self._ran:
+            return np.zeros((24 * self.n_steps,))
+        x = self._fetch_full()
+        return x if self._batched else x[0]
+
+    @property
+    def x_robot(self):                                  # MPC.py:437-447
+        if not self._ran:
+            return np.zeros((12, self.n_steps))
+        x, N = self._fetch_full(), self.n_steps
+        xr = x[:, :12 * N].reshape(self._B, N, 12).transpose(0, 2, 1) + self._xb[:, :, 1:]
+        return xr if self._batched else xr[0]
+
+    @property
+    def status(self):
+        """Per-instance solver status of the last run (mpcqp.STATUS: 1 solved, 2 max_iter, 3 bad_input); warns once per
+        tick when a robot was not solved -- its forces are feasible (or zero) but not certified optimal."""
+        if not self._ran:
+            return None
+        if self._status is None:
+            self._status = self._engine.status()
+            bad = int((self._status != 1).sum())
+            if bad:
+                warnings.warn("%d of %d MPC instances were not solved (status %s)" % (
+                    bad, self._B, sorted(set(int(s) for s in self._status[self._status != 1]))), RuntimeWarning)
+        return self._status if self._batched else int(self._status[0])
+
+    def run_async(self, k, xref, fsteps, slot):
+        """Enqueue one tick and the copy of its forces into the engine's pinned slot; returns without waiting.
+        Used by MPC_Wrapper's asynchronous mode; the caller owns xref / fsteps until the result has been collected."""
+        xref, batched, xb, fb = self._check_inputs(xref, fsteps)
+        self._settle()
         self._batched = batched
         self._engine.run(float(k), np.array(xb), np.array(fb))      # private copies: the planner reuses its arrays
         self._engine.result_async(slot)
+        self._ran, self._pending = True, False          # the asynchronous protocol hands out forces only (MPC_Wrapper.py:116-141)
+        self._step = self._full = self._status = None
+        self._xb = xb
         return 0
 
     @property

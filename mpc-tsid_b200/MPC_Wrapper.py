@@ -42,10 +42,7 @@ class MPC_Wrapper:
             return self.mpc.f_applied                        # MPC_Wrapper.py:74
         self.not_first_iter = True                           # MPC_Wrapper.py:76-78
         first = np.array([0.0, 0.0, 8.0] * 4)
-        fa = np.asarray(self.mpc.f_applied)
-        batched = self.mpc._batched if self.multiprocessing else fa.ndim == 2
-        nb = self.mpc._engine.B if (self.multiprocessing and self.mpc._engine is not None) else (fa.shape[0] if fa.ndim == 2 else 1)
-        return np.tile(first, (nb, 1)) if batched else first
+        return np.tile(first, (self.mpc._B, 1)) if self.mpc._batched else first
 
     def run_MPC_synchronous(self, k, fstep_planner):
         self.mpc.run((k / self.k_mpc), fstep_planner.xref, fstep_planner.fsteps)    # MPC_Wrapper.py:103

@@ -76,7 +76,7 @@ cudaError_t configure_kernels() {
 #endif
 namespace mpcqp {
 #define RIC_DECL(N)                                                                                                   \
-    cudaError_t ric_configure_##N(int* ctas_per_sm);                                                                  \
+    cudaError_t ric_configure_##N(int* ctas_per_sm, int* ipm_ctas_per_sm);                                                                \
     void ric_launch_##N(int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,      \
                         const double* dx, const double* df, double* ws, int* ctr, int first, int off, int n_inst);     \
     void ipm_launch_##N(int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,      \
@@ -171,7 +171,7 @@ struct mpcqp_handle {
         use.enabled = closed_loop ? 1 : 0;
         if (admm && fallback_is_ipm()) {
             // the main stream's workspace: every active-set launch of this tick has been joined into `s` by now
-            launch_ipm(ric_capacity(p.n_steps), ric_max_ctas, s, dp, st, use, dx, df, d_ric_ws, first);
+            launch_ipm(ric_capacity(p.n_steps), ipm_max_ctas, s, dp, st, use, dx, df, d_ric_ws, first);
         } else if (!admm && (p.mode & MPCQP_MODE_STAGEWISE)) {
             // active-set stage on the stage-wise factorisation: half a warp per robot, persistent grid; every stream
             // that may run it concurrently has its own gain workspace
@@ -204,7 +204,7 @@ struct mpcqp_handle {
 
     double* d_ric_ws = nullptr;     // stage-wise path: per-stage gains of the resident robots, x3 (main + two side streams)
     size_t ric_ws_doubles = 0;
-    int ric_max_ctas = 0;
+    int ric_max_ctas = 0, ipm_max_ctas = 0;
 };
 
 extern "C" {
@@ -401,17 +401,20 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     h->ctr_base = h->st.fb_count; h->st.fb_next = nullptr;
     h->st.sig = (uint8_t*)(base + o_sig);
     CUH(cudaMemset(h->st.sig, SIG_FREE, (size_t)B * 4 * N));
-    int ric_per_sm = 0;
+    int ric_per_sm = 0, ipm_per_sm = 0;
     const int cap = ric_capacity(N);
     if (N == 16) CUH(configure_kernels<16>());
     else if (N == 32) CUH(configure_kernels<32>());
-    if (cap == 16) CUH(ric_configure_16(&ric_per_sm));
-    else if (cap == 32) CUH(ric_configure_32(&ric_per_sm));
-    else CUH(ric_configure_64(&ric_per_sm));
+    if (cap == 16) CUH(ric_configure_16(&ric_per_sm, &ipm_per_sm));
+    else if (cap == 32) CUH(ric_configure_32(&ric_per_sm, &ipm_per_sm));
+    else CUH(ric_configure_64(&ric_per_sm, &ipm_per_sm));
+    if (const char* e = std::getenv("MPCQP_RIC_CTAS")) { const int c = std::atoi(e); if (c > 0 && c < ric_per_sm) ric_per_sm = c; }      // tuning hook
     if (p->mode & MPCQP_MODE_STAGEWISE) {
-        if (ric_per_sm < 1) return bail(fail(MPCQP_ERR_CUDA, "the stage-wise kernel does not fit on this device"));
+        if (ric_per_sm < 1 || ipm_per_sm < 1) return bail(fail(MPCQP_ERR_CUDA, "the stage-wise kernel does not fit on this device"));
         h->ric_max_ctas = ric_per_sm * h->sms;
-        h->ric_ws_doubles = (size_t)h->ric_max_ctas * RIC_PER_CTA * (RIC_GAIN + 4 * RIC_ADM) * cap;
+        h->ipm_max_ctas = ipm_per_sm * h->sms;
+        const int slots = h->ric_max_ctas > h->ipm_max_ctas ? h->ric_max_ctas : h->ipm_max_ctas;
+        h->ric_ws_doubles = (size_t)slots * RIC_PER_CTA * (RIC_GAIN + 4 * RIC_ADM) * cap;
         CUH(cudaMalloc(&h->d_ric_ws, 3 * h->ric_ws_doubles * sizeof(double)));
     }
     if (!(p->mode & MPCQP_MODE_ACTIVE_SET)) {
@@ -537,6 +540,32 @@ int mpcqp_get_latest_result(mpcqp_handle* h, double* forces, int location) {
     if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
     CU(cudaSetDevice(h->p.device));
     int rc = fetch(h, forces, h->st.f0, (size_t)h->p.batch * 12 * sizeof(double), location);
+    if (rc) return rc;
+    if (location == MPCQP_HOST) CU(cudaStreamSynchronize(h->stream));
+    return MPCQP_OK;
+}
+
+// MPC.f_applied and the first predicted state in one call (one synchronisation): what a control loop needs per tick
+// (MPC_Wrapper.py:114 reads f_applied; MPC.py:448-450, 503-510 use q_next / v_next).  `dev1` is X_1 - xref_1 (12 per robot).
+int mpcqp_get_step_result(mpcqp_handle* h, double* forces, double* dev1, int location) {
+    if (!h || (!forces && !dev1)) return fail(MPCQP_ERR_INVALID, "null argument");
+    if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
+    if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "bad location");
+    CU(cudaSetDevice(h->p.device));
+    const size_t B = h->p.batch, row = 12 * sizeof(double);
+    const cudaMemcpyKind kind = location == MPCQP_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (forces) CU(cudaMemcpyAsync(forces, h->st.f0, B * row, kind, h->stream));
+    if (dev1) CU(cudaMemcpy2DAsync(dev1, row, h->st.xs, (size_t)h->p.n_steps * row, row, B, kind, h->stream));
+    if (location == MPCQP_HOST) CU(cudaStreamSynchronize(h->stream));
+    return MPCQP_OK;
+}
+
+// per-instance status only (4 B per robot)
+int mpcqp_get_status(mpcqp_handle* h, int32_t* status, int location) {
+    if (!h || !status) return fail(MPCQP_ERR_INVALID, "null argument");
+    if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
+    CU(cudaSetDevice(h->p.device));
+    int rc = fetch(h, status, h->st.status, (size_t)h->p.batch * 4, location);
     if (rc) return rc;
     if (location == MPCQP_HOST) CU(cudaStreamSynchronize(h->stream));
     return MPCQP_OK;

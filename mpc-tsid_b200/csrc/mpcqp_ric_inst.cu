@@ -13,7 +13,7 @@
 namespace mpcqp {
 
 // shared memory per CTA and resident CTAs per SM of this capacity's kernels
-cudaError_t RIC_CAT(ric_configure_, RIC_N)(int* ctas_per_sm) {
+cudaError_t RIC_CAT(ric_configure_, RIC_N)(int* ctas_per_sm, int* ipm_ctas_per_sm) {
     constexpr int N = RIC_N;
     cudaError_t e;
     const int smem = (int)(RIC_PER_CTA * sizeof(RicInst<N>));
@@ -29,7 +29,8 @@ cudaError_t RIC_CAT(ric_configure_, RIC_N)(int* ctas_per_sm) {
     if ((e = cudaFuncSetAttribute(ipm_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
     if ((e = cudaFuncSetAttribute(ipm_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ipm_kernel<N>, 32 * RIC_WARPS, smem))) return e;
-    *ctas_per_sm = a < b ? a : b;          // one workspace slot per resident half-warp serves both kernels
+    *ctas_per_sm = a;                      // the two kernels size their persistent grids separately; the workspace holds
+    *ipm_ctas_per_sm = b;                  // one slot per resident half-warp of the larger one
     return cudaSuccess;
 }
 

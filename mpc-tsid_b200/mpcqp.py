@@ -24,6 +24,7 @@ EXPORTS = (
     "mpcqp_measure_fp64_peak", "mpcqp_last_error", "mpcqp_version",
     "mpcqp_scenario_init", "mpcqp_scenario_run", "mpcqp_scenario_get", "mpcqp_get_inputs",
     "mpcqp_get_cost_components", "mpcqp_result_async", "mpcqp_result_ready", "mpcqp_result_wait",
+    "mpcqp_get_step_result", "mpcqp_get_status",
 )
 
 
@@ -84,6 +85,8 @@ def load():
     lib.mpcqp_result_async.argtypes = [vp, C.c_int]
     lib.mpcqp_result_ready.argtypes = [vp, C.c_int]
     lib.mpcqp_result_wait.argtypes = [vp, C.c_int, dp]
+    lib.mpcqp_get_step_result.argtypes = [vp, dp, dp, C.c_int]
+    lib.mpcqp_get_status.argtypes = [vp, i32p, C.c_int]
     lib.mpcqp_last_error.restype = C.c_char_p
     lib.mpcqp_version.restype = C.c_char_p
     _lib = lib
@@ -180,6 +183,18 @@ class Engine:
         out = np.empty((self.B, 12)) if out is None else out
         _check(self.lib.mpcqp_get_latest_result(self._h, _ptr(out), HOST))
         return out
+
+    def step_result(self, forces=None, dev1=None):
+        """Forces (B,12) and X_1 - xref_1 (B,12) of the last run in one call / one synchronisation."""
+        forces = np.empty((self.B, 12)) if forces is None else forces
+        dev1 = np.empty((self.B, 12)) if dev1 is None else dev1
+        _check(self.lib.mpcqp_get_step_result(self._h, _ptr(forces), _ptr(dev1), HOST))
+        return forces, dev1
+
+    def status(self):
+        st = np.empty(self.B, np.int32)
+        _check(self.lib.mpcqp_get_status(self._h, _ptr(st), HOST))
+        return st
 
     def forces_device(self, ptr):
         _check(self.lib.mpcqp_get_latest_result(self._h, C.c_void_p(int(ptr)), DEVICE))

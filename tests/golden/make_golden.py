@@ -45,7 +45,7 @@ def run_case(name, scen, ticks, first_state=None, prefix="solve"):
     if first_state is not None:
         scen.state[:] = first_state
     rec = {k: [] for k in ("xref", "fsteps", "k", "ML_data", "NK", "NK_inf", "x", "f_applied", "x_robot", "obj",
-                           "warm_x", "x_admm", "cert_prim", "cert_stat", "cert_comp", "cert_sign", "osqp_iter")}
+                           "warm_x", "x_admm", "cert_prim", "cert_stat", "cert_comp", "cert_sign", "osqp_iter", "q_w")}
     for t in range(ticks):
         xref, fsteps = scen.inputs()
         fs_in = fsteps[0].copy()
@@ -60,6 +60,7 @@ def run_case(name, scen, ticks, first_state=None, prefix="solve"):
         for key, ck in (("cert_prim", "prim"), ("cert_stat", "stat"), ("cert_comp", "comp"), ("cert_sign", "bad_sign")):
             rec[key].append(prob.last_cert[ck])
         rec["osqp_iter"].append(mpc.sol.info.iter)
+        rec["q_w"].append(mpc.q_w[:, 0].copy())                     # dead-reckoned world pose, MPC.py:503-510
         prob.calls.clear()
         scen.advance(mpc.x_robot[:, 0][None, :])
         print("  %s tick %2d  osqp-port iters %4d  |x_admm - x*| %.1e  stat %.1e  f0z %s" % (
@@ -77,7 +78,7 @@ def run_case(name, scen, ticks, first_state=None, prefix="solve"):
             out[key] = out[key][:2]
     np.savez_compressed(os.path.join(HERE, "%s_%s.npz" % (prefix, name)), **out)
     nact = int(((np.abs(out["x"][:, 12 * scen.N:].reshape(ticks, -1, 3)[:, :, 2] - 25.0) < 1e-9)).sum())
-    print("wrote solve_%s.npz  (%d ticks, %d foot-steps at fz_max)" % (name, ticks, nact))
+    print("wrote %s_%s.npz  (%d ticks, %d foot-steps at fz_max)" % (prefix, name, ticks, nact))
 
 
 def planner_fixture():

@@ -97,3 +97,43 @@ def test_logger_cost_components():
         c = m.x[b] * P * m.x[b]                             # diag(x) diag(P) x
         ref = np.array([c[i:12 * 16:12].sum() for i in range(12)] + [c[12 * 16:].sum()])
         np.testing.assert_allclose(cost[b], ref, rtol=1e-12, atol=1e-15)
+
+
+def test_world_pose_dead_reckoning_matches_reference():
+    """MPC.q_w (MPC.py:58, 503-510) against the reference's own value, tick by tick, on a turning trot (N = 24, a horizon that
+    fills no capacity class): single robot and the same robot twice in a batch.  Results are fetched lazily: q_w must come out
+    the same whether or not anything was read between the ticks."""
+    import MPC
+    g = np.load(os.path.join(G, "horizon_trot_N24.npz"))
+    dt, T_gait, n = float(g["dt"]), float(g["T_gait"]), g["x"].shape[1] // 24
+    solo, lazy, pair = MPC.MPC(dt, n, T_gait), MPC.MPC(dt, n, T_gait), MPC.MPC(dt, n, T_gait)
+    np.testing.assert_array_equal(solo.q_w[:, 0], [0.0, 0.0, 0.2027682, 0.0, 0.0, 0.0])
+    for t in range(len(g["k"])):
+        solo.run(g["k"][t], g["xref"][t], g["fsteps"][t])
+        lazy.run(g["k"][t], g["xref"][t], g["fsteps"][t])          # nothing is read from `lazy` until the end
+        pair.run(g["k"][t], np.stack([g["xref"][t]] * 2), np.stack([g["fsteps"][t]] * 2))
+        assert solo.q_w.shape == (6, 1) and pair.q_w.shape == (2, 6, 1)
+        np.testing.assert_allclose(solo.q_w[:, 0], g["q_w"][t], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(pair.q_w[1, :, 0], g["q_w"][t], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(solo.q_next[:, 0], g["x_robot"][t][0:6, 0], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(solo.v_next[:, 0], g["x_robot"][t][6:12, 0], rtol=0, atol=1e-6)
+        assert solo.status == 1 and (pair.status == 1).all()
+    np.testing.assert_allclose(lazy.q_w[:, 0], g["q_w"][-1], rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(lazy.q_w, solo.q_w)
+    # a different batch size is a new set of robots: world poses restart from the initial pose instead of breaking
+    pair.run(0, np.stack([g["xref"][0]] * 3), np.stack([g["fsteps"][0]] * 3))
+    assert pair.q_w.shape == (3, 6, 1) and pair.f_applied.shape == (3, 12)
+    np.testing.assert_allclose(pair.q_w[2, :, 0], g["q_w"][0], rtol=0, atol=1e-6)
+
+
+def test_status_is_reported_and_unsolved_robots_warn():
+    import MPC
+    g = np.load(os.path.join(G, "solve_trot_N64.npz"))
+    ok = MPC.MPC(0.02, 64, 0.32)
+    ok.run(0, g["xref"][0], g["fsteps"][0])
+    assert ok.status == 1
+    starved = MPC.MPC(0.02, 64, 0.32, max_sweeps=1, ipm_max_iter=3)
+    starved.run(0, g["xref"][0], g["fsteps"][0])
+    with pytest.warns(RuntimeWarning):
+        assert starved.status == 2
+    assert np.isfinite(starved.f_applied).all() and np.isfinite(starved.x).all()
