@@ -93,7 +93,7 @@ def reference_main(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD % 4096,
                    "sample": "one closed-loop trot robot per host core, one QP per tick (same generator, same tick shape)"},
-        "cpu_baseline": base,
+        "cpu_baseline": base, "cores": base["cores"],
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "osqp is not installable offline and /root/reference is absent on the GPU box: this is the oracle port in C "
                 "(oracle/mpc_osqp.c: restated MPC.py build + restated OSQP algorithm), a step = one tick of every host thread",
@@ -195,22 +195,32 @@ def flops_stagewise_fixed(N=N_STEPS):
     return feet * 40 + N * 30 + 12 * N * 4 + feet * 40   # decode, inertia blocks, outputs/objective, multipliers
 
 
-def sweep_main(args, torch, mpcqp, Scenario, rank, local_rank, world, dist, barrier, max_over_ranks, sum_over_ranks):
-    """BASELINE configs[4] shape: a closed-loop scenario sweep that never leaves the GPU.  Every tick plans footsteps and
-    the reference trajectory, builds and solves the QP and integrates the centroidal state, per robot, inside one kernel
-    (mpcqp_scenario_run).  `value` times K ticks back to back; `e2e` runs the same ticks one C-ABI call at a time and reads
-    every robot's state back to pinned host memory after each tick."""
-    B, K, W = args.batch, args.steps, max(args.warmup, 3) + max(args.settle, 0)
-    gaits = ["trot"] if args.workload == "sweep" else ["trot", "pace", "bound", "walk"]
-    sc = Scenario(B, gaits=gaits, seed=4242 + rank, noise_kind="hash")
-    eng = mpcqp.Engine(batch=B, device=local_rank, mode=args.mode)
+def profile_metric(path, name):
+    """A `name [unit]: value` line of a committed ncu summary (profiles/*.txt written by tools/summarize_ncu.py)."""
+    try:
+        for ln in open(os.path.join(ROOT, path)):
+            if ln.startswith(name + " ["):
+                unit = ln[ln.index("[") + 1:ln.index("]")]
+                v = float(ln.split(":")[-1].split("|")[0].strip().replace(",", ""))
+                return v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(unit, 1.0)
+    except (OSError, ValueError):
+        pass
+    return None
+
+
+def run_sweep(torch, mpcqp, Scenario, rank, local_rank, world, barrier, max_over_ranks, B, K, W, gaits, n_steps=N_STEPS, mode=None,
+              e2e=True, peak_tflops=None):
+    """Device-resident closed loop (BASELINE configs[2..4] shapes): every tick plans footsteps and the reference trajectory,
+    builds and solves the QP and integrates the centroidal state, per robot, inside the solve kernel (mpcqp_scenario_run).
+    `value` times K ticks back to back; `e2e` runs the same ticks one C-ABI call at a time and reads every robot's state back."""
+    sc = Scenario(B, n_steps=n_steps, gaits=gaits, seed=4242 + rank, noise_kind="hash")
+    kw = {} if mode is None else {"mode": mode}
+    eng = mpcqp.Engine(batch=B, n_steps=n_steps, device=local_rank, **kw)
     eng.scenario_init(sc)
     eng.scenario_run(W)
     eng.synchronize()
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     l0 = eng.launches
     e0.record(stream)
@@ -221,28 +231,49 @@ def sweep_main(args, torch, mpcqp, Scenario, rank, local_rank, world, dist, barr
     launches = eng.launches - l0
     total_ms = max_over_ranks(e0.elapsed_time(e1))
     info = eng.info(with_y=False)
-    unsolved = int((info["status"] != 1).sum())
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(K):
-        eng.scenario_run(1)
-        st = eng.scenario_state()
-    e2e_s = max_over_ranks(time.perf_counter() - w0)
+    out = {"value": world * B * K / (total_ms * 1e-3), "unit": UNIT, "ms_per_tick": total_ms / K, "ticks": K, "instances_per_gpu": B,
+           "n_steps": n_steps, "gaits": "/".join(gaits), "gpu_launches": int(launches),
+           "unsolved_instances_last_tick": int((info["status"] != 1).sum()),
+           "sweeps_per_solve_last_tick": float(info["sweeps"].mean()), "fallback_frac_last_tick": float((info["iters"] > 0).mean())}
+    if peak_tflops:
+        flop = float(info["sweeps"].mean()) * flops_stagewise_sweep(n_steps) + flops_stagewise_fixed(n_steps)
+        out["roofline_frac"] = flop * B * K / (total_ms * 1e-3) * 1e-12 / peak_tflops
+    if e2e:
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(K):
+            eng.scenario_run(1)
+            st = eng.scenario_state()
+        e2e_s = max_over_ranks(time.perf_counter() - w0)
+        out["e2e"] = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": B * 23 * 8,
+                      "ms_per_step": 1e3 * e2e_s / K,
+                      "what": "one mpcqp_scenario_run(1) + mpcqp_scenario_get per tick (states, frames, feet to the host)"}
+        out["state_checksum"] = float(np.abs(st["state"]).sum())
+    eng.close()
+    return out
+
+
+def sweep_main(args, torch, mpcqp, Scenario, rank, local_rank, world, dist, barrier, max_over_ranks, sum_over_ranks):
+    """`--workload sweep | mixed-sweep`: the closed-loop scenario sweep as the bench line (BASELINE configs[4] / configs[2] shape)."""
+    B, K, W = args.batch, args.steps, max(args.warmup, 3) + max(args.settle, 0)
+    gaits = ["trot"] if args.workload == "sweep" else ["trot", "pace", "bound", "walk"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    r = run_sweep(torch, mpcqp, Scenario, rank, local_rank, world, barrier, max_over_ranks, B, K, W, gaits, n_steps=args.n_steps, mode=args.mode)
     clocks = sampler.stop()
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC.replace("Solo trot", "closed-loop sweep"), "value": world * B * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC.replace("Solo trot", "closed-loop sweep"), "value": r["value"], "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_tick"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[4] shape: device-resident closed-loop sweep, %d robots per GPU, gaits %s, N=16: footstep "
+            "config": {"workload": "BASELINE.json configs[4] shape: device-resident closed-loop sweep, %d robots per GPU, gaits %s, N=%d: footstep "
                                    "planner + QP build + solve + centroidal state integration per tick inside the solve kernel, seeded "
-                                   "counter-based state noise" % (B, "/".join(gaits)),
+                                   "counter-based state noise" % (B, "/".join(gaits), args.n_steps),
                        "instances_per_gpu": B, "settle_ticks": max(args.settle, 0), "l2": "no inputs: the planner runs in the kernel; carried state %.0f MB" % (B * 6.5e-3)},
-            "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": B * 23 * 8,
-                    "ms_per_step": 1e3 * e2e_s / K, "what": "one mpcqp_scenario_run(1) + mpcqp_scenario_get per tick (states, frames, feet to the host)"},
-            "gpu_launches": int(launches), "clocks": clocks, "unsolved_instances_last_tick": unsolved,
-            "sweeps_per_solve_last_tick": float(info["sweeps"].mean()), "fallback_frac_last_tick": float((info["iters"] > 0).mean()),
-            "state_checksum": float(np.abs(st["state"]).sum())}))
+            "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": clocks,
+            "unsolved_instances_last_tick": r["unsolved_instances_last_tick"],
+            "sweeps_per_solve_last_tick": r["sweeps_per_solve_last_tick"], "fallback_frac_last_tick": r["fallback_frac_last_tick"],
+            "state_checksum": r["state_checksum"]}))
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -257,7 +288,12 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="robots per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bind", action="store_true", help="leave the process on whatever cores the launcher gave it")
-    ap.add_argument("--mode", type=int, default=7, help="solver stages (include/mpcqp.h MPCQP_MODE_*): 7 = stage-wise active set + ADMM fallback (default), 3 = dense")
+    ap.add_argument("--mode", type=int, default=13, help="solver stages (include/mpcqp.h MPCQP_MODE_*): 13 = stage-wise active set + interior-point "
+                    "fallback (default), 7 = stage-wise + dense ADMM fallback, 3 = dense")
+    ap.add_argument("--n-steps", type=int, default=N_STEPS, help="horizon of the sweep workloads (the trot headline is N = 16)")
+    ap.add_argument("--latency-ticks", type=int, default=200, help="ticks of the separate latency window (SURVEY 8d: p50 / p99 over >= 200 ticks)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short sub-runs of BASELINE configs[2], [3], [4]")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the MPC_Wrapper end-to-end leg")
     ap.add_argument("--cpu-ticks", type=int, default=100)
     ap.add_argument("--workload", default="trot", choices=["trot", "sweep", "mixed-sweep"],
                     help="trot = BASELINE configs[1] (the headline line, default); sweep / mixed-sweep = device-resident closed-loop "
@@ -310,7 +346,8 @@ def main():
 
     B, N, K = args.batch, N_STEPS, args.steps
     W = max(args.warmup, 3) + max(args.settle, 0)       # untimed ticks: settle + warm-up
-    T = W + K
+    KL = max(K, args.latency_ticks)                     # ticks of the latency window (its first K ticks are the throughput window's)
+    T = W + KL
     eng = mpcqp.Engine(batch=B, device=local_rank, mode=args.mode)
     peaks = mpcqp.measure_fp64_peak(local_rank)
 
@@ -327,7 +364,7 @@ def main():
         eng.run(t, hx[t], hf[t])
         x = eng.solution()
         info = eng.info(with_y=False)
-        if t >= W:
+        if W <= t < W + K:
             tot_sweeps += float(info["sweeps"].sum()); tot_iters += float(info["iters"].sum())
             tot_fb += float((info["iters"] > 0).sum())
         unsolved += int((info["status"] != 1).sum())
@@ -339,52 +376,97 @@ def main():
     brief = bool((hf[:, :, 7, 0] == 0.0).all())
     in_bytes = B * (12 * (N + 1) + (8 * 13 if brief else 260)) * esz
 
-    # ---- timed, device resident
+    # ---- timed, device resident: exactly K ticks between barrier + synchronise
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
-    eng.reset_warm_start()
-    for t in range(W):
-        eng.run_device(t, d_x[t].data_ptr(), d_f[t].data_ptr())
-    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    eng.synchronize()
+
+    def device_window(n_ticks):
+        eng.reset_warm_start()
+        for t in range(W):
+            eng.run_device(t, d_x[t].data_ptr(), d_f[t].data_ptr())
+        a = [torch.cuda.Event(enable_timing=True) for _ in range(n_ticks)]
+        b = [torch.cuda.Event(enable_timing=True) for _ in range(n_ticks)]
+        eng.synchronize()
+        barrier()
+        l0 = eng.launches
+        for i in range(n_ticks):
+            a[i].record(stream)
+            eng.run_device(W + i, d_x[W + i].data_ptr(), d_f[W + i].data_ptr())
+            b[i].record(stream)
+        eng.synchronize()
+        barrier()
+        return a[0].elapsed_time(b[n_ticks - 1]), np.array([x.elapsed_time(y) for x, y in zip(a, b)]), eng.launches - l0
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    l0 = eng.launches
-    for i in range(K):
-        e0[i].record(stream)
-        eng.run_device(W + i, d_x[W + i].data_ptr(), d_f[W + i].data_ptr())
-        e1[i].record(stream)
-    eng.synchronize()
-    barrier()
-    launches = eng.launches - l0
-    total_ms = e0[0].elapsed_time(e1[K - 1])
-    per_step = np.array([a.elapsed_time(b) for a, b in zip(e0, e1)])
+    time.sleep(0.6)                                     # let nvidia-smi finish starting up (it takes driver locks while it does)
+    total_ms, per_step, launches = device_window(K)
     total_ms = max_over_ranks(total_ms)
     value = world * B * K / (total_ms * 1e-3)
+    lat_ms, lat_steps, _ = device_window(KL) if KL > K else (total_ms, per_step, 0)
 
     # ---- timed, end to end through the host API (pinned host in, forces out)
     h_out = torch.empty((B, 12), dtype=torch.float64, pin_memory=True)
     out_np = h_out.numpy()
-    eng.reset_warm_start()
-    for t in range(W):
-        eng.run(t, hx[t], hf[t])
-        eng.forces(out=out_np)
-    barrier()
-    lat = []
-    w0 = time.perf_counter()
-    for i in range(K):
-        s0 = time.perf_counter()
-        eng.run(W + i, hx[W + i], hf[W + i])
-        eng.forces(out=out_np)                      # D2H of the step's result, synchronises
-        lat.append(time.perf_counter() - s0)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    barrier()
-    clocks = sampler.stop()
+
+    def host_window(n_ticks):
+        eng.reset_warm_start()
+        for t in range(W):
+            eng.run(t, hx[t], hf[t])
+            eng.forces(out=out_np)
+        barrier()
+        lat = []
+        w0 = time.perf_counter()
+        for i in range(n_ticks):
+            s0 = time.perf_counter()
+            eng.run(W + i, hx[W + i], hf[W + i])
+            eng.forces(out=out_np)                      # D2H of the step's result, synchronises
+            lat.append(time.perf_counter() - s0)
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - w0
+        barrier()
+        return dt_s, np.array(lat)
+
+    e2e_s, lat = host_window(K)
     e2e_s = max_over_ranks(e2e_s)
     e2e_value = world * B * K / e2e_s
     checksum = float(np.abs(out_np).sum())
+    forces_k = out_np.copy()
+    e2e_lat_s, e2e_lat = host_window(KL) if KL > K else (e2e_s, lat)
+
+    # ---- the same K ticks through the reference-facing classes: MPC_Wrapper.solve(k, planner) + get_latest_result()
+    #      (MPC_Wrapper.py:39-78, processing.py:142-145), host arrays in, forces out
+    dropin = None
+    if not args.no_dropin:
+        import MPC_Wrapper
+
+        class _Planner:                                 # what processing.process_mpc hands over: .xref and .fsteps
+            pass
+
+        wr = MPC_Wrapper.MPC_Wrapper(0.02, N, 20, 0.32, multiprocessing=False, device=local_rank, mode=args.mode)
+        pl = _Planner()
+        for t in range(W):
+            pl.xref, pl.fsteps = hx[t], hf[t]
+            wr.solve(20 * t, pl)
+            f_d = wr.get_latest_result()
+        barrier()
+        dl = []
+        w0 = time.perf_counter()
+        for i in range(K):
+            s0 = time.perf_counter()
+            pl.xref, pl.fsteps = hx[W + i], hf[W + i]
+            wr.solve(20 * (W + i), pl)
+            f_d = wr.get_latest_result()
+            dl.append(time.perf_counter() - s0)
+        d_s = max_over_ranks(time.perf_counter() - w0)
+        barrier()
+        dropin = {"value": world * B * K / d_s, "unit": UNIT, "ms_per_step": 1e3 * d_s / K,
+                  "latency_ms_p50": 1e3 * float(np.percentile(dl, 50)), "latency_ms_p99": 1e3 * float(np.percentile(dl, 99)),
+                  "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 2 * B * 12 * esz,
+                  "forces_match_engine_path": bool(np.abs(np.asarray(f_d) - forces_k).max() <= 1e-9),
+                  "what": "MPC_Wrapper.solve(k, planner) + get_latest_result() per tick (the drop-in classes of mpc-tsid_b200/), "
+                          "forces + first predicted state read back"}
+        wr.mpc._engine.close()
+    clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel.  Neither HBM nor tensor bound: the stage-wise kernel is a chain of
     #      6x6 FP64 factorisations per robot, bounded by FP64-FMA-pipe latency/throughput; the denominator is the FP64
@@ -392,23 +474,28 @@ def main():
     stagewise = bool(eng.params.mode & 4)
     if stagewise:
         flop = (tot_sweeps * flops_stagewise_sweep() + B * K * flops_stagewise_fixed()
-                + flops_per_tick(0, tot_iters, tot_fb) - flops_per_tick(0, 0, 0))
+                + tot_iters * flops_stagewise_sweep())            # an interior-point iteration is one stage-wise factorisation + solve
         peak, peak_name = peaks["dfma_tflops"], "FP64 FMA"
-        kernel = "riccati_kernel<16> (+ dense ADMM fallback kernel for the robots the sweeps give up on)"
-        traffic = 29.09e6 * B / 4096.0
-        traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum of one riccati_kernel<16> launch at 4096 robots, ncu --set full "
-                       "(profiles/r01_riccati_kernel_ncu_summary.txt), scaled to this batch")
+        kernel = "riccati_kernel<16, true> (+ ipm_kernel<16> for the robots the sweeps give up on)"
+        prof = "profiles/r02_riccati_kernel_ncu_summary.txt"
+        if not os.path.exists(os.path.join(ROOT, prof)):
+            prof = "profiles/r01_riccati_kernel_ncu_summary.txt"
         model = "engine's own count, DESIGN.md section 5: sweeps*%.0f + %.0f per solve (+ fallback work)" % (
             flops_stagewise_sweep(), flops_stagewise_fixed())
     else:
         flop = flops_per_tick(tot_sweeps, tot_iters, tot_fb)        # this rank, K ticks
         peak, peak_name = peaks["dmma_tflops"], "FP64 tensor (DMMA m8n8k4)"
         kernel = "solve_kernel<16,false> (+ ADMM fallback kernel)"
-        traffic = 22.49e6 * B / 4096.0
-        traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel<16,false> launch at 4096 instances, ncu --set full "
-                       "(profiles/r01_solve_kernel_ncu_summary.txt), scaled to this batch")
+        prof = "profiles/r01_solve_kernel_ncu_summary.txt"
         model = "engine's own count, DESIGN.md section 5: sweeps*%.0f + admm_iters*%.0f per solve" % (
             flops_per_tick(1, 0, 0) - flops_per_tick(0, 0, 0), flops_per_tick(0, 1, 0) - flops_per_tick(0, 0, 0))
+    # DRAM traffic of the dominant kernel: read from the committed ncu summary of one 4096-robot launch (not measured in this run:
+    # bench.py never runs under a profiler); null when the batch differs from the profiled one
+    rd, wrb = profile_metric(prof, "dram__bytes_read.sum"), profile_metric(prof, "dram__bytes_write.sum")
+    traffic = (rd + wrb) if (rd is not None and wrb is not None and B == 4096) else None
+    traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at 4096 robots, parsed at run time from "
+                   "the committed ncu --set full summary %s" % prof)
+    pipe_busy = profile_metric(prof, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
     flop_all = sum_over_ranks(flop)
     achieved = flop_all / world / (total_ms * 1e-3) * 1e-12          # per GPU
     hbm_alg = 21216.0                                               # B per solve, SURVEY.md 8(d)
@@ -423,17 +510,38 @@ def main():
         "bound": "fp64", "bound_note": "neither hbm nor tensor: FP64 FMA pipe latency/throughput (SURVEY.md 8d)", "pipe": peak_name,
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
         "traffic": traffic, "kernel": kernel, "traffic_source": traffic_src,
+        "frac_note": "frac counts USEFUL FP64 work (one copy of every 6x6 factorisation per robot); the kernel factors redundantly in "
+                     "every lane, so the FP64 pipe is busier than that: executed_fp64_pipe_busy_frac (ncu, same committed profile)",
+        "executed_fp64_pipe_busy_frac": None if pipe_busy is None else pipe_busy / 100.0,
         "peak_source": "issue loop of that instruction measured on this GPU in this run (mpcqp_measure_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 entry",
         "flop_model": model,
         "mflop_per_solve": flop / (B * K) * 1e-6, "canonical_mflop_per_solve_survey_8d_it60": 4.31,
         "canonical_equivalent_tflops": canon,
-        "sweeps_per_solve": tot_sweeps / (B * K), "admm_iters_per_solve": tot_iters / (B * K),
+        "sweeps_per_solve": tot_sweeps / (B * K), "fallback_iters_per_solve": tot_iters / (B * K),
         "fallback_frac": tot_fb / (B * K),
         "dfma_peak_tflops": peaks["dfma_tflops"], "dmma_peak_tflops": peaks["dmma_tflops"],
         "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                 "bytes_per_solve": hbm_alg, "peak_source": hbm_src},
     }
+
+    eng.close()
+    del d_x, d_f
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, short device-resident sub-runs (planner + QP + integration per tick on the GPU)
+    other = None
+    if not args.no_other_configs:
+        sw = lambda **kw: run_sweep(torch, mpcqp, Scenario, rank, local_rank, world, barrier, max_over_ranks, W=25, e2e=False,
+                                    peak_tflops=peaks["dfma_tflops"], **kw)
+        other = {
+            "configs[2] mixed gaits N=16, 65536 robots per GPU": sw(B=65536, K=20, gaits=["trot", "pace", "bound", "walk"]),
+            "configs[3] long horizon N=32, 4096 trot robots per GPU": sw(B=4096, K=20, gaits=["trot"], n_steps=32),
+            "configs[3] long horizon N=64, 2048 trot robots per GPU": sw(B=2048, K=20, gaits=["trot"], n_steps=64),
+            "configs[4] closed-loop sweep N=16, 131072 trot robots per GPU": sw(B=131072, K=20, gaits=["trot"]),
+            "what": "mpcqp_scenario_run: footstep planner + QP build + solve + centroidal state integration per tick inside the solve "
+                    "kernel, 25 untimed closed-loop ticks first; value = robots x ticks / device time (max over ranks), whole job",
+        }
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -450,18 +558,29 @@ def main():
                        "cpu_affinity": affinity,
                        "settle_ticks": max(args.settle, 0),
                        "tick_window": "ticks %d..%d of the closed loop are timed (steady operation; the first %d ticks after "
-                                      "release from rest run untimed before the %d warm-up ticks)" % (W, T - 1, max(args.settle, 0), max(args.warmup, 3)),
+                                      "release from rest run untimed before the %d warm-up ticks)" % (W, W + K - 1, max(args.settle, 0), max(args.warmup, 3)),
                        "l2": "each timed tick reads its own input block (%d x %.1f MB > 126 MB L2 over the run); the "
                              "carried warm-start state (%.1f MB) is hot by design" % (K, B * (12 * (N + 1) + 260) * esz / 1e6, B * 4.2e-3)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * 12 * esz,
                     "host_buffer_bytes_per_step": B * (12 * (N + 1) + 260) * esz,
                     "ms_per_step": 1e3 * e2e_s / K, "latency_ms_p50": 1e3 * float(np.percentile(lat, 50)),
-                    "latency_ms_p99": 1e3 * float(np.percentile(lat, 99))},
+                    "latency_ms_p99": 1e3 * float(np.percentile(lat, 99)),
+                    "what": "mpcqp_run(host xref, host fsteps) + mpcqp_get_latest_result(host forces) per tick through the C ABI"},
+            "e2e_dropin": dropin,
             "gpu_launches": int(launches),
             "latency_ms": {"p50": float(np.percentile(per_step, 50)), "p99": float(np.percentile(per_step, 99)),
-                           "what": "device time of one batch tick (CUDA events on the engine stream)"},
+                           "what": "device time of one batch tick (CUDA events on the engine stream), the K timed ticks"},
+            "latency_window": {"ticks": int(KL), "after_untimed_ticks": int(W),
+                               "device_ms_p50": float(np.percentile(lat_steps, 50)), "device_ms_p99": float(np.percentile(lat_steps, 99)),
+                               "device_ms_max": float(lat_steps.max()),
+                               "e2e_ms_p50": 1e3 * float(np.percentile(e2e_lat, 50)), "e2e_ms_p99": 1e3 * float(np.percentile(e2e_lat, 99)),
+                               "e2e_ms_max": 1e3 * float(e2e_lat.max()),
+                               "what": "SURVEY.md 8d: one batch tick from enqueue to forces readable, p50 / p99 over this many consecutive "
+                                       "closed-loop ticks (a separate pass over the same inputs; its first %d ticks are the timed ones)" % K},
             "roofline": roofline,
+            "other_configs": other,
             "cpu_baseline": cpu,
+            "reference_arm_cores": None if cpu is None else cpu["cores"],
             "clocks": clocks,
             "unsolved_instances": unsolved, "forces_checksum": checksum,
         }

@@ -106,9 +106,13 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
 int mpcqp_get_latest_result(mpcqp_handle* h, double* forces, int location);
 
 /* What a control loop reads every tick, in one call and one synchronisation: forces (B x 12, as above; may be NULL) and
- * dev1 (B x 12; may be NULL) = X_1 - xref_1, the first predicted state minus its reference, from which MPC.q_next / v_next
- * (MPC.py:448-450) and the dead-reckoned MPC.q_w (MPC.py:503-510) follow as dev1 + xref[:, 1]. */
-int mpcqp_get_step_result(mpcqp_handle* h, double* forces, double* dev1, int location);
+ * next_state (B x 12; may be NULL) = x_robot[:, 0], the first predicted state: MPC.q_next = next_state[0:6], MPC.v_next =
+ * next_state[6:12] (MPC.py:448-450), from which the dead-reckoned MPC.q_w (MPC.py:503-510) follows. */
+int mpcqp_get_step_result(mpcqp_handle* h, double* forces, double* next_state, int location);
+
+/* MPC.q_w (MPC.py:58, 503-510), B x 6: the world pose every run dead-reckons from MPC.q_next on the device (starts at
+ * [0, 0, 0.2027682, 0, 0, 0], MPC.py:55-58).  set == 0 reads it, set != 0 overwrites it (e.g. to re-anchor on an estimator). */
+int mpcqp_world_pose(mpcqp_handle* h, double* qw, int set, int location);
 
 /* status[B] alone (MPCQP_STATUS_*): the cheap check the reference never makes (MPC.py:427 ignores sol.info.status). */
 int mpcqp_get_status(mpcqp_handle* h, int32_t* status, int location);
@@ -133,6 +137,10 @@ int mpcqp_reset_warm_start(mpcqp_handle* h);
 int mpcqp_synchronize(mpcqp_handle* h);
 /* the CUDA stream (cudaStream_t) work is enqueued on; owned by the handle */
 void* mpcqp_stream(mpcqp_handle* h);
+/* Page-locked host memory for arrays that cross the bus every tick (xref, fsteps, forces): copies to / from pageable
+ * memory are staged by the driver and cost about a fifth of a 4096-robot tick.  NULL on failure. */
+void* mpcqp_host_alloc(size_t bytes);
+int mpcqp_host_free(void* p);
 /* kernels launched by this handle since creation (for bench.py's gpu_launches claim) */
 int64_t mpcqp_launch_count(mpcqp_handle* h);
 

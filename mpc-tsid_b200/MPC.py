@@ -21,6 +21,8 @@ import mpcqp
 
 
 class MPC:
+    _SLOTS = 8                                          # page-locked result slots per engine (batched results are views of them)
+
     def __init__(self, dt, n_steps, T_gait, batch=None, device=0, **solver_options):
         self.dt = dt                                    # MPC.py:25
         self.n_steps = int(n_steps)                     # MPC.py:42
@@ -43,8 +45,6 @@ class MPC:
         self._batched = False
         self._B = 1
         self._ran = False
-        self._pending = False                           # the last tick's dead-reckoning step has not been applied yet
-        self._qw = self._qw0[None, :].copy()            # (B, 6) dead-reckoned world poses
         self._step = None                               # (f_applied, x_next) of the last tick once fetched
         self._full = None                               # full solution of the last tick once fetched
         self._status = None
@@ -68,10 +68,12 @@ class MPC:
             self._engine.close()
         self._engine = mpcqp.Engine(batch=batch, n_steps=self.n_steps, device=self._device, dt=float(self.dt),
                                     T_gait=float(self.T_gait), **self._opts)
-        if self._qw.shape[0] != batch:
-            # a new batch size is a new set of robots: they start from the initial world pose (MPC.py:58)
-            self._qw = np.tile(self._qw0, (batch, 1))
+        # a new batch size is a new set of robots: they start from the initial world pose (MPC.py:58)
+        if not np.array_equal(self._qw0, [0.0, 0.0, 0.2027682, 0.0, 0.0, 0.0]):
+            self._engine.world_pose(np.tile(self._qw0, (batch, 1)))
         self._B = batch
+        self._slots = [(self._engine.pinned((batch, 12)), self._engine.pinned((batch, 12))) for _ in range(self._SLOTS)]
+        self._tick = 0
         self._ran = False
         self._step = self._full = self._status = None
 
@@ -91,10 +93,9 @@ class MPC:
         if xref is None or fsteps is None:
             raise TypeError("run(k, xref, fsteps): xref and fsteps are required")
         xref, batched, xb, fb = self._check_inputs(xref, fsteps)
-        self._settle()                                  # the previous tick's step of the dead reckoning, if nobody asked for it
         self._batched = batched
         self._engine.run(float(k), xb, fb)              # asynchronous: build + solve + extract on the device
-        self._ran, self._pending = True, True
+        self._ran = True
         self._step = self._full = self._status = None
         self._xb = xb
         self.xref = xref                                # MPC.py:486 (aliased there too)
@@ -106,20 +107,17 @@ class MPC:
 
     # ---- results, fetched when read ---------------------------------------------------------------------------
     def _settle(self):
-        """Forces + first predicted state of the last tick (one small copy), and this tick's step of MPC.py:503-510."""
+        """Forces + first predicted state of the last tick: one small copy into a page-locked slot.  (The dead reckoning of
+        MPC.py:503-510 runs on the device at the end of every solve; q_w is fetched when it is read.)"""
         if not self._ran or self._step is not None:
             return
-        f0, dev1 = self._engine.step_result()
-        xn = dev1 + self._xb[:, :, 1]                   # MPC.py:437: x_robot[:, 0]
+        # result slots are used in rotation: a batched result is a VIEW of its slot and stays valid for _SLOTS ticks
+        slot = self._slots[self._tick % len(self._slots)]
+        f0, xn = self._engine.step_result(slot[0], slot[1])
+        if not self._batched:
+            f0, xn = f0.copy(), xn.copy()               # one robot: hand out private arrays like the reference does
         self._step = (f0, xn)
-        if self._pending:
-            c, s = np.cos(self._qw[:, 5]), np.sin(self._qw[:, 5])
-            self._qw[:, 0] += c * xn[:, 0] - s * xn[:, 1]
-            self._qw[:, 1] += s * xn[:, 0] + c * xn[:, 1]
-            self._qw[:, 2] = xn[:, 2]
-            self._qw[:, 3:5] = xn[:, 3:5]
-            self._qw[:, 5] += xn[:, 5]
-            self._pending = False
+        self._tick += 1
 
     def _fetch_full(self):
         if self._full is None and self._ran:
@@ -152,8 +150,19 @@ class MPC:
 
     @property
     def q_w(self):                                      # MPC.py:58, 503-510
-        self._settle()
-        return self._qw[:, :, None].copy() if self._batched else self._qw[0].reshape(6, 1).copy()
+        if self._engine is None:
+            return self._qw0.reshape(6, 1).copy()
+        qw = self._engine.world_pose()
+        return qw[:, :, None] if self._batched else qw[0].reshape(6, 1)
+
+    @q_w.setter
+    def q_w(self, value):
+        """Re-anchor the dead reckoning (the reference's attribute is plain data; (6, 1) or (B, 6, 1))."""
+        v = np.asarray(value, dtype=np.float64)
+        if self._engine is None:
+            self._qw0 = v.reshape(-1)[:6].copy()
+        else:
+            self._engine.world_pose(np.broadcast_to(v.reshape(-1, 6), (self._B, 6)))
 
     @property
     def x(self):                                        # MPC.py:52, 428
@@ -192,7 +201,7 @@ class MPC:
         self._batched = batched
         self._engine.run(float(k), np.array(xb), np.array(fb))      # private copies: the planner reuses its arrays
         self._engine.result_async(slot)
-        self._ran, self._pending = True, False          # the asynchronous protocol hands out forces only (MPC_Wrapper.py:116-141)
+        self._ran = True
         self._step = self._full = self._status = None
         self._xb = xb
         return 0

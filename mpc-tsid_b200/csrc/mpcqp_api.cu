@@ -385,7 +385,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_f = take((size_t)B * 12 * N * 8), o_y = take((size_t)B * 20 * N * 8), o_xs = take((size_t)B * 12 * N * 8);
-    const size_t o_f0 = take((size_t)B * 12 * 8), o_obj = take((size_t)B * 8);
+    const size_t o_f0 = take((size_t)B * 12 * 8), o_x1 = take((size_t)B * 12 * 8), o_qw = take((size_t)B * 6 * 8), o_obj = take((size_t)B * 8);
     const size_t o_status = take((size_t)B * 4), o_sweeps = take((size_t)B * 4), o_iters = take((size_t)B * 4);
     const size_t o_contact = take((size_t)B * h->cw * 4), o_active = take((size_t)B * h->aw * 4);
     const size_t o_list = take((size_t)B * 4), o_count = take(256), o_sig = take((size_t)B * 4 * N);
@@ -394,7 +394,13 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     CUH(cudaMemset(h->d_block, 0, off));
     char* base = (char*)h->d_block;
     h->st.f = (double*)(base + o_f); h->st.y = (double*)(base + o_y); h->st.xs = (double*)(base + o_xs);
-    h->st.f0 = (double*)(base + o_f0); h->st.obj = (double*)(base + o_obj);
+    h->st.f0 = (double*)(base + o_f0); h->st.x1 = (double*)(base + o_x1); h->st.qw = (double*)(base + o_qw); h->st.obj = (double*)(base + o_obj);
+    {
+        // MPC.py:55-58: every robot's world pose starts at [0, 0, h_ref, 0, 0, 0]
+        std::vector<double> qw((size_t)B * 6, 0.0);
+        for (int b = 0; b < B; ++b) qw[(size_t)b * 6 + 2] = 0.2027682;
+        CUH(cudaMemcpy(h->st.qw, qw.data(), qw.size() * 8, cudaMemcpyHostToDevice));
+    }
     h->st.status = (int32_t*)(base + o_status); h->st.sweeps = (int32_t*)(base + o_sweeps); h->st.iters = (int32_t*)(base + o_iters);
     h->st.contact = (uint32_t*)(base + o_contact); h->st.active = (uint32_t*)(base + o_active);
     h->st.fb_list = (int32_t*)(base + o_list); h->st.fb_count = (int32_t*)(base + o_count);
@@ -546,8 +552,9 @@ int mpcqp_get_latest_result(mpcqp_handle* h, double* forces, int location) {
 }
 
 // MPC.f_applied and the first predicted state in one call (one synchronisation): what a control loop needs per tick
-// (MPC_Wrapper.py:114 reads f_applied; MPC.py:448-450, 503-510 use q_next / v_next).  `dev1` is X_1 - xref_1 (12 per robot).
-int mpcqp_get_step_result(mpcqp_handle* h, double* forces, double* dev1, int location) {
+// (MPC_Wrapper.py:114 reads f_applied; MPC.py:448-450, 503-510 use q_next / v_next).  `next_state` is x_robot[:, 0] (12 per robot).
+int mpcqp_get_step_result(mpcqp_handle* h, double* forces, double* next_state, int location) {
+    double* dev1 = next_state;
     if (!h || (!forces && !dev1)) return fail(MPCQP_ERR_INVALID, "null argument");
     if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
     if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "bad location");
@@ -555,7 +562,19 @@ int mpcqp_get_step_result(mpcqp_handle* h, double* forces, double* dev1, int loc
     const size_t B = h->p.batch, row = 12 * sizeof(double);
     const cudaMemcpyKind kind = location == MPCQP_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     if (forces) CU(cudaMemcpyAsync(forces, h->st.f0, B * row, kind, h->stream));
-    if (dev1) CU(cudaMemcpy2DAsync(dev1, row, h->st.xs, (size_t)h->p.n_steps * row, row, B, kind, h->stream));
+    if (dev1) CU(cudaMemcpyAsync(dev1, h->st.x1, B * row, kind, h->stream));
+    if (location == MPCQP_HOST) CU(cudaStreamSynchronize(h->stream));
+    return MPCQP_OK;
+}
+
+// MPC.q_w (MPC.py:58, 503-510): the dead-reckoned world pose of every robot, B x 6; `set` != 0 writes it instead
+int mpcqp_world_pose(mpcqp_handle* h, double* qw, int set, int location) {
+    if (!h || !qw) return fail(MPCQP_ERR_INVALID, "null argument");
+    if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "bad location");
+    CU(cudaSetDevice(h->p.device));
+    const size_t bytes = (size_t)h->p.batch * 6 * sizeof(double);
+    if (set) CU(cudaMemcpyAsync(h->st.qw, qw, bytes, location == MPCQP_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+    else CU(cudaMemcpyAsync(qw, h->st.qw, bytes, location == MPCQP_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
     if (location == MPCQP_HOST) CU(cudaStreamSynchronize(h->stream));
     return MPCQP_OK;
 }
@@ -629,6 +648,22 @@ int mpcqp_synchronize(mpcqp_handle* h) {
 }
 
 void* mpcqp_stream(mpcqp_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+// page-locked host memory for the caller's input / output arrays (copies from pageable memory are staged by the driver
+// and cost ~20 % of a 4096-robot tick)
+void* mpcqp_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        fail(MPCQP_ERR_CUDA, "cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+int mpcqp_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return MPCQP_OK;
+}
 int64_t mpcqp_launch_count(mpcqp_handle* h) { return h ? h->launches : 0; }
 
 int mpcqp_export_build(mpcqp_handle* h, double k, const double* xref, const double* fsteps, int location,

@@ -52,6 +52,8 @@ struct DevState {
     uint8_t* sig;       // B x N*4    active-set signature per foot-step
     double* xs;         // B x N*12   state half of MPC.x (X - xref)
     double* f0;         // B x 12     f_applied
+    double* x1;         // B x 12     X_1 = x_robot[:, 0], the first predicted state (MPC.q_next, MPC.v_next), packed
+    double* qw;         // B x 6      dead-reckoned world pose MPC.q_w (MPC.py:58, 503-510), carried across ticks
     double* obj;        // B
     int32_t* status;    // B
     int32_t* sweeps;    // B
@@ -62,6 +64,16 @@ struct DevState {
     int32_t* fb_count;  // its length
     int32_t* fb_next;   // the next tick's copy of {fb_count, three work counters}: zeroed by this tick's stage-wise launch on the main stream (null: not this launch)
 };
+
+// MPC.py:503-510: the world pose advances by the first predicted pose, rotated by the current world yaw.  One thread per robot.
+__device__ __forceinline__ void world_pose_step(double* __restrict__ qw, const double* xn) {
+    double s, c;
+    sincos(qw[5], &s, &c);
+    qw[0] += c * xn[0] - s * xn[1];
+    qw[1] += s * xn[0] + c * xn[1];
+    qw[2] = xn[2]; qw[3] = xn[3]; qw[4] = xn[4];
+    qw[5] += xn[5];
+}
 
 __host__ __device__ constexpr int tile_index(int I, int J) { return I * (I + 1) / 2 + J; }
 __host__ __device__ constexpr int elem_off(int r, int c) { return (c >> 2) * 32 + r * 4 + (c & 3); }

@@ -310,6 +310,7 @@ __device__ __forceinline__ void finish(const DevParams& P, const DevScenario& S,
             const double ep = p - sm.xr[c * (N + 1) + s + 1], ev = v - sm.xr[(6 + c) * (N + 1) + s + 1];
             xs[12 * s + c] = ep;
             xs[12 * s + 6 + c] = ev;
+            if (s == 0) { st.x1[(size_t)inst * 12 + c] = p; st.x1[(size_t)inst * 12 + 6 + c] = v; }
             part += 0.5 * (P.wp[c] * ep * ep + P.wv[c] * ev * ev);
         }
     }
@@ -358,6 +359,7 @@ __device__ __forceinline__ void finish(const DevParams& P, const DevScenario& S,
         st.status[inst] = status;
         st.sweeps[inst] = sweeps;
         st.iters[inst] = iters;
+        if (status != 3) world_pose_step(st.qw + (size_t)inst * 6, sm.sc.xnext);
         // device-resident closed loop: the robot moves to the state the MPC predicted for the next tick
         if (S.enabled && status != 3) scenario_advance(S, inst, sm.sc.xnext);
     }

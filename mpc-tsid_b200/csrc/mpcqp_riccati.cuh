@@ -857,6 +857,7 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
         const double e = sm.xst[i] - sm.xr[c * ld + s + 1];
         const double ee = isfinite(e) ? e : 0.0;                                             // malformed input: never NaN out
         if (commit) xs[i] = ee;                                                              // MPC.x[:12N] (MPC.py:428)
+        if (commit && i < 12) st.x1[(size_t)inst * 12 + i] = isfinite(e) ? sm.xst[i] : 0.0;              // MPC.q_next / v_next (MPC.py:448-450)
         part = fma(0.5 * (c < 6 ? P.wp[c] : P.wv[c - 6]) * ee, ee, part);
     }
     if (hl < 12) sm.xnext[hl] = sm.xst[hl];                                                  // MPC.q_next / v_next (MPC.py:448-450)
@@ -924,6 +925,7 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
         st.status[inst] = status;
         st.sweeps[inst] = sweeps;
         st.iters[inst] = iters;
+        if (status != 3) world_pose_step(st.qw + (size_t)inst * 6, sm.xnext);
         if (SC.enabled && status != 3) scenario_advance(SC, inst, sm.xnext);
     }
 }

@@ -24,7 +24,8 @@ EXPORTS = (
     "mpcqp_measure_fp64_peak", "mpcqp_last_error", "mpcqp_version",
     "mpcqp_scenario_init", "mpcqp_scenario_run", "mpcqp_scenario_get", "mpcqp_get_inputs",
     "mpcqp_get_cost_components", "mpcqp_result_async", "mpcqp_result_ready", "mpcqp_result_wait",
-    "mpcqp_get_step_result", "mpcqp_get_status",
+    "mpcqp_get_step_result", "mpcqp_get_status", "mpcqp_host_alloc", "mpcqp_host_free",
+    "mpcqp_world_pose",
 )
 
 
@@ -87,6 +88,10 @@ def load():
     lib.mpcqp_result_wait.argtypes = [vp, C.c_int, dp]
     lib.mpcqp_get_step_result.argtypes = [vp, dp, dp, C.c_int]
     lib.mpcqp_get_status.argtypes = [vp, i32p, C.c_int]
+    lib.mpcqp_world_pose.argtypes = [vp, dp, C.c_int, C.c_int]
+    lib.mpcqp_host_alloc.argtypes = [C.c_size_t]
+    lib.mpcqp_host_alloc.restype = C.c_void_p
+    lib.mpcqp_host_free.argtypes = [vp]
     lib.mpcqp_last_error.restype = C.c_char_p
     lib.mpcqp_version.restype = C.c_char_p
     _lib = lib
@@ -161,8 +166,23 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None):
+            self.lib.mpcqp_synchronize(self._h)
+            for ptr in getattr(self, "_pinned", []):
+                self.lib.mpcqp_host_free(ptr)
+            self._pinned = []
             self.lib.mpcqp_destroy(self._h)
             self._h = None
+
+    def pinned(self, shape, dtype=np.float64):
+        """A page-locked numpy array owned by this engine (freed by close()): what xref / fsteps / forces should live in."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = self.lib.mpcqp_host_alloc(n)
+        if not ptr:
+            raise MpcqpError("mpcqp_host_alloc(%d) failed: %s" % (n, self.lib.mpcqp_last_error().decode()))
+        if not hasattr(self, "_pinned"):
+            self._pinned = []
+        self._pinned.append(ptr)
+        return np.frombuffer((C.c_char * n).from_address(ptr), dtype=dtype).reshape(shape)
 
     __del__ = close
 
@@ -184,12 +204,22 @@ class Engine:
         _check(self.lib.mpcqp_get_latest_result(self._h, _ptr(out), HOST))
         return out
 
-    def step_result(self, forces=None, dev1=None):
-        """Forces (B,12) and X_1 - xref_1 (B,12) of the last run in one call / one synchronisation."""
+    def step_result(self, forces=None, next_state=None):
+        """Forces (B,12) and the first predicted state x_robot[:, 0] (B,12) of the last run in one call / one synchronisation."""
         forces = np.empty((self.B, 12)) if forces is None else forces
-        dev1 = np.empty((self.B, 12)) if dev1 is None else dev1
-        _check(self.lib.mpcqp_get_step_result(self._h, _ptr(forces), _ptr(dev1), HOST))
-        return forces, dev1
+        next_state = np.empty((self.B, 12)) if next_state is None else next_state
+        _check(self.lib.mpcqp_get_step_result(self._h, _ptr(forces), _ptr(next_state), HOST))
+        return forces, next_state
+
+    def world_pose(self, set_to=None):
+        """MPC.q_w of every robot, (B, 6): read it, or overwrite it with `set_to`."""
+        if set_to is not None:
+            q = _host_f64(set_to, (self.B, 6))
+            _check(self.lib.mpcqp_world_pose(self._h, _ptr(q), 1, HOST))
+            return q
+        q = np.empty((self.B, 6))
+        _check(self.lib.mpcqp_world_pose(self._h, _ptr(q), 0, HOST))
+        return q
 
     def status(self):
         st = np.empty(self.B, np.int32)
