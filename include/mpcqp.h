@@ -156,12 +156,16 @@ int mpcqp_export_build(mpcqp_handle* h, double k, const double* xref, const doub
  * The footstep planner (FootstepPlanner.update_fsteps / getRefStates, FootstepPlanner.py:76-161, 284-445) and the
  * closed-loop state update (MPC.q_next / v_next, MPC.py:448-450, moved into the next local frame as
  * Interface.py:100-132 does) run inside the solve kernel, so a tick needs no host producer and no input copy.
- * Per instance: seq = 64 bits, bit 4*s + j = foot j in contact at step s of the 16-step gait period
+ * Per instance: seq = 64 bits, bit 4*s + j = foot j in contact at step s of the gait period (T_gait / dt <= 16 steps)
  * (FootstepPlanner.py:207-282), phase = offset into that period, vref = 6 commanded velocities, state = 12 initial
  * measured states; sigma4 = Gaussian noise (position, angle, linear, angular velocity) drawn from a counter-based
  * generator keyed by (seed, instance, tick, component).  All pointers are HOST pointers. */
 int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* phase, const double* vref,
                         const double* state, const double* sigma4, uint64_t seed);
+/* New joystick commands from the next tick on (Joystick.update_v_ref, Joystick.py:29-43): vref B x 6 (HOST pointer, NULL keeps the
+ * current ones) -- vz / roll-rate / pitch-rate commands drive getRefStates' state machine (FootstepPlanner.py:128-152) -- and
+ * the `reduced` support-polygon switch (Joystick.py:66-67, FootstepPlanner.py:330-332). */
+int mpcqp_scenario_set_commands(mpcqp_handle* h, const double* vref, int reduced);
 /* Run `ticks` closed-loop ticks (plan -> build -> solve -> integrate) back to back on the device.  With
  * emit_inputs != 0 the xref / fsteps generated by the last tick can be read with mpcqp_get_inputs. */
 int mpcqp_scenario_run(mpcqp_handle* h, int ticks, int emit_inputs);

@@ -748,6 +748,7 @@ int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* pha
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_state = take(B * 12 * 8), o_frame = take(B * 3 * 8), o_feet = take(B * 8 * 8), o_target = take(B * 8 * 8);
     const size_t o_vref = take(B * 6 * 8), o_seq = take(B * 8), o_phase = take(B * 4), o_prev = take(B);
+    const size_t o_cmd = take(B * 3 * 8), o_cflag = take(B), o_ctick = take(B * 4);
     if (!h->d_scen) CU(cudaMalloc(&h->d_scen, off));
     CU(cudaMemset(h->d_scen, 0, off));
     char* base = (char*)h->d_scen;
@@ -756,6 +757,13 @@ int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* pha
     s.state = (double*)(base + o_state); s.frame = (double*)(base + o_frame); s.feet = (double*)(base + o_feet);
     s.target = (double*)(base + o_target); s.vref = (const double*)(base + o_vref);
     s.seq = (const unsigned long long*)(base + o_seq); s.phase = (const int32_t*)(base + o_phase); s.prevc = (uint8_t*)(base + o_prev);
+    s.cmd = (double*)(base + o_cmd); s.cmd_flag = (uint8_t*)(base + o_cflag); s.cmd_tick = (int32_t*)(base + o_ctick);
+    {
+        std::vector<double> cmd(B * 3);
+        for (size_t b = 0; b < B; ++b) { cmd[b * 3] = SC_H_ROTATION0; cmd[b * 3 + 1] = SC_H_REF; cmd[b * 3 + 2] = 0.0; }
+        CU(cudaMemcpy(base + o_cmd, cmd.data(), B * 3 * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemset(base + o_ctick, 0xFF, B * 4));           // -1: no tick applied yet
+    }
     std::vector<double> feet(B * 8);
     for (size_t b = 0; b < B; ++b)
         for (int j = 0; j < 4; ++j) { feet[b * 8 + j] = sc_shoulder_x(j); feet[b * 8 + 4 + j] = sc_shoulder_y(j); }
@@ -777,6 +785,20 @@ int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* pha
     h->scen_tick = 0;
     h->scen_ready = true;
     CU(mpcqp_reset_warm_start(h) == 0 ? cudaSuccess : cudaErrorUnknown);
+    return MPCQP_OK;
+}
+
+// New joystick commands for the following ticks (Joystick.update_v_ref, Joystick.py:29-43): vref B x 6 (HOST; may be NULL to
+// keep the current ones) and the `reduced` support-polygon switch (Joystick.py:66-67, FootstepPlanner.py:330-332).
+int mpcqp_scenario_set_commands(mpcqp_handle* h, const double* vref, int reduced) {
+    if (!h) return fail(MPCQP_ERR_INVALID, "null argument");
+    if (!h->scen_ready) return fail(MPCQP_ERR_STATE, "mpcqp_scenario_init has not been called");
+    CU(cudaSetDevice(h->p.device));
+    if (vref) {
+        CU(cudaMemcpyAsync((void*)h->sc.vref, vref, (size_t)h->p.batch * 6 * 8, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));                  // the caller's buffer is free on return
+    }
+    h->sc.reduced = reduced ? 1 : 0;
     return MPCQP_OK;
 }
 

@@ -836,6 +836,12 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
     const int AW = (20 * n + 31) / 32, CW = (4 * n + 31) / 32, ld = n + 1;
     const double lin = P.dt / P.mass;
     for (int i = hl; i < AWC + CWC; i += 16) sm.amask[i] = 0u;
+    // the world pose this tick advances (MPC.py:503-510): fetched now, used by lane 0 at the very end
+    double qw[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (commit && hl == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; c += 2) { const double2 v = *reinterpret_cast<const double2*>(st.qw + (size_t)inst * 6 + c); qw[c] = v.x; qw[c + 1] = v.y; }
+    }
     if (!solved) {
         // no forces: the states are the free response  p_{s+1} = p_s + dt v_s, v_{s+1} = v_s + g   (MPC.py:110-111, 200-205)
         if (hl < 6) {
@@ -925,7 +931,11 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
         st.status[inst] = status;
         st.sweeps[inst] = sweeps;
         st.iters[inst] = iters;
-        if (status != 3) world_pose_step(st.qw + (size_t)inst * 6, sm.xnext);
+        if (status != 3) {
+            world_pose_step(qw, sm.xnext);
+#pragma unroll
+            for (int c = 0; c < 6; c += 2) *reinterpret_cast<double2*>(st.qw + (size_t)inst * 6 + c) = make_double2(qw[c], qw[c + 1]);
+        }
         if (SC.enabled && status != 3) scenario_advance(SC, inst, sm.xnext);
     }
 }

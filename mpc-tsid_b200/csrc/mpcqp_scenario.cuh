@@ -6,7 +6,7 @@
 //     gait roll / run-length table       FootstepPlanner.py:401-425
 //     compute_footsteps                  FootstepPlanner.py:284-361
 //     compute_next_footstep              FootstepPlanner.py:363-399
-//     getRefStates                       FootstepPlanner.py:76-161   (vz / roll / pitch commands = 0)
+//     getRefStates                       FootstepPlanner.py:76-161   (with the vz / roll / pitch command state machine, :128-152)
 // and closes the loop on the centroidal model: the next measured state is the MPC's one-step
 // prediction (MPC.py:448-450) re-expressed in the next yaw-aligned local frame (Interface.py:100-132)
 // plus counter-based Gaussian noise (same generator as scenario.py's noise_kind="hash").
@@ -20,7 +20,10 @@ struct DevScenario {
     double* frame;          // B x 3   local frame in the world (x, y, yaw)
     double* feet;           // B x 8   feet in the world, [x0..x3, y0..y3]
     double* target;         // B x 8   where each swinging foot is planned to land (world)
-    const double* vref;     // B x 6
+    const double* vref;     // B x 6   joystick commands (mpcqp_scenario_set_commands replaces them between ticks)
+    double* cmd;            // B x 3   getRefStates' command state: h_rotation_command, and the xref[2, 1:] / xref[8, 1:] it leaves behind
+    uint8_t* cmd_flag;      // B       flag_rotation_command (0 idle, 1 commanding, 2 released), FootstepPlanner.py:66, 128-152
+    int32_t* cmd_tick;      // B       tick whose command step has been applied (a robot's inputs may be rebuilt by the fallback stage)
     const unsigned long long* seq;   // B: bit 4 s + j = foot j in contact at step s of the gait period (<= 16 steps)
     const int32_t* phase;   // B
     uint8_t* prevc;         // B: bits 0..3 contact of the previous tick's first step, bit 7 = valid
@@ -32,6 +35,7 @@ struct DevScenario {
     unsigned long long seed;
     int tick;               // closed-loop tick of this launch
     int period;             // steps per gait period (T_gait / dt), <= 16
+    int reduced;            // Joystick.reduced: the smaller support polygon of FootstepPlanner.py:330-332
     int enabled;
 };
 
@@ -39,6 +43,7 @@ struct DevScenario {
 __host__ __device__ constexpr double sc_shoulder_x(int j) { return j < 2 ? 0.19 : -0.19; }
 __host__ __device__ constexpr double sc_shoulder_y(int j) { return (j & 1) ? -0.15005 : 0.15005; }
 constexpr double SC_H_REF = 0.2027682, SC_K_FEEDBACK = 0.03, SC_LEG_L = 0.12, SC_T_STANCE = 0.16, SC_G = 9.81;
+constexpr double SC_CMD_STEP = 0.05, SC_H_ROTATION0 = 0.20;       // FootstepPlanner.py:131, 69
 
 __host__ __device__ inline unsigned long long splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -64,6 +69,8 @@ struct ScenarioSmem {
     double xnext[12];
     int cnt[20], mask[20];
     int nrows;
+    double zref, vzref;     // xref[2, 1:], xref[8, 1:] of this tick
+    int flag;
 };
 
 // Build xref (12 x (N+1)) and fsteps (20 x 13) of instance `inst` in shared memory.  Called by every thread of
@@ -98,6 +105,23 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
         }
         sc.nrows = rows;
         for (int r = 0; r < rows; ++r) fs[r * 13] = (double)sc.cnt[r];
+        // the command state machine of getRefStates (FootstepPlanner.py:128-152), advanced once per tick and robot
+        int flag = S.cmd_flag[inst];
+        double hrot = S.cmd[(size_t)inst * 3], zref = S.cmd[(size_t)inst * 3 + 1], vzref = S.cmd[(size_t)inst * 3 + 2];
+        if (S.cmd_tick[inst] != S.tick) {
+            const double vz = sc.vr[2];
+            const bool big = fabs(vz) > SC_CMD_STEP, small = fabs(vz) < SC_CMD_STEP;
+            if (big && flag != 1) flag = 1;
+            if (big && flag == 1) { hrot += vz * P.dt; zref = hrot; vzref = vz; }
+            else if (small && flag == 1) { vzref = 0.0; flag = 2; }
+            else if (flag == 0) { zref = SC_H_REF; vzref = 0.0; }
+            if (commit) {
+                S.cmd[(size_t)inst * 3] = hrot; S.cmd[(size_t)inst * 3 + 1] = zref; S.cmd[(size_t)inst * 3 + 2] = vzref;
+                S.cmd_flag[inst] = (uint8_t)flag;
+                S.cmd_tick[inst] = S.tick;
+            }
+        }
+        sc.zref = zref; sc.vzref = vzref; sc.flag = flag;
     }
     for (int i = WARP ? tid : tid - 32; i >= 0 && i < N; i += WARP ? GROUP : N) {
         double sn, cs;
@@ -127,6 +151,7 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
         double nfy = SC_T_STANCE * 0.5 * sc.vr[1] + SC_K_FEEDBACK * (sc.vr[1] - sc.vr[1]) + kc * cry;
         nfx = fmin(fmax(nfx, -SC_LEG_L), SC_LEG_L) + sc_shoulder_x(j);
         nfy = fmin(fmax(nfy, -SC_LEG_L), SC_LEG_L) + sc_shoulder_y(j);
+        if (S.reduced) { nfx -= (j < 2) ? 0.14 : -0.14; nfy -= (j & 1) ? -0.12 : 0.12; }        // FootstepPlanner.py:330-332
         const double vcx = sc.st[6], vcy = sc.st[7];
         double dt_cum = 0.0;
         bool got = false;
@@ -176,9 +201,16 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
         }
     }
     for (int i = WARP ? tid : tid - 64; i >= 0 && i < N; i += WARP ? GROUP : N) {
-        xr[2 * (N + 1) + 1 + i] = SC_H_REF;
+        xr[2 * (N + 1) + 1 + i] = sc.zref;
+        xr[8 * (N + 1) + 1 + i] = sc.vzref;
         xr[5 * (N + 1) + 1 + i] = w * S.lin_b[i];
         xr[11 * (N + 1) + 1 + i] = w;
+        if (sc.flag != 0) {                                                                    // FootstepPlanner.py:153-158
+            xr[3 * (N + 1) + 1 + i] = sc.st[3] + sc.vr[3] * S.lin_a[i];
+            xr[4 * (N + 1) + 1 + i] = sc.st[4] + sc.vr[4] * S.lin_a[i];
+            xr[9 * (N + 1) + 1 + i] = sc.vr[3];
+            xr[10 * (N + 1) + 1 + i] = sc.vr[4];
+        }
     }
     if (WARP ? tid < 12 : (tid >= 96 && tid < 108)) { const int c = WARP ? tid : tid - 96; xr[c * (N + 1)] = sc.st[c]; }
     group_sync();

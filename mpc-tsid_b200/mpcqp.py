@@ -25,7 +25,7 @@ EXPORTS = (
     "mpcqp_scenario_init", "mpcqp_scenario_run", "mpcqp_scenario_get", "mpcqp_get_inputs",
     "mpcqp_get_cost_components", "mpcqp_result_async", "mpcqp_result_ready", "mpcqp_result_wait",
     "mpcqp_get_step_result", "mpcqp_get_status", "mpcqp_host_alloc", "mpcqp_host_free",
-    "mpcqp_world_pose",
+    "mpcqp_world_pose", "mpcqp_scenario_set_commands",
 )
 
 
@@ -80,6 +80,7 @@ def load():
     lib.mpcqp_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.mpcqp_scenario_init.argtypes = [vp, dp, dp, dp, dp, dp, C.c_uint64]
     lib.mpcqp_scenario_run.argtypes = [vp, C.c_int, C.c_int]
+    lib.mpcqp_scenario_set_commands.argtypes = [vp, dp, C.c_int]
     lib.mpcqp_scenario_get.argtypes = [vp, dp, dp, dp]
     lib.mpcqp_get_inputs.argtypes = [vp, dp, dp]
     lib.mpcqp_get_cost_components.argtypes = [vp, dp, C.c_int]
@@ -275,6 +276,13 @@ class Engine:
         sigma = np.ascontiguousarray(scen.noise, dtype=np.float64)
         _check(self.lib.mpcqp_scenario_init(self._h, _ptr(seq), _ptr(phase), _ptr(vref), _ptr(state), _ptr(sigma),
                                             C.c_uint64(int(scen.seed))))
+        if getattr(scen, "reduced", False):
+            self.scenario_set_commands(None, True)
+
+    def scenario_set_commands(self, v_ref=None, reduced=False):
+        """Joystick commands for the following ticks: v_ref (B, 6) or (6,) or None (unchanged), and the `reduced` switch."""
+        v = None if v_ref is None else np.ascontiguousarray(np.broadcast_to(np.asarray(v_ref, dtype=np.float64), (self.B, 6)))
+        _check(self.lib.mpcqp_scenario_set_commands(self._h, None if v is None else _ptr(v), int(bool(reduced))))
 
     def scenario_run(self, ticks, emit_inputs=False):
         _check(self.lib.mpcqp_scenario_run(self._h, int(ticks), 1 if emit_inputs else 0))

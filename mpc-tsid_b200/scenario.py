@@ -9,7 +9,7 @@ parts of the planner that define what the MPC sees:
     gait tables + roll            FootstepPlanner.py:207-282, 401-425
     compute_footsteps             FootstepPlanner.py:284-361
     compute_next_footstep         FootstepPlanner.py:363-399
-    getRefStates                  FootstepPlanner.py:76-161   (joystick vz / roll / pitch commands = 0)
+    getRefStates                  FootstepPlanner.py:76-161   (including the vz / roll / pitch command state machine, :128-152)
     velocity ramp                 Joystick.py:82-83
 
 and a closed-loop state update: the next measured state is the MPC's own one-step prediction
@@ -31,6 +31,10 @@ LEG_L = 0.12                                                      # FootstepPlan
 T_STANCE = 0.16                                                   # FootstepPlanner.py:377
 G = 9.81
 MAX_ROWS = 20                                                     # FootstepPlanner.py:62, MPC.py:82
+CMD_STEP = 0.05                                                   # FootstepPlanner.py:131: joystick dead band of the vz command
+H_ROTATION0 = 0.20                                                # FootstepPlanner.py:69: h_rotation_command at start
+REDUCED_OFFSET = np.array([[0.14, 0.14, -0.14, -0.14],
+                           [0.12, -0.12, 0.12, -0.12]])           # FootstepPlanner.py:331-332 (`reduced` support polygon)
 
 # per-step contact patterns over one gait period of 16 steps, feet = FL, FR, HL, HR
 _ALL = (1, 1, 1, 1)
@@ -96,7 +100,7 @@ class Scenario:
 
     def __init__(self, batch, n_steps=16, dt=0.02, T_gait=0.32, gaits="trot", seed=20260,
                  v_ref=None, phase=None, noise=(1e-3, 5e-3, 1e-2, 2e-2), random_commands=True,
-                 ramp=False, noise_kind="numpy"):
+                 ramp=False, noise_kind="numpy", reduced=False):
         self.B, self.N, self.dt, self.T_gait = int(batch), int(n_steps), float(dt), float(T_gait)
         B, N = self.B, self.N
         self.period = int(round(T_gait / dt))
@@ -119,6 +123,13 @@ class Scenario:
             self.v_ref[:, 1] = self._bulk_rng.uniform(-0.3, 0.3, B)
             self.v_ref[:, 5] = self._bulk_rng.uniform(-0.4, 0.4, B)
         self.ramp = bool(ramp)
+        self.reduced = bool(reduced)                                         # Joystick.reduced (processing.py:78-88)
+        # getRefStates' command state machine, one per robot (FootstepPlanner.py:66-69, 128-152): flag_rotation_command,
+        # h_rotation_command, and the two reference rows it leaves untouched between ticks (xref[2, 1:], xref[8, 1:])
+        self.cmd_flag = np.zeros(B, dtype=np.int64)
+        self.h_rot = np.full(B, H_ROTATION0)
+        self.z_ref = np.full(B, H_REF)
+        self.vz_ref = np.zeros(B)
         self.noise = np.asarray(noise, dtype=np.float64)
         # "numpy": one numpy Generator per robot (configs[0..2]); "hash": a counter-based generator keyed by
         # (seed, robot, tick, component) that the device-resident closed loop reproduces (mpcqp_scenario.cuh)
@@ -173,6 +184,8 @@ class Scenario:
         nf[:, 0:2, :] += (0.5 * np.sqrt(h / G))[:, None, None] * cross[:, 0:2, None]
         nf[:, 0:2, :] = np.clip(nf[:, 0:2, :], -LEG_L, LEG_L)
         nf[:, 0:2, :] += SHOULDERS[None]
+        if self.reduced:                                                     # FootstepPlanner.py:330-332
+            nf[:, 0:2, :] -= REDUCED_OFFSET[None]
         return nf
 
     def _compute_footsteps(self, gait, l_feet, v_cur, v_ref, h):
@@ -211,19 +224,42 @@ class Scenario:
         return fs
 
     def _ref_states(self, v_ref):
-        """FootstepPlanner.py:76-161 with the joystick's vz / roll / pitch commands at zero."""
+        """FootstepPlanner.py:76-161, including the state machine of the vz / roll / pitch commands (:128-152): it keeps
+        per-robot state (cmd_flag, h_rot) and leaves xref[2, 1:] / xref[8, 1:] as they were when no branch rewrites them."""
         B, N, dt = self.B, self.N, self.dt
         xr = np.zeros((B, 12, N + 1))
-        yaw = np.linspace(0.0, self.T_gait - dt, N)[None, :] * v_ref[:, 5:6]
+        to = np.linspace(0.0, self.T_gait - dt, N)[None, :]
+        yaw = to * v_ref[:, 5:6]
         xr[:, 6, 1:] = v_ref[:, 0:1] * np.cos(yaw) - v_ref[:, 1:2] * np.sin(yaw)
         xr[:, 7, 1:] = v_ref[:, 0:1] * np.sin(yaw) + v_ref[:, 1:2] * np.cos(yaw)
         xr[:, 0, 1:] = dt * np.cumsum(xr[:, 6, 1:], axis=1) + self.state[:, 0:1]
         xr[:, 1, 1:] = dt * np.cumsum(xr[:, 7, 1:], axis=1) + self.state[:, 1:2]
-        xr[:, 2, 1:] = H_REF
         xr[:, 5, 1:] = v_ref[:, 5:6] * np.linspace(dt, self.T_gait, N)[None, :]
         xr[:, 11, 1:] = v_ref[:, 5:6]
         xr[:, :, 0] = self.state
+        # ---- command state machine
+        vz = v_ref[:, 2]
+        big, small = np.abs(vz) > CMD_STEP, np.abs(vz) < CMD_STEP
+        self.cmd_flag = np.where(big & (self.cmd_flag != 1), 1, self.cmd_flag)                  # :134-135
+        commanding = big & (self.cmd_flag == 1)                                                 # :138-143
+        releasing = small & (self.cmd_flag == 1)                                                # :144-148
+        idle = ~commanding & ~releasing & (self.cmd_flag == 0)                                  # :149-151
+        self.h_rot = np.where(commanding, self.h_rot + vz * dt, self.h_rot)
+        self.z_ref = np.where(commanding, self.h_rot, np.where(idle, H_REF, self.z_ref))
+        self.vz_ref = np.where(commanding, vz, np.where(releasing | idle, 0.0, self.vz_ref))
+        self.cmd_flag = np.where(releasing, 2, self.cmd_flag)
+        xr[:, 2, 1:] = self.z_ref[:, None]
+        xr[:, 8, 1:] = self.vz_ref[:, None]
+        on = (self.cmd_flag != 0)[:, None]                                                      # :153-158
+        xr[:, 3, 1:] = np.where(on, self.state[:, 3:4] + v_ref[:, 3:4] * to, 0.0)
+        xr[:, 4, 1:] = np.where(on, self.state[:, 4:5] + v_ref[:, 4:5] * to, 0.0)
+        xr[:, 9, 1:] = np.where(on, v_ref[:, 3:4], 0.0)
+        xr[:, 10, 1:] = np.where(on, v_ref[:, 4:5], 0.0)
         return xr
+
+    def set_v_ref(self, v_ref):
+        """New joystick commands (Joystick.update_v_ref, Joystick.py:29-43) from the next inputs() on: (6,) or (B, 6)."""
+        self.v_ref[:] = np.asarray(v_ref, dtype=np.float64)
 
     # ------------------------------------------------------------------ loop
     def current_v_ref(self):

@@ -103,6 +103,27 @@ def planner_fixture():
         rec["xref_N%d" % N] = np.array(xs); rec["fsteps_N%d" % N] = np.array(fs)
         rec["state_N%d" % N] = np.array(states); rec["lfeet_N%d" % N] = np.array(feet)
     rec["v_ref"] = np.array([0.4, -0.1, 0, 0, 0, 0.3])
+    # joystick commands that change in time, including vz / roll / pitch (the state machine of FootstepPlanner.py:128-152)
+    # and the `reduced` support polygon (FootstepPlanner.py:330-332, toggled by Joystick.py:66-67)
+    fp = RefPlanner.FootstepPlanner(0.02, 1)
+    sc = Scenario(1, n_steps=16, gaits="trot", v_ref=np.zeros(6), phase=[0], random_commands=False)
+    sched = [(0, [0.3, 0.0, 0.0, 0.0, 0.0, 0.2], False), (10, [0.3, 0.1, 0.1, 0.2, -0.15, 0.2], False),
+             (25, [0.2, 0.0, 0.0, 0.1, 0.0, -0.3], False), (30, [0.2, 0.0, 0.03, 0.1, 0.0, -0.3], True),
+             (40, [0.0, -0.2, -0.08, 0.0, 0.05, 0.0], True), (50, [0.0, 0.0, 0.0, 0.0, 0.0, 0.0], False)]
+    xs, fs, states, vs, rs = [], [], [], [], []
+    for k in range(60):
+        v, red = [(vv, rr) for (t0, vv, rr) in sched if t0 <= k][-1]
+        sc.set_v_ref(v); sc.reduced = red
+        sc.inputs()
+        st = sc.state[0].copy()
+        vr = np.array(v, dtype=np.float64).reshape(6, 1)
+        fp.update_fsteps(k, sc.local_feet()[0], st[6:12].reshape(6, 1), vr, st[2], None, None, red)
+        fp.getRefStates(k, 0.32, st[0:3].reshape(3, 1), st[3:6].reshape(3, 1), st[6:9].reshape(3, 1), st[9:12].reshape(3, 1), vr)
+        xs.append(fp.xref.copy()); fs.append(fp.fsteps.copy()); states.append(st); vs.append(np.array(v, dtype=np.float64)); rs.append(red)
+        xn = fp.xref[:, 1] + 0.01 * np.sin(np.arange(12) + k)
+        sc.advance(xn[None])
+    rec["cmd_xref"], rec["cmd_fsteps"], rec["cmd_state"] = np.array(xs), np.array(fs), np.array(states)
+    rec["cmd_v_ref"], rec["cmd_reduced"] = np.array(vs), np.array(rs)
     np.savez_compressed(os.path.join(HERE, "planner_trot.npz"), **rec)
     print("wrote planner_trot.npz")
 
@@ -154,7 +175,9 @@ def general_horizons():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "horizons":
+    if len(sys.argv) > 1 and sys.argv[1] == "planner":
+        planner_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "horizons":
         general_horizons()
     elif len(sys.argv) > 1 and sys.argv[1] == "long":
         long_horizon()

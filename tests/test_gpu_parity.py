@@ -472,6 +472,47 @@ def test_device_closed_loop_matches_host_loop(noise):
     host.close(); dev.close()
 
 
+def test_device_planner_follows_changing_commands():
+    """SURVEY 8f row f1, the rest of the planner: joystick commands that change between ticks, including vz / roll-rate /
+    pitch-rate (getRefStates' state machine, FootstepPlanner.py:128-152) and the `reduced` support polygon
+    (FootstepPlanner.py:330-332).  Device planner vs the host twin (pinned to the reference planner by
+    tests/test_planner.py::test_command_state_machine_and_reduced_polygon_match_reference): inputs, forces, states."""
+    B, T = 40, 36
+    kw = dict(gaits=["trot", "pace", "bound", "walk"], seed=77, noise=(1e-3, 5e-3, 1e-2, 2e-2), noise_kind="hash")
+    host_sc, dev_sc = Scenario(B, **kw), Scenario(B, **kw)
+    host, dev = mpcqp.Engine(batch=B), mpcqp.Engine(batch=B)
+    dev.scenario_init(dev_sc)
+    rng = np.random.default_rng(5)
+    base = host_sc.v_ref.copy()
+    flags = set()
+    for t in range(T):
+        if t % 6 == 0:                                   # new commands every 6 ticks; vz toggles above / below the dead band
+            v = base.copy()
+            phase = (t // 6) % 4
+            v[:, 2] = [0.0, 0.09, 0.02, -0.07][phase] * np.sign(rng.standard_normal(B))
+            v[:, 3] = rng.uniform(-0.2, 0.2, B) * (phase > 0)
+            v[:, 4] = rng.uniform(-0.2, 0.2, B) * (phase > 0)
+            red = phase >= 2
+            host_sc.set_v_ref(v); host_sc.reduced = red
+            dev.scenario_set_commands(v, red)
+        xref, fsteps = host_sc.inputs()
+        flags |= set(int(f) for f in host_sc.cmd_flag)
+        host.run(t, xref, fsteps)
+        xh = host.solution()
+        dev.scenario_run(1, emit_inputs=True)
+        xd_ref, fd = dev.last_inputs()
+        assert np.array_equal(np.isnan(fd), np.isnan(fsteps)), "tick %d: swing pattern" % t
+        np.testing.assert_allclose(np.nan_to_num(fd), np.nan_to_num(fsteps), rtol=0, atol=1e-9)
+        np.testing.assert_allclose(xd_ref, xref, rtol=0, atol=1e-9)
+        assert (dev.info()["status"] == 1).all()
+        np.testing.assert_allclose(dev.forces(), host.forces(), rtol=0, atol=1e-6)
+        host_sc.advance(xh[:, :12] + xref[:, :, 1])
+        st = dev.scenario_state()
+        np.testing.assert_allclose(st["state"], host_sc.state, rtol=0, atol=1e-9)
+    assert flags == {0, 1, 2}
+    host.close(); dev.close()
+
+
 def test_mixed_gait_sweep_on_device():
     """BASELINE configs[2] shape (65 536 robots, trot / pace / bound / walk, per-instance contact masks),
     run as a device-resident closed loop: everything solved, forces feasible, contact masks follow the

@@ -51,3 +51,24 @@ def test_batched_equals_single():
 def test_reference_ramp():
     assert reference_ramp(0) == 0.0 and reference_ramp(48) == 0.0
     assert abs(reference_ramp(100) - (2000 - 960) / 3500) < 1e-15 and reference_ramp(1000) == 1.0
+
+
+def test_command_state_machine_and_reduced_polygon_match_reference():
+    """Joystick commands that change in time, including vz / roll / pitch (getRefStates' state machine, FootstepPlanner.py:128-152:
+    idle -> commanding -> released -> commanding again) and the `reduced` support polygon (FootstepPlanner.py:330-332), against
+    the reference planner's own xref / fsteps, tick by tick over 60 ticks."""
+    sc = Scenario(1, gaits="trot", v_ref=np.zeros(6), phase=[0], random_commands=False)
+    flags = []
+    for k in range(G["cmd_xref"].shape[0]):
+        sc.set_v_ref(G["cmd_v_ref"][k])
+        sc.reduced = bool(G["cmd_reduced"][k])
+        xr, fs = sc.inputs()
+        flags.append(int(sc.cmd_flag[0]))
+        np.testing.assert_allclose(sc.state[0], G["cmd_state"][k], rtol=0, atol=1e-15)
+        assert np.array_equal(np.isnan(fs[0]), np.isnan(G["cmd_fsteps"][k]))
+        np.testing.assert_allclose(np.nan_to_num(fs[0]), np.nan_to_num(G["cmd_fsteps"][k]), rtol=0, atol=1e-14)
+        np.testing.assert_allclose(xr[0], G["cmd_xref"][k], rtol=0, atol=1e-14)
+        xn = G["cmd_xref"][k][:, 1] + 0.01 * np.sin(np.arange(12) + k)
+        sc.advance(xn[None])
+    assert set(flags) == {0, 1, 2} and flags[9] == 0 and flags[10] == 1 and flags[25] == 2 and flags[40] == 1
+    assert np.abs(G["cmd_xref"][:, 2, 1] - 0.2027682).max() > 1e-3 and np.abs(G["cmd_xref"][:, 3, 5]).max() > 1e-3

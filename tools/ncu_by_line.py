@@ -5,10 +5,16 @@ import collections, csv, io, os, re, subprocess, sys, tempfile
 
 rep, so, ksub = sys.argv[1], sys.argv[2], sys.argv[3]
 which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+# the library links several objects whose embedded cubins share a name: extract each object of the build directory on its own
+objs = [so] + sorted(os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", "build", f)
+                     for f in os.listdir(os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", "build")) if f.endswith(".o"))
+dis = ""
+for o in objs:
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(o)], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for cub in sorted(os.listdir(tmp)):
+        if cub.endswith(".cubin"):
+            dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout + "\n"
 # per function: list of (line_file, line_no) per instruction in order
 funcs, cur, loc = {}, None, ("?", 0)
 for ln in dis.splitlines():
@@ -34,7 +40,7 @@ if "solve_kernel" in ksub:
     mangled = [f for f in funcs if ("Lb0" in f) == ("(bool)0" in sec["name"]) and "solve_kernel" in f]
 elif "riccati_kernel" in ksub:
     n = re.search(r"\(int\)(\d+)", sec["name"]).group(1)
-    mangled = [f for f in funcs if "riccati_kernelILi%sE" % n in f]
+    mangled = [f for f in funcs if "riccati_kernelILi%sELb1" % n in f] or [f for f in funcs if "riccati_kernelILi%sE" % n in f]
 else:
     mangled = list(funcs)
 lines = funcs[mangled[0]]

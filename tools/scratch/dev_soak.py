@@ -1,30 +1,32 @@
-"""Soak: many closed-loop ticks, all gaits, checking statuses / finiteness / feasibility every tick."""
+"""Soak: closed loop on the device, every tick checked: status, pyramid feasibility, sweeps / fallback statistics."""
 import sys, time
 import numpy as np
 sys.path.insert(0, "/root/repo/mpc-tsid_b200"); sys.path.insert(0, "/root/repo")
 import mpcqp
 from scenario import Scenario
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-T = int(sys.argv[2]) if len(sys.argv) > 2 else 300
-N = int(sys.argv[3]) if len(sys.argv) > 3 else 16
-sc = Scenario(B, n_steps=N, gaits=["trot", "pace", "bound", "walk"], seed=777)
-eng = mpcqp.Engine(batch=B, n_steps=N)
-mu = eng.params.mu
-worst = dict(status2=0, status0=0, max_sweeps=0, max_iters=0, max_ms=0.0)
-t0 = time.perf_counter()
-for t in range(T):
-    xref, fsteps = sc.inputs()
-    s0 = time.perf_counter(); eng.run(t, xref, fsteps); x = eng.solution(); ms = (time.perf_counter() - s0) * 1e3
-    info = eng.info(with_y=False)
-    f = x[:, 12 * N:].reshape(B, N, 4, 3)
-    viol = np.maximum.reduce([np.abs(f[..., 0]) - mu * f[..., 2], np.abs(f[..., 1]) - mu * f[..., 2], -f[..., 2], f[..., 2] - 25.0]).max(axis=(1, 2))
-    bad = (~np.isfinite(x).all(axis=1)) | (viol > 1e-7)
-    if bad.any():
-        b = np.flatnonzero(bad)
-        print("tick %d: %d bad robots; first %s status %s sweeps %s iters %s viol %s gait %s" % (t, len(b), b[:5], info["status"][b[:5]], info["sweeps"][b[:5]], info["iters"][b[:5]], viol[b[:5]], [sc.kinds[i] for i in b[:5]]))
-        worst.setdefault("bad", 0); worst["bad"] += len(b)
-    worst["status2"] += int((info["status"] == 2).sum()); worst["status0"] += int((info["status"] == 0).sum())
-    worst["max_sweeps"] = max(worst["max_sweeps"], int(info["sweeps"].max())); worst["max_iters"] = max(worst["max_iters"], int(info["iters"].max()))
-    if t > 5: worst["max_ms"] = max(worst["max_ms"], ms)
-    sc.advance(x[:, :12] + xref[:, :, 1])
-print("soak B=%d N=%d ticks=%d: %s  total %.1f s" % (B, N, T, worst, time.perf_counter() - t0))
+def soak(N, B, ticks, gaits, seed=7):
+    sc = Scenario(B, n_steps=N, gaits=gaits, seed=seed, noise_kind="hash")
+    eng = mpcqp.Engine(batch=B, n_steps=N)
+    eng.scenario_init(sc)
+    bad = 0; msw = 0; mit = 0; fb = 0; worst = 0.0
+    t0 = time.time()
+    x = np.empty((B, 24 * N))
+    for t in range(ticks):
+        eng.scenario_run(1)
+        st = eng.status()
+        bad += int((st != 1).sum())
+        if t % 10 == 0 or t == ticks - 1:
+            info = eng.info(with_y=False); eng.solution(out=x)
+            f = x[:, 12 * N:].reshape(B, N, 4, 3)
+            mu = eng.params.mu
+            v = max((np.abs(f[..., 0]) - mu * f[..., 2]).max(), (np.abs(f[..., 1]) - mu * f[..., 2]).max(), (-f[..., 2]).max(), (f[..., 2] - 25).max())
+            worst = max(worst, v); msw = max(msw, info["sweeps"].max()); mit = max(mit, info["iters"].max()); fb += int((info["iters"] > 0).sum())
+    print("soak N %d: %d robots x %d ticks (%s): not-solved %d, worst pyramid violation %.1e, max sweeps %d, max ipm iters %d, fallback robots on sampled ticks %d, %.1f s"
+          % (N, B, ticks, "/".join(gaits), bad, worst, msw, mit, fb, time.time() - t0), flush=True)
+    eng.close()
+if __name__ == "__main__":
+    soak(64, 1024, 100, ["trot"])
+    soak(64, 512, 60, ["trot", "pace", "bound", "walk"])
+    soak(32, 1024, 100, ["trot", "pace", "bound", "walk"])
+    soak(16, 4096, 300, ["trot", "pace", "bound", "walk"])
+    soak(24, 1024, 100, ["trot", "pace", "bound", "walk"])
