@@ -336,6 +336,9 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     d.max_sweeps = p->max_sweeps; d.max_iter = p->max_iter; d.min_iter = p->min_iter > 0 ? p->min_iter : 1;
     d.check_every = p->check_every > 0 ? p->check_every : 1;
     d.warm_start = p->warm_start; d.mode = p->mode; d.refine = p->refine > 0 ? 1 : 0;
+#ifdef MPCQP_CANARY
+    d.refine = p->refine;           // debug build: refine == 77 makes robot 0 write one element past its state array (detector self-test)
+#endif
     d.ipm_max_iter = p->ipm_max_iter > 0 ? p->ipm_max_iter : 60;
 
     // Gram matrices of the double-integrator response and their inverses (constant per handle)
@@ -388,7 +391,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     const size_t o_f0 = take((size_t)B * 12 * 8), o_x1 = take((size_t)B * 12 * 8), o_qw = take((size_t)B * 6 * 8), o_obj = take((size_t)B * 8);
     const size_t o_status = take((size_t)B * 4), o_sweeps = take((size_t)B * 4), o_iters = take((size_t)B * 4);
     const size_t o_contact = take((size_t)B * h->cw * 4), o_active = take((size_t)B * h->aw * 4);
-    const size_t o_list = take((size_t)B * 4), o_count = take(256), o_sig = take((size_t)B * 4 * N);
+    const size_t o_list = take((size_t)B * 4), o_count = take(256), o_sig = take((size_t)B * 4 * N), o_canary = take(256);
     h->block_bytes = off;
     CUH(cudaMalloc(&h->d_block, off));
     CUH(cudaMemset(h->d_block, 0, off));
@@ -406,6 +409,11 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     h->st.fb_list = (int32_t*)(base + o_list); h->st.fb_count = (int32_t*)(base + o_count);
     h->ctr_base = h->st.fb_count; h->st.fb_next = nullptr;
     h->st.sig = (uint8_t*)(base + o_sig);
+#ifdef MPCQP_CANARY
+    h->st.canary = (unsigned int*)(base + o_canary);
+#else
+    h->st.canary = nullptr; (void)o_canary;
+#endif
     CUH(cudaMemset(h->st.sig, SIG_FREE, (size_t)B * 4 * N));
     int ric_per_sm = 0, ipm_per_sm = 0;
     const int cap = ric_capacity(N);
@@ -420,7 +428,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
         h->ric_max_ctas = ric_per_sm * h->sms;
         h->ipm_max_ctas = ipm_per_sm * h->sms;
         const int slots = h->ric_max_ctas > h->ipm_max_ctas ? h->ric_max_ctas : h->ipm_max_ctas;
-        h->ric_ws_doubles = (size_t)slots * RIC_PER_CTA * (RIC_GAIN + 4 * RIC_ADM) * cap;
+        h->ric_ws_doubles = (size_t)slots * RIC_PER_CTA * ric_ws_slot_doubles(cap);
         CUH(cudaMalloc(&h->d_ric_ws, 3 * h->ric_ws_doubles * sizeof(double)));
     }
     if (!(p->mode & MPCQP_MODE_ACTIVE_SET)) {
@@ -905,6 +913,18 @@ int mpcqp_result_wait(mpcqp_handle* h, int slot, double* forces) {
     std::memcpy(forces, h->pin[slot], (size_t)h->p.batch * 12 * sizeof(double));
     return MPCQP_OK;
 }
+
+#ifdef MPCQP_CANARY
+// debug build only (`make canary`): read (and clear) the guard-word / invariant violation counters of the stage-wise kernels
+int mpcqp_debug_canary(mpcqp_handle* h, unsigned int* out8) {
+    if (!h || !out8) return fail(MPCQP_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->p.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out8, h->st.canary, sizeof(unsigned int) * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(h->st.canary, 0, sizeof(unsigned int) * 8));
+    return MPCQP_OK;
+}
+#endif
 
 #ifdef MPCQP_PROFILE
 // debug builds only: read (and clear) the per-phase cycle counters

@@ -62,6 +62,7 @@ struct DevState {
     uint32_t* active;   // B x ceil(20N/32)
     int32_t* fb_list;   // fallback queue (instance ids)
     int32_t* fb_count;  // its length
+    unsigned int* canary;   // debug build (MPCQP_CANARY): 8 violation counters, null otherwise
     int32_t* fb_next;   // the next tick's copy of {fb_count, three work counters}: zeroed by this tick's stage-wise launch on the main stream (null: not this launch)
 };
 

@@ -65,6 +65,14 @@ namespace mpcqp {
 }  // namespace mpcqp
 #include "mpcqp_ric_consts.h"
 namespace mpcqp {
+#ifdef MPCQP_CANARY
+// DevState.canary: [0] a shared-memory guard word was overwritten, [1] the guard behind a slot's gains, [2] behind its
+// interior-point state, [3] an index invariant failed (queue slot / robot id out of range)
+constexpr unsigned long long RIC_CANARY_WORD = 0xC0FFEE0DDEADBEEFull;
+#define RIC_GUARD(name) alignas(16) unsigned long long name[2];
+#else
+#define RIC_GUARD(name)
+#endif
 constexpr int RIC_DEPTH = 4;        // stages of gains the forward pass keeps in flight from the workspace
 
 // cost-to-go of one stage, row major 6x6 blocks (double-buffered: stage k reads one, writes the other)
@@ -78,34 +86,72 @@ struct alignas(16) RicInst {
     static constexpr int ROUNDS = NF / 16;                     // feet per lane
     static constexpr int AW = (20 * N + 31) / 32, CW = (4 * N + 31) / 32;
     double xr[12 * (N + 1)];            // xref of this robot
+    RIC_GUARD(g0)
     union {
         double fs[20 * 13];             // fsteps (dead after decode)
         double E[21 * N];               // per sweep: packed lower triangles of the 6x6 blocks E_k; once the
                                         // backward pass is done the same bytes hold the sweep's forces (3 x NF)
     };
+    RIC_GUARD(g1)
     double lev[3 * NF];                 // lever arms foothold - xref[0:3, k], struct of arrays
+    RIC_GUARD(g2)
     double Ii[9 * N];                   // inv(R_z(yaw_k) gI) per step, row major
+    RIC_GUARD(g3)
     union {
         double beta[6 * N];             // ubar_k + g (dead once the forward pass is done)
         double lam[6 * N];              // velocity costates lam^v_1..lam^v_N (written by the costate pass that follows it)
     };
+    RIC_GUARD(g4)
     union {
         double xst[12 * N];             // states x_1..x_N of the forward pass
         ScenarioSmem sc;                // planner scratch of the device-resident closed loop (dead after the inputs exist)
     };
+    RIC_GUARD(g5)
     RicCost cost[2];
+    RIC_GUARD(g6)
     double T[36];                       // E_k L, row major
     double hp[6];
     double xnext[12];
+    RIC_GUARD(g7)
     unsigned long long hist[16];        // hashes of the signatures already tried
     unsigned long long mbar;
     unsigned int amask[AW + CW];
     uint8_t sigb[NF];                   // per foot-step: signature of the sweep being assembled | contact << 7
+    RIC_GUARD(g8)
     static_assert(21 * N >= 260 && 21 * N >= 12 * N, "union sizing");
     static_assert(12 * N * 8 >= sizeof(ScenarioSmem), "union sizing");
 };
 
 #define RIC_TI(r, c) ((r) * ((r) + 1) / 2 + (c))
+
+#ifdef MPCQP_CANARY
+// one lane per half-warp arms / checks the guards of its robot's shared memory and workspace slot
+template <int N>
+__device__ void canary_arm(RicInst<N>& sm, double* ws) {
+    unsigned long long* g[9] = {sm.g0, sm.g1, sm.g2, sm.g3, sm.g4, sm.g5, sm.g6, sm.g7, sm.g8};
+    for (int i = 0; i < 9; ++i) { g[i][0] = RIC_CANARY_WORD; g[i][1] = ~RIC_CANARY_WORD; }
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(ws + (size_t)RIC_GAIN * N);
+    unsigned long long* b = reinterpret_cast<unsigned long long*>(ws + (size_t)ric_ws_slot_doubles(N) - RIC_WS_PAD);
+    a[0] = RIC_CANARY_WORD; a[1] = ~RIC_CANARY_WORD; b[0] = RIC_CANARY_WORD; b[1] = ~RIC_CANARY_WORD;
+}
+template <int N>
+__device__ void canary_check(const RicInst<N>& sm, const double* ws, unsigned int* g_canary_errors) {
+    const unsigned long long* g[9] = {sm.g0, sm.g1, sm.g2, sm.g3, sm.g4, sm.g5, sm.g6, sm.g7, sm.g8};
+    for (int i = 0; i < 9; ++i)
+        if (g[i][0] != RIC_CANARY_WORD || g[i][1] != ~RIC_CANARY_WORD) atomicAdd(&g_canary_errors[0], 1u);
+    const unsigned long long* a = reinterpret_cast<const unsigned long long*>(ws + (size_t)RIC_GAIN * N);
+    const unsigned long long* b = reinterpret_cast<const unsigned long long*>(ws + (size_t)ric_ws_slot_doubles(N) - RIC_WS_PAD);
+    if (a[0] != RIC_CANARY_WORD || a[1] != ~RIC_CANARY_WORD) atomicAdd(&g_canary_errors[1], 1u);
+    if (b[0] != RIC_CANARY_WORD || b[1] != ~RIC_CANARY_WORD) atomicAdd(&g_canary_errors[2], 1u);
+}
+#define RIC_CANARY_ARM() do { if (hl == 0) canary_arm<N>(sm, ws); __syncwarp(); } while (0)
+#define RIC_CANARY_CHECK() do { __syncwarp(); if (hl == 0) canary_check<N>(sm, ws, st.canary); } while (0)
+#define RIC_INVARIANT(cond) do { if (!(cond)) atomicAdd(&st.canary[3], 1u); } while (0)
+#else
+#define RIC_CANARY_ARM() do {} while (0)
+#define RIC_CANARY_CHECK() do {} while (0)
+#define RIC_INVARIANT(cond) do {} while (0)
+#endif
 
 // The two robots of a warp run CONVERGED: one instruction stream, full-mask collectives, shuffles of width 16.
 constexpr unsigned RIC_FULL = 0xffffffffu;
@@ -1006,8 +1052,9 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
     const int sub = lane >> 4, hl = lane & 15;
     const int gwarp = blockIdx.x * RIC_WARPS + warp;
     S& sm = reinterpret_cast<S*>(smem_raw)[warp * 2 + sub];
-    double* ws = ws_g + (size_t)(gwarp * 2 + sub) * (RIC_GAIN + 4 * RIC_ADM) * N;      // per half-warp: stage gains, then interior-point state
+    double* ws = ws_g + (size_t)(gwarp * 2 + sub) * ric_ws_slot_doubles(N);      // per half-warp: stage gains, then interior-point state
     if (hl == 0) mbar_init(&sm.mbar, 1);
+    RIC_CANARY_ARM();
     // the fallback kernel behind this one is launched programmatically dependent: let it become resident (its prologue runs, then it
     // blocks in griddepcontrol.wait) as the CTAs of this persistent grid retire, instead of after the grid has drained
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -1054,12 +1101,17 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
         const bool pushed = valid && !done && !any_bad && has_fallback;
         if (pushed && hl == 0) {
             const int q = atomicAdd(st.fb_count, 1);
+            RIC_INVARIANT(q >= 0 && q < P.batch && inst >= 0 && inst < P.batch);
             st.fb_list[q] = inst;
             st.sweeps[inst] = sweeps;
         }
         RPROF(15);
         ric_finish<N>(P, SC, sm, st, inst, sub, hl, n, conbits, sg, done, status, sweeps, 0, nullptr, valid && !pushed);
         RPROF(16);
+#ifdef MPCQP_CANARY
+        if (P.refine == 77 && hl == 0 && inst == 0) sm.xst[12 * N] = 1.0;      // self-test of the detector: one element past the states
+#endif
+        RIC_CANARY_CHECK();
     }
 }
 
@@ -1081,10 +1133,11 @@ ipm_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ 
     const int sub = lane >> 4, hl = lane & 15;
     const int gwarp = blockIdx.x * RIC_WARPS + warp;
     S& sm = reinterpret_cast<S*>(smem_raw)[warp * 2 + sub];
-    double* ws = ws_g + (size_t)(gwarp * 2 + sub) * (RIC_GAIN + 4 * RIC_ADM) * N;
-    double* adm = ws + (size_t)RIC_GAIN * N;
+    double* ws = ws_g + (size_t)(gwarp * 2 + sub) * ric_ws_slot_doubles(N);
+    double* adm = ws + (size_t)RIC_GAIN * N + RIC_WS_PAD;
     if (hl == 0) mbar_init(&sm.mbar, 1);
     __syncwarp();
+    RIC_CANARY_ARM();
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int n_work = *st.fb_count;
     unsigned int phase = 0;
@@ -1146,8 +1199,10 @@ ipm_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ 
         }
         ric_sweep<N>(P, sm, ws, sub, hl, n, conbits, sg, nsg, adm);
         if (any_bad) status = 3;
+        RIC_INVARIANT(inst >= 0 && inst < P.batch);
         ric_finish<N>(P, SC, sm, st, inst, sub, hl, n, any_bad ? 0u : conbits, sg, (done || failed) && !any_bad, status, sweeps, iters,
                       failed ? adm : nullptr, valid);
+        RIC_CANARY_CHECK();
     }
 }
 

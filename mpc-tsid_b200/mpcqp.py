@@ -14,7 +14,8 @@ MODE_STAGEWISE = 4           # active-set stage on the stage-wise (Riccati) fact
 MODE_IPM = 8                 # fallback stage of the stage-wise path: interior-point iterations on the same factorisation (any horizon)
 STATUS = {0: "unsolved", 1: "solved", 2: "max_iter", 3: "bad_input"}
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmpcqp.so")
+# MPCQP_LIB selects another build of the same library (the debug build libmpcqp_canary.so of `make canary`)
+_LIB_PATH = os.environ.get("MPCQP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmpcqp.so")
 
 # every symbol include/mpcqp.h declares (tests check that the built library exports all of them)
 EXPORTS = (

@@ -1,0 +1,116 @@
+"""Memory-safety and race evidence without compute-sanitizer (closed on the B200 pool):
+
+1. the debug build (`make canary` -> libmpcqp_canary.so: guard words between every shared-memory array of a robot and behind
+   both halves of its workspace slot, index invariants, all counted on the device) runs every solver path and horizon class
+   with zero violations -- and the detector is shown to fire when a kernel is made to write one element too far;
+2. racecheck in spirit: results must not depend on how robots are scheduled -- occupancy, batch order, neighbours in the
+   warp, batch size -- bit for bit.  A race between the two robots of a warp, between warps sharing a workspace slot, or a read
+   of another robot's shared memory would show up as a dependence on exactly these."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CANARY = os.path.join(ROOT, "mpc-tsid_b200", "libmpcqp_canary.so")
+
+_SCRIPT = r"""
+import ctypes, sys
+import numpy as np
+sys.path.insert(0, %(root)r + "/mpc-tsid_b200"); sys.path.insert(0, %(root)r)
+import mpcqp
+from scenario import Scenario
+lib = mpcqp.load()
+assert hasattr(lib, "mpcqp_debug_canary"), "not the canary build"
+def counters(eng):
+    out = (ctypes.c_uint * 8)()
+    assert lib.mpcqp_debug_canary(eng._h, out) == 0
+    return list(out)
+total = [0] * 8
+for mode, n, B, kw in ((13, 16, 37, {}), (13, 16, 9, {"max_sweeps": 0}), (13, 24, 11, {}), (13, 32, 9, {"max_sweeps": 0}),
+                       (13, 64, 5, {}), (13, 64, 4, {"max_sweeps": 1, "ipm_max_iter": 3}), (13, 5, 7, {})):
+    dt, T_gait = (0.02, 0.32) if n != 24 else (0.02, 0.48)
+    sc = Scenario(B, n_steps=n, dt=dt, T_gait=T_gait, gaits=["trot", "walk", "pace", "bound"], seed=5)
+    eng = mpcqp.Engine(batch=B, n_steps=n, mode=mode, dt=dt, T_gait=T_gait, **kw)
+    for t in range(4):
+        xref, fsteps = sc.inputs()
+        eng.run(t, xref, fsteps)
+        x = eng.solution()
+        assert np.isfinite(x).all()
+        sc.advance(x[:, :12] + xref[:, :, 1])
+    c = counters(eng)
+    total = [a + b for a, b in zip(total, c)]
+    eng.close()
+sc = Scenario(40, gaits=["trot", "bound", "walk"], seed=9, noise_kind="hash")
+eng = mpcqp.Engine(batch=40)
+eng.scenario_init(sc)
+eng.scenario_run(6)
+eng.synchronize()
+total = [a + b for a, b in zip(total, counters(eng))]
+eng.close()
+print("CLEAN", total)
+# the detector itself: refine = 77 makes robot 0 write one element past its state array in the debug build
+sc = Scenario(4, gaits="trot", seed=1)
+eng = mpcqp.Engine(batch=4, refine=77)
+xref, fsteps = sc.inputs()
+eng.run(0, xref, fsteps)
+eng.run(1, xref, fsteps)
+eng.synchronize()
+print("TRIPPED", counters(eng))
+eng.close()
+"""
+
+
+def test_canary_build_is_clean_and_its_detector_fires():
+    if not os.path.exists(CANARY):
+        pytest.skip("libmpcqp_canary.so not built (make -C mpc-tsid_b200/csrc canary)")
+    env = dict(os.environ, MPCQP_LIB=CANARY)
+    out = subprocess.run([sys.executable, "-c", _SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    lines = {ln.split()[0]: eval(ln[ln.index("["):]) for ln in out.stdout.splitlines() if ln.startswith(("CLEAN", "TRIPPED"))}
+    assert lines["CLEAN"] == [0] * 8, lines
+    assert lines["TRIPPED"][0] >= 1 and lines["TRIPPED"][1:] == [0] * 7, lines
+
+
+@pytest.mark.parametrize("n,kw", [(16, {}), (16, {"max_sweeps": 0}), (24, {}), (64, {})], ids=["N16", "N16-ipm", "N24", "N64"])
+def test_results_do_not_depend_on_scheduling(n, kw):
+    import mpcqp
+    from scenario import Scenario
+    B = 301
+    dt, T_gait = (0.02, 0.32) if n != 24 else (0.02, 0.48)
+    if n == 64:
+        B = 93
+    sc = Scenario(B, n_steps=n, dt=dt, T_gait=T_gait, gaits=["trot", "pace", "bound", "walk"], seed=41)
+    ticks = []
+    ref = mpcqp.Engine(batch=B, n_steps=n, dt=dt, T_gait=T_gait, **kw)
+    for t in range(3):
+        xref, fsteps = sc.inputs()
+        ref.run(t, xref, fsteps)
+        x = ref.solution()
+        ticks.append((xref, fsteps, x.copy(), ref.info()))
+        sc.advance(x[:, :12] + xref[:, :, 1])
+    ref.close()
+
+    def replay(perm, batch_kw):
+        eng = mpcqp.Engine(batch=len(perm), n_steps=n, dt=dt, T_gait=T_gait, **kw, **batch_kw)
+        for t, (xref, fsteps, x, info) in enumerate(ticks):
+            eng.run(t, np.ascontiguousarray(xref[perm]), np.ascontiguousarray(fsteps[perm]))
+            got, gi = eng.solution(), eng.info()
+            np.testing.assert_array_equal(got, x[perm])
+            np.testing.assert_array_equal(gi["sweeps"], info["sweeps"][perm])
+            np.testing.assert_array_equal(gi["iters"], info["iters"][perm])
+            np.testing.assert_array_equal(gi["y"], info["y"][perm])
+        eng.close()
+
+    rng = np.random.default_rng(0)
+    replay(np.arange(B)[::-1].copy(), {})                      # other neighbours in every warp
+    replay(rng.permutation(B), {})
+    replay(np.arange(0, B, 7), {})                             # another batch size: other robots, other tail
+    os.environ["MPCQP_RIC_CTAS"] = "1"                         # one warp per SM: another interleaving of everything
+    try:
+        replay(np.arange(B), {})
+    finally:
+        del os.environ["MPCQP_RIC_CTAS"]

@@ -6,10 +6,10 @@ import numpy as np
 sys.path.insert(0, "/root/repo/mpc-tsid_b200"); sys.path.insert(0, "/root/repo")
 import mpcqp
 from scenario import Scenario
-for mode, n in ((7, 16), (3, 16), (2, 16), (7, 32)):
+for mode, n in ((13, 16), (-13, 16), (7, 16), (3, 16), (2, 16), (13, 24), (-13, 64)):
     B = 6
     sc = Scenario(B, n_steps=n, gaits=["trot", "walk", "pace"], seed=5)
-    eng = mpcqp.Engine(batch=B, n_steps=n, mode=mode)
+    eng = mpcqp.Engine(batch=B, n_steps=n, mode=abs(mode), **({'max_sweeps': 0} if mode < 0 else {}))       # mode < 0: every robot through ipm_kernel
     for t in range(4):
         xref, fsteps = sc.inputs()
         eng.run(t, xref, fsteps)
