@@ -73,9 +73,21 @@ def cpu_arm(steps, warmup, cores=None):
         recs = list(pool.map(_record_closed_loop, [(w, T) for w in range(distinct)]))
     xr = np.stack([recs[i % distinct][0] for i in range(cores)])
     fs = np.stack([recs[i % distinct][1] for i in range(cores)])
-    wall, _, iters = c_port.replay_mt(xr, fs, warm=warmup, n_steps=N_STEPS, eps=1e-8)
+    wall, f_ref, iters = c_port.replay_mt(xr, fs, warm=warmup, n_steps=N_STEPS, eps=1e-8)
+    # the same replay with the cost scale OSQP would pick if it left the (all-zero) q out of its rule: context for the ratio, since
+    # the faithful rule costs ~20x more ADMM iterations on this QP (tools/baseline_experiments.py)
+    c_port.set_cost_scaling_variant(True)
+    try:
+        wall_v, f_var, iters_v = c_port.replay_mt(xr, fs, warm=warmup, n_steps=N_STEPS, eps=1e-8)
+    finally:
+        c_port.set_cost_scaling_variant(False)
     return dict(value=cores * steps / wall, unit=UNIT, cores=cores, kind="port",
                 osqp_iterations_per_solve=iters, eps=1e-8,
+                cost_scaled_variant={"value": cores * steps / wall_v, "unit": UNIT, "osqp_iterations_per_solve": iters_v,
+                                     "max_force_difference_N": float(np.abs(f_ref[:, warmup:] - f_var[:, warmup:]).max()),
+                                     "what": "same replay, cost scale c = 1 / mean column norm of P instead of OSQP's published rule "
+                                             "(which treats the reference's q = 0 as 1 and leaves c = 1): NOT the reference's behaviour, "
+                                             "shown because the GPU / CPU ratio moves ~20x with it"},
                 sample="%d host threads x %d consecutive closed-loop trot ticks each (after %d untimed warm-up ticks; %d distinct "
                        "robots) through oracle/mpc_osqp.c = C restatement of MPC.py's build + the OSQP algorithm (sparse LDL', "
                        "Ruiz scaling, adaptive rho, warm start) at eps 1e-8, polish off; the reference's own build half is "

@@ -91,6 +91,12 @@ class MPC:
         return dict(x=x, y=y, f=f, iter=int(info[0]), status=int(info[1]), rho_updates=int(info[2]), factorizations=int(info[3]))
 
 
+def set_cost_scaling_variant(ignore_zero_q):
+    """False (default): OSQP's published rule (a zero q counts as 1: cost scale 1 for the reference's QP).  True: leave a zero q
+    out (cost scale 1 / mean column norm of P).  Process-wide."""
+    load().mpc_oracle_set_cost_scaling_variant(1 if ignore_zero_q else 0)
+
+
 def replay_mt(xref, fsteps, warm, n_steps=16, dt=0.02, eps=1e-8):
     """`threads` robots, one per host thread, each replaying its own recorded input sequence.
     xref (threads, T, 12, N+1), fsteps (threads, T, 20, 13).  -> (seconds of the slowest thread over its

@@ -220,6 +220,11 @@ typedef struct {
 } osqp_t;
 
 static double limit_scaling(double v) { v = v < MIN_SCALING ? 1.0 : v; return v > MAX_SCALING ? MAX_SCALING : v; }
+/* 0 (default): OSQP's cost scaling as published -- ||q||_inf below 1e-4 counts as 1, so with the reference's q = 0 (MPC.py:286-288)
+ * the cost scale stays c = 1 and ADMM needs ~1000 iterations at eps 1e-8.  1: a zero q is left out of the max, c = 1 / mean column
+ * norm of P (~6e3 here) and ~50 iterations suffice -- what a cost-scaled OSQP WOULD do, reported next to the faithful arm. */
+static int g_ignore_zero_q = 0;
+void mpc_oracle_set_cost_scaling_variant(int ignore_zero_q) { g_ignore_zero_q = ignore_zero_q; }
 static double scale_bound(double b, double e) { return fabs(b) < OSQP_INFTY ? e * b : b; }
 
 static void osqp_scale(osqp_t* s) {
@@ -255,7 +260,7 @@ static void osqp_scale(osqp_t* s) {
         }
         for (int i = 0; i < m; ++i) s->E[i] *= e[i];
         mean_P = limit_scaling(n ? mean_P / n : 0.0);
-        norm_q = limit_scaling(norm_q);
+        norm_q = (g_ignore_zero_q && norm_q == 0.0) ? 0.0 : limit_scaling(norm_q);
         const double ci = 1.0 / (mean_P > norm_q ? mean_P : norm_q);
         for (int j = 0; j < n; ++j) { s->P[j] *= ci; s->q[j] *= ci; }
         s->c *= ci;
