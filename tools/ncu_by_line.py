@@ -69,6 +69,7 @@ print("kernel:", sec["name"][:80], " total samples", tot)
 allst = collections.Counter()
 for a in agg.values(): allst.update(a[2])
 print("stall mix:", ", ".join("%s %.1f%%" % (k[6:], 100 * v / sum(allst.values())) for k, v in allst.most_common(8)))
-for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+TOP = int(os.environ.get("NCU_BY_LINE_TOP", "40"))
+for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:TOP]:
     top = ",".join("%s:%.0f%%" % (k[6:], 100 * v / max(1, sum(a[2].values()))) for k, v in a[2].most_common(2))
     print("%5.1f%%  inst %9.0f  %s:%d  [%s]  %s" % (100 * a[0] / tot, a[1], loc[0], loc[1], top, src(loc)))
