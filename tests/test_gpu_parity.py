@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 import mpcqp
+import batch_kkt
 from common import FORCE_TOL, OBJ_RTOL, assert_certified, certify
 from scenario import Scenario
 
@@ -218,6 +219,7 @@ def test_aggressive_cold_starts_are_solved(n):
         eng.run(t, xref, fsteps)
         x, info = eng.solution(), eng.info()
         assert (info["status"] == 1).all(), (t, np.flatnonzero(info["status"] != 1), info["sweeps"].max(), info["iters"].max())
+        batch_kkt.assert_batch_certified(batch_kkt.certificate(xref, fsteps, x, info["y"], par, first_tick=(t == 0)), "tick %d" % t)   # every robot
         for b in range(0, B, 37):
             assert_certified(certify(xref[b], fsteps[b], x[b], info["y"][b], first_tick=(t == 0), params=par), "tick %d robot %d" % (t, b))
         sc.advance(x[:, :12] + xref[:, :, 1])
@@ -416,8 +418,9 @@ def test_engine_against_an_independent_solver():
 
 
 def test_full_batch_properties():
-    """BASELINE configs[1] size (4096 robots): determinism, warm-start invariance, KKT on a sample,
-    friction / unilateral / fz_max feasibility everywhere, objective consistent with x."""
+    """BASELINE configs[1] size (4096 robots): EVERY robot of every tick passes the vectorised KKT certificate (tests/batch_kkt.py,
+    pinned to the oracle's sparse certificate by tests/test_batch_kkt.py), the oracle's own certificate on a sample, warm-start
+    invariance, friction / unilateral / fz_max feasibility everywhere, objective consistent with x."""
     B = 4096
     eng = mpcqp.Engine(batch=B)
     sc = Scenario(B, gaits="trot", seed=20260)
@@ -433,6 +436,9 @@ def test_full_batch_properties():
         assert (f[..., 2] >= -1e-9).all() and (f[..., 2] <= 25 + 1e-8).all()
         assert (f[~info["contact"]] == 0).all()
         np.testing.assert_allclose(info["obj"], 0.5 * (x * x * w).sum(axis=1), rtol=1e-12)
+        cert = batch_kkt.certificate(xref, fsteps, x, info["y"], first_tick=(t == 0))
+        batch_kkt.assert_batch_certified(cert, "tick %d" % t)
+        np.testing.assert_array_equal(cert["contact"], info["contact"])
         if t == 4:
             for b in range(0, B, 173):
                 assert_certified(certify(xref[b], fsteps[b], x[b], info["y"][b]), "robot %d" % b)
@@ -533,6 +539,8 @@ def test_mixed_gait_sweep_on_device():
     expect = np.take_along_axis(sc.seq, idx[:, :, None], axis=1) == 1.0
     np.testing.assert_array_equal(info["contact"], expect)
     xref, fsteps = eng.last_inputs()
+    cert = batch_kkt.certificate(xref, fsteps, x, info["y"])                  # all 65 536 robots
+    batch_kkt.assert_batch_certified(cert, "mixed sweep")
     for b in range(0, B, 4099):
         assert_certified(certify(xref[b], fsteps[b], x[b], info["y"][b]), "robot %d" % b)
     eng.close()
