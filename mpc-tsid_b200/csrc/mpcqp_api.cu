@@ -422,6 +422,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     if (cap == 16) CUH(ric_configure_16(&ric_per_sm, &ipm_per_sm));
     else if (cap == 32) CUH(ric_configure_32(&ric_per_sm, &ipm_per_sm));
     else CUH(ric_configure_64(&ric_per_sm, &ipm_per_sm));
+    if (std::getenv("MPCQP_VERBOSE")) std::fprintf(stderr, "mpcqp: stage-wise kernels fit %d (active-set) / %d (interior-point) CTAs per SM\n", ric_per_sm, ipm_per_sm);
     if (const char* e = std::getenv("MPCQP_RIC_CTAS")) { const int c = std::atoi(e); if (c > 0 && c < ric_per_sm) ric_per_sm = c; }      // tuning hook
     if (p->mode & MPCQP_MODE_STAGEWISE) {
         if (ric_per_sm < 1 || ipm_per_sm < 1) return bail(fail(MPCQP_ERR_CUDA, "the stage-wise kernel does not fit on this device"));

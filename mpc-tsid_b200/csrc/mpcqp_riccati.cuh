@@ -1040,8 +1040,11 @@ __device__ __forceinline__ bool ric_load_decode(const DevParams& P, const DevSce
 // fallback stage the mode selects: ipm_kernel below (MPCQP_MODE_IPM) or the dense ADMM kernel (MPCQP_MODE_ADMM, N <= 32).
 // FULL: the horizon fills the capacity (n = N is a compile-time constant: the headline horizons 16, 32, 64 keep static index
 // arithmetic); otherwise n = P.N < N at run time.
+#ifndef RIC_MIN_CTAS
+#define RIC_MIN_CTAS 1          // tuning hook: a larger value caps the registers (12 -> 168 registers, three warps per scheduler)
+#endif
 template <int N, bool FULL>
-__global__ void __launch_bounds__(32 * RIC_WARPS)
+__global__ void __launch_bounds__(32 * RIC_WARPS, RIC_MIN_CTAS)
 riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ xref_g, const double* __restrict__ fsteps_g,
                double* __restrict__ ws_g, int* __restrict__ work_ctr, int first_tick, int inst_offset, int inst_count) {
     using S = RicInst<N>;
