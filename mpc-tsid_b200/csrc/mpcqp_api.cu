@@ -80,7 +80,7 @@ namespace mpcqp {
     void ric_launch_##N(int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,      \
                         const double* dx, const double* df, double* ws, int* ctr, int first, int off, int n_inst);     \
     void ipm_launch_##N(int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,      \
-                        const double* dx, const double* df, double* ws, int first);
+                        const double* dx, const double* df, double* ws, int first, int pdl);
 RIC_DECL(16) RIC_DECL(32) RIC_DECL(64)
 #undef RIC_DECL
 }  // namespace mpcqp
@@ -105,10 +105,10 @@ cudaError_t launch_stagewise(int cap, int n_inst, int max_ctas, cudaStream_t s, 
 }
 
 void launch_ipm(int cap, int max_ctas, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc,
-                const double* dx, const double* df, double* ws, int first) {
-    if (cap == 16) ipm_launch_16(max_ctas, s, dp, st, sc, dx, df, ws, first);
-    else if (cap == 32) ipm_launch_32(max_ctas, s, dp, st, sc, dx, df, ws, first);
-    else ipm_launch_64(max_ctas, s, dp, st, sc, dx, df, ws, first);
+                const double* dx, const double* df, double* ws, int first, int pdl) {
+    if (cap == 16) ipm_launch_16(max_ctas, s, dp, st, sc, dx, df, ws, first, pdl);
+    else if (cap == 32) ipm_launch_32(max_ctas, s, dp, st, sc, dx, df, ws, first, pdl);
+    else ipm_launch_64(max_ctas, s, dp, st, sc, dx, df, ws, first, pdl);
 }
 
 template <int N>
@@ -128,13 +128,21 @@ void launch_solve(bool admm, int grid, cudaStream_t s, const DevParams& dp, cons
     else solve_kernel<N, false><<<grid, 32 * Cfg<N>::NW, sizeof(Smem<N, false>), s>>>(dp, st, sc, dx, df, first, off, n);
 }
 
+constexpr int MAX_RANGES = 4;        // index ranges of a batch that may advance through the ticks independently (mpcqp_set_overlap)
+
 struct mpcqp_handle {
     mpcqp_params p;
     DevParams dp;
     DevState st;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[2] = {nullptr, nullptr};      // host-input runs: copy + solve of alternate chunks overlap
-    cudaEvent_t ev_main = nullptr, ev_side[2] = {nullptr, nullptr};
+    // side streams.  Host-input runs: copy + solve of alternate chunks overlap on side[0], side[1] (joined every tick).
+    // Overlapped index ranges: range r lives on side[r] from tick to tick with its own counters, queue region and workspace.
+    cudaStream_t side[MAX_RANGES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_main = nullptr, ev_side[MAX_RANGES] = {nullptr, nullptr, nullptr, nullptr};
+    int ranges = 0;                 // mpcqp_set_overlap: 0 = automatic inside mpcqp_scenario_run only, 1 = off, 2 .. MAX_RANGES
+    bool forked = false;            // ranges are in flight on the side streams: the main stream has not been joined yet
+    int forked_ranges = 0;
+    int rparity[MAX_RANGES] = {0, 0, 0, 0};
     double* d_xref = nullptr;
     double* d_fsteps = nullptr;
     double* d_Minv = nullptr;
@@ -149,6 +157,7 @@ struct mpcqp_handle {
     bool zero_next = false;         // set by solve(): a main-stream stage-wise launch of this tick zeroes the next tick's copy
     int64_t launches = 0;
     int sms = 0;
+    int last_ranges = 1;            // how the last tick was issued (mpcqp_get_fallback_count sums the ranges' queues)
 
     double* pin[2] = {nullptr, nullptr};            // asynchronous result slots (pinned host memory)
     cudaEvent_t ev_pin[2] = {nullptr, nullptr};
@@ -171,7 +180,7 @@ struct mpcqp_handle {
         use.enabled = closed_loop ? 1 : 0;
         if (admm && fallback_is_ipm()) {
             // the main stream's workspace: every active-set launch of this tick has been joined into `s` by now
-            launch_ipm(ric_capacity(p.n_steps), ipm_max_ctas, s, dp, st, use, dx, df, d_ric_ws, first);
+            launch_ipm(ric_capacity(p.n_steps), ipm_max_ctas, s, dp, st, use, dx, df, d_ric_ws, first, 1);
         } else if (!admm && (p.mode & MPCQP_MODE_STAGEWISE)) {
             // active-set stage on the stage-wise factorisation: half a warp per robot, persistent grid; every stream
             // that may run it concurrently has its own gain workspace
@@ -185,6 +194,44 @@ struct mpcqp_handle {
         } else if (p.n_steps == 16) launch_solve<16>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         else launch_solve<32>(admm, grid, s, dp, st, use, dx, df, first, off, n);
         ++launches;
+    }
+    // One tick of index range r = robots off .. off + n - 1 on its own stream: the active-set kernel, then (ordinary launch: its CTAs
+    // must not sit resident while the range's last sweeps finish) the interior-point kernel over the range's own fallback queue.
+    // Counters: 16 ints per range behind the main stream's (two copies of {queue length, work counter, 0, 0}, alternating by tick;
+    // the active-set kernel clears the copy of the next tick); queue: the range's slice of fb_list; workspace copy 1 + r.
+    void solve_range(int r, int off, int n, const double* dx, const double* df, int first, bool closed_loop) {
+        DevScenario use = sc;
+        use.enabled = closed_loop ? 1 : 0;
+        int32_t* ctr = ctr_base + 16 + 16 * r;
+        rparity[r] ^= 1;
+        DevState stl = st;
+        stl.fb_count = ctr + 8 * rparity[r];
+        stl.fb_next = ctr + 8 * (rparity[r] ^ 1);
+        stl.fb_list = st.fb_list + off;
+        double* ws = d_ric_ws + (size_t)(1 + r) * ric_ws_doubles;
+        const int cap = ric_capacity(p.n_steps);
+        const cudaError_t e = launch_stagewise(cap, n, ric_max_ctas, side[r], dp, stl, use, dx, df, ws, stl.fb_count + 1, false, first, off);
+        if (e != cudaSuccess && launch_err == cudaSuccess) launch_err = e;
+        ++launches;
+        if (fallback_is_ipm()) {
+            const int want = (n + RIC_PER_CTA - 1) / RIC_PER_CTA;
+            launch_ipm(cap, want < ipm_max_ctas ? want : ipm_max_ctas, side[r], dp, stl, use, dx, df, ws, first, 0);
+            ++launches;
+        }
+    }
+    // ranges to use for a tick issued now (1 = the ordinary single-stream tick)
+    int ranges_for(bool automatic_ok) const {
+        if (!(p.mode & MPCQP_MODE_STAGEWISE) || (has_fallback() && !fallback_is_ipm())) return 1;
+        int r = ranges;
+        if (r == 0) {
+            // automatic: two ranges when the batch is between one and eight waves of resident robots -- there the last sweeps of a tick
+            // leave most of the GPU idle (a robot that needs a second sweep ends its tick a whole sweep after the others)
+            if (!automatic_ok) return 1;
+            r = (p.batch > wave() && p.batch <= 8 * wave()) ? 2 : 1;
+            if (const char* e = std::getenv("MPCQP_RANGES")) { const int c = std::atoi(e); if (c >= 1 && c <= MAX_RANGES) r = c; }      // tuning hook
+        }
+        while (r > 1 && p.batch < 2 * RIC_PER_CTA * r) --r;
+        return r;
     }
     int ctas_per_sm(bool admm) const { return p.n_steps == 16 ? (admm ? 2 : 4) : 1; }
     // robots of the active-set stage that are resident at once (one wave)
@@ -270,8 +317,8 @@ int mpcqp_destroy(mpcqp_handle* h) {
         if (h->pin[i]) cudaFreeHost(h->pin[i]);
         if (h->ev_pin[i]) cudaEventDestroy(h->ev_pin[i]);
     }
-    for (int i = 0; i < 2; ++i) {
-        if (h->side[i]) cudaStreamDestroy(h->side[i]);
+    for (int i = 0; i < MAX_RANGES; ++i) {
+        if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
         if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
     }
     if (h->ev_main) cudaEventDestroy(h->ev_main);
@@ -370,7 +417,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
         if (e_ != cudaSuccess) return bail(fail(MPCQP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
     } while (0)
     CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < MAX_RANGES; ++i) {
         CUH(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
         CUH(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming));
     }
@@ -391,7 +438,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     const size_t o_f0 = take((size_t)B * 12 * 8), o_x1 = take((size_t)B * 12 * 8), o_qw = take((size_t)B * 6 * 8), o_obj = take((size_t)B * 8);
     const size_t o_status = take((size_t)B * 4), o_sweeps = take((size_t)B * 4), o_iters = take((size_t)B * 4);
     const size_t o_contact = take((size_t)B * h->cw * 4), o_active = take((size_t)B * h->aw * 4);
-    const size_t o_list = take((size_t)B * 4), o_count = take(256), o_sig = take((size_t)B * 4 * N), o_canary = take(256);
+    const size_t o_list = take((size_t)B * 4), o_count = take(4 * (16 + 16 * MAX_RANGES)), o_sig = take((size_t)B * 4 * N), o_canary = take(256);
     h->block_bytes = off;
     CUH(cudaMalloc(&h->d_block, off));
     CUH(cudaMemset(h->d_block, 0, off));
@@ -430,7 +477,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
         h->ipm_max_ctas = ipm_per_sm * h->sms;
         const int slots = h->ric_max_ctas > h->ipm_max_ctas ? h->ric_max_ctas : h->ipm_max_ctas;
         h->ric_ws_doubles = (size_t)slots * RIC_PER_CTA * ric_ws_slot_doubles(cap);
-        CUH(cudaMalloc(&h->d_ric_ws, 3 * h->ric_ws_doubles * sizeof(double)));
+        CUH(cudaMalloc(&h->d_ric_ws, (1 + MAX_RANGES) * h->ric_ws_doubles * sizeof(double)));
     }
     if (!(p->mode & MPCQP_MODE_ACTIVE_SET)) {
         std::vector<int32_t> all((size_t)B + 1);
@@ -440,6 +487,47 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     }
 #undef CUH
     *out = h;
+    return MPCQP_OK;
+}
+
+// Overlapped index ranges (mpcqp_set_overlap).  fork: the side streams pick up everything issued on the main stream so far.
+// join: the main stream waits for every range; every entry point that reads or changes the handle's state calls it first,
+// so results, resets and host-input runs see whole ticks.  Between fork and join a range's tick t + 1 is ordered behind its
+// own tick t only.
+static int fork_ranges(mpcqp_handle* h, int R) {
+    if (h->forked && h->forked_ranges == R) return MPCQP_OK;
+    if (h->forked) {
+        for (int r = 0; r < h->forked_ranges; ++r) {
+            CU(cudaEventRecord(h->ev_side[r], h->side[r]));
+            CU(cudaStreamWaitEvent(h->stream, h->ev_side[r], 0));
+        }
+    }
+    CU(cudaEventRecord(h->ev_main, h->stream));
+    for (int r = 0; r < R; ++r) CU(cudaStreamWaitEvent(h->side[r], h->ev_main, 0));
+    h->forked = true;
+    h->forked_ranges = R;
+    return MPCQP_OK;
+}
+static int join_ranges(mpcqp_handle* h) {
+    if (!h->forked) return MPCQP_OK;
+    for (int r = 0; r < h->forked_ranges; ++r) {
+        CU(cudaEventRecord(h->ev_side[r], h->side[r]));
+        CU(cudaStreamWaitEvent(h->stream, h->ev_side[r], 0));
+    }
+    h->forked = false;
+    return MPCQP_OK;
+}
+// one tick of the whole batch as R independent index ranges (even sizes: the two robots of a warp stay in one range)
+static int run_ranges(mpcqp_handle* h, int R, const double* dx, const double* df, int first, bool closed_loop) {
+    int rc = fork_ranges(h, R);
+    if (rc) return rc;
+    const int B = h->p.batch;
+    const int per = ((B + R - 1) / R + 1) & ~1;
+    for (int r = 0; r < R; ++r) {
+        const int off = r * per, n = B - off < per ? B - off : per;
+        if (n > 0) h->solve_range(r, off, n, dx, df, first, closed_loop);
+    }
+    h->last_ranges = R;
     return MPCQP_OK;
 }
 
@@ -490,8 +578,22 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
     const int B = h->p.batch, N = h->p.n_steps;
     const int first = (k == 0.0) ? 1 : 0;                       // MPC.py:491, 413: only k == 0 vs k > 0 matters
     const size_t xs = (size_t)12 * (N + 1), fs = 260;
-    CU(begin_tick(h));
     const bool stageA = (h->p.mode & MPCQP_MODE_ACTIVE_SET) != 0;
+    if (location == MPCQP_DEVICE && stageA) {
+        // device-resident inputs with overlap switched on: the tick is issued as independent index ranges, no join
+        const int R = h->ranges_for(false);
+        if (R > 1) {
+            const int rc = run_ranges(h, R, xref, fsteps, first, false);
+            if (rc) return rc;
+            CU(h->launch_err);
+            CU(cudaGetLastError());
+            h->ran = true;
+            return MPCQP_OK;
+        }
+    }
+    { const int rc = join_ranges(h); if (rc) return rc; }
+    h->last_ranges = 1;
+    CU(begin_tick(h));
     const double *dx = xref, *df = fsteps;
     // Host inputs: the batch is cut into chunks of two full waves (2 x 4 CTAs x #SM instances); chunk
     // c is copied and solved on side stream c & 1, so the H2D copy of one chunk overlaps the solve of
@@ -554,6 +656,7 @@ int mpcqp_get_latest_result(mpcqp_handle* h, double* forces, int location) {
     if (!h || !forces) return fail(MPCQP_ERR_INVALID, "null argument");
     if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     int rc = fetch(h, forces, h->st.f0, (size_t)h->p.batch * 12 * sizeof(double), location);
     if (rc) return rc;
     if (location == MPCQP_HOST) CU(cudaStreamSynchronize(h->stream));
@@ -568,6 +671,7 @@ int mpcqp_get_step_result(mpcqp_handle* h, double* forces, double* next_state, i
     if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
     if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "bad location");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     const size_t B = h->p.batch, row = 12 * sizeof(double);
     const cudaMemcpyKind kind = location == MPCQP_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     if (forces) CU(cudaMemcpyAsync(forces, h->st.f0, B * row, kind, h->stream));
@@ -581,6 +685,7 @@ int mpcqp_world_pose(mpcqp_handle* h, double* qw, int set, int location) {
     if (!h || !qw) return fail(MPCQP_ERR_INVALID, "null argument");
     if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "bad location");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     const size_t bytes = (size_t)h->p.batch * 6 * sizeof(double);
     if (set) CU(cudaMemcpyAsync(h->st.qw, qw, bytes, location == MPCQP_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
     else CU(cudaMemcpyAsync(qw, h->st.qw, bytes, location == MPCQP_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
@@ -593,6 +698,7 @@ int mpcqp_get_status(mpcqp_handle* h, int32_t* status, int location) {
     if (!h || !status) return fail(MPCQP_ERR_INVALID, "null argument");
     if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     int rc = fetch(h, status, h->st.status, (size_t)h->p.batch * 4, location);
     if (rc) return rc;
     if (location == MPCQP_HOST) CU(cudaStreamSynchronize(h->stream));
@@ -603,6 +709,7 @@ int mpcqp_get_solution(mpcqp_handle* h, double* x, int location) {
     if (!h || !x) return fail(MPCQP_ERR_INVALID, "null argument");
     if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     const int N = h->p.n_steps, B = h->p.batch;
     const cudaMemcpyKind kind = location == MPCQP_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "bad location");
@@ -618,6 +725,7 @@ int mpcqp_get_info(mpcqp_handle* h, int32_t* status, int32_t* sweeps, int32_t* i
     if (!h) return fail(MPCQP_ERR_INVALID, "null argument");
     if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     const size_t B = h->p.batch;
     int rc;
     if ((rc = fetch(h, status, h->st.status, B * 4, location))) return rc;
@@ -634,6 +742,16 @@ int mpcqp_get_info(mpcqp_handle* h, int32_t* status, int32_t* sweeps, int32_t* i
 int mpcqp_get_fallback_count(mpcqp_handle* h, int32_t* count) {
     if (!h || !count) return fail(MPCQP_ERR_INVALID, "null argument");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
+    if (h->last_ranges > 1) {
+        // the last tick ran as index ranges: each has its own queue
+        int32_t part[MAX_RANGES] = {0, 0, 0, 0};
+        for (int r = 0; r < h->last_ranges; ++r)
+            CU(cudaMemcpyAsync(&part[r], h->ctr_base + 16 + 16 * r + 8 * h->rparity[r], 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        *count = part[0] + part[1] + part[2] + part[3];
+        return MPCQP_OK;
+    }
     CU(cudaMemcpyAsync(count, h->st.fb_count, 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return MPCQP_OK;
@@ -642,6 +760,7 @@ int mpcqp_get_fallback_count(mpcqp_handle* h, int32_t* count) {
 int mpcqp_reset_warm_start(mpcqp_handle* h) {
     if (!h) return fail(MPCQP_ERR_INVALID, "null argument");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     const size_t B = h->p.batch, N = h->p.n_steps;
     CU(cudaMemsetAsync(h->st.f, 0, B * 12 * N * 8, h->stream));
     CU(cudaMemsetAsync(h->st.y, 0, B * 20 * N * 8, h->stream));
@@ -652,11 +771,26 @@ int mpcqp_reset_warm_start(mpcqp_handle* h) {
 int mpcqp_synchronize(mpcqp_handle* h) {
     if (!h) return fail(MPCQP_ERR_INVALID, "null argument");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     CU(cudaStreamSynchronize(h->stream));
     return MPCQP_OK;
 }
 
 void* mpcqp_stream(mpcqp_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+// Overlap of consecutive ticks (see include/mpcqp.h)
+int mpcqp_set_overlap(mpcqp_handle* h, int ranges) {
+    if (!h || ranges < 0 || ranges > MAX_RANGES) return fail(MPCQP_ERR_INVALID, "ranges must be 0 (automatic) .. 4");
+    CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
+    h->ranges = ranges;
+    return MPCQP_OK;
+}
+int mpcqp_join(mpcqp_handle* h) {
+    if (!h) return fail(MPCQP_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->p.device));
+    return join_ranges(h);
+}
 
 // page-locked host memory for the caller's input / output arrays (copies from pageable memory are staged by the driver
 // and cost ~20 % of a 4096-robot tick)
@@ -679,6 +813,7 @@ int mpcqp_export_build(mpcqp_handle* h, double k, const double* xref, const doub
                        double* B_vals, double* S_vals, double* NK) {
     if (!h || !xref || !fsteps || !B_vals || !S_vals || !NK) return fail(MPCQP_ERR_INVALID, "null argument");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     const double *dx, *df;
     int rc = stage_inputs(h, xref, fsteps, location, &dx, &df);
     if (rc) return rc;
@@ -752,6 +887,7 @@ int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* pha
     if (period < 1 || period > 16 || std::fabs(h->p.T_gait / h->p.dt - period) > 1e-9)
         return fail(MPCQP_ERR_INVALID, "closed loop needs a gait period T_gait / dt of 1 .. 16 whole steps");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     CU(cudaStreamSynchronize(h->stream));
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -803,6 +939,7 @@ int mpcqp_scenario_set_commands(mpcqp_handle* h, const double* vref, int reduced
     if (!h) return fail(MPCQP_ERR_INVALID, "null argument");
     if (!h->scen_ready) return fail(MPCQP_ERR_STATE, "mpcqp_scenario_init has not been called");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     if (vref) {
         CU(cudaMemcpyAsync((void*)h->sc.vref, vref, (size_t)h->p.batch * 6 * 8, cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));                  // the caller's buffer is free on return
@@ -820,6 +957,24 @@ int mpcqp_scenario_run(mpcqp_handle* h, int ticks, int emit_inputs) {
     if (!stageA) return fail(MPCQP_ERR_INVALID, "the closed loop needs the active-set stage enabled");
     h->sc.xref_out = emit_inputs ? h->d_xref : nullptr;
     h->sc.fsteps_out = emit_inputs ? h->d_fsteps : nullptr;
+    // every robot's tick depends on its own previous tick only (planner, solve and integration are per robot): with two or more
+    // ticks in one call the batch advances as independent index ranges, joined before the call returns
+    const int R = h->ranges_for(ticks >= 2);
+    if (R > 1 && ticks >= 1) {
+        for (int t = 0; t < ticks; ++t) {
+            h->sc.tick = h->scen_tick;
+            const int rc = run_ranges(h, R, nullptr, nullptr, h->scen_tick == 0 ? 1 : 0, true);
+            if (rc) return rc;
+            ++h->scen_tick;
+        }
+        if (h->ranges == 0) { const int rc = join_ranges(h); if (rc) return rc; }     // automatic: whole ticks at the call boundary
+        CU(h->launch_err);
+        CU(cudaGetLastError());
+        h->ran = true;
+        return MPCQP_OK;
+    }
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
+    if (ticks > 0) h->last_ranges = 1;
     for (int t = 0; t < ticks; ++t) {
         h->sc.tick = h->scen_tick;
         const int first = h->scen_tick == 0 ? 1 : 0;
@@ -840,6 +995,7 @@ int mpcqp_scenario_get(mpcqp_handle* h, double* state, double* frame, double* fe
     if (!h) return fail(MPCQP_ERR_INVALID, "null argument");
     if (!h->scen_ready) return fail(MPCQP_ERR_STATE, "mpcqp_scenario_init has not been called");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     const size_t B = h->p.batch;
     if (state) CU(cudaMemcpyAsync(state, h->sc.state, B * 12 * 8, cudaMemcpyDeviceToHost, h->stream));
     if (frame) CU(cudaMemcpyAsync(frame, h->sc.frame, B * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -851,6 +1007,7 @@ int mpcqp_scenario_get(mpcqp_handle* h, double* state, double* frame, double* fe
 int mpcqp_get_inputs(mpcqp_handle* h, double* xref, double* fsteps) {
     if (!h || !xref || !fsteps) return fail(MPCQP_ERR_INVALID, "null argument");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     const size_t B = h->p.batch, N = h->p.n_steps;
     CU(cudaMemcpyAsync(xref, h->d_xref, B * 12 * (N + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(fsteps, h->d_fsteps, B * 260 * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -864,6 +1021,7 @@ int mpcqp_get_cost_components(mpcqp_handle* h, double* cost, int location) {
     if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
     if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "location must be MPCQP_HOST or MPCQP_DEVICE");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     const size_t B = h->p.batch, bytes = B * 13 * sizeof(double);
     double* d = cost;
     if (location == MPCQP_HOST) { CU(h->scratch(bytes)); d = h->d_scratch; }
@@ -884,6 +1042,7 @@ int mpcqp_result_async(mpcqp_handle* h, int slot) {
     if (!h || slot < 0 || slot > 1) return fail(MPCQP_ERR_INVALID, "bad argument");
     if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
     CU(cudaSetDevice(h->p.device));
+    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     const size_t bytes = (size_t)h->p.batch * 12 * sizeof(double);
     if (!h->pin[slot]) {
         CU(cudaMallocHost(&h->pin[slot], bytes));

@@ -42,17 +42,19 @@ void RIC_CAT(ric_launch_, RIC_N)(int grid, cudaStream_t s, const DevParams& dp, 
     else riccati_kernel<N, false><<<grid, 32 * RIC_WARPS, smem, s>>>(dp, st, sc, dx, df, ws, ctr, first, off, n_inst);
 }
 
-// fallback stage: programmatic dependent launch behind the active-set kernel of the same stream (the kernel blocks in
-// griddepcontrol.wait before it reads the queue); behind anything else the attribute is an ordinary launch
+// fallback stage.  pdl: programmatic dependent launch behind the active-set kernel of the same stream (the kernel blocks in
+// griddepcontrol.wait before it reads the queue); behind anything else the attribute is an ordinary launch.  Without it the CTAs
+// are not scheduled before the active-set kernel has drained (overlapped index ranges: a blocked resident CTA would hold a slot
+// another range's robots could use).
 void RIC_CAT(ipm_launch_, RIC_N)(int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc, const double* dx,
-                                 const double* df, double* ws, int first) {
+                                 const double* df, double* ws, int first, int pdl) {
     constexpr int N = RIC_N;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * RIC_WARPS); cfg.dynamicSmemBytes = RIC_PER_CTA * sizeof(RicInst<N>); cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, ipm_kernel<N>, dp, st, sc, dx, df, ws, first);
 }
 

@@ -26,7 +26,7 @@ EXPORTS = (
     "mpcqp_scenario_init", "mpcqp_scenario_run", "mpcqp_scenario_get", "mpcqp_get_inputs",
     "mpcqp_get_cost_components", "mpcqp_result_async", "mpcqp_result_ready", "mpcqp_result_wait",
     "mpcqp_get_step_result", "mpcqp_get_status", "mpcqp_host_alloc", "mpcqp_host_free",
-    "mpcqp_world_pose", "mpcqp_scenario_set_commands",
+    "mpcqp_world_pose", "mpcqp_scenario_set_commands", "mpcqp_set_overlap", "mpcqp_join",
 )
 
 
@@ -91,6 +91,8 @@ def load():
     lib.mpcqp_get_step_result.argtypes = [vp, dp, dp, C.c_int]
     lib.mpcqp_get_status.argtypes = [vp, i32p, C.c_int]
     lib.mpcqp_world_pose.argtypes = [vp, dp, C.c_int, C.c_int]
+    lib.mpcqp_set_overlap.argtypes = [vp, C.c_int]
+    lib.mpcqp_join.argtypes = [vp]
     lib.mpcqp_host_alloc.argtypes = [C.c_size_t]
     lib.mpcqp_host_alloc.restype = C.c_void_p
     lib.mpcqp_host_free.argtypes = [vp]
@@ -325,6 +327,15 @@ class Engine:
 
     def synchronize(self):
         _check(self.lib.mpcqp_synchronize(self._h))
+
+    def set_overlap(self, ranges):
+        """Issue device-resident ticks as `ranges` independent index ranges (2 .. 4) so that consecutive ticks overlap; 1 = off,
+        0 = automatic (inside scenario_run only).  Results are unchanged; see mpcqp_set_overlap in include/mpcqp.h."""
+        _check(self.lib.mpcqp_set_overlap(self._h, int(ranges)))
+
+    def join(self):
+        """Make the engine's stream wait for every index range in flight (needed only before enqueuing own work on `stream`)."""
+        _check(self.lib.mpcqp_join(self._h))
 
     @property
     def stream(self):

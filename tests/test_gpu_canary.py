@@ -114,3 +114,76 @@ def test_results_do_not_depend_on_scheduling(n, kw):
         replay(np.arange(B), {})
     finally:
         del os.environ["MPCQP_RIC_CTAS"]
+
+
+@pytest.mark.parametrize("n,ranges,kw", [(16, 2, {}), (16, 3, {}), (16, 4, {"max_sweeps": 0}), (32, 2, {}), (64, 2, {})],
+                         ids=["N16-2", "N16-3", "N16-4-ipm", "N32-2", "N64-2"])
+def test_overlapped_index_ranges_change_nothing(n, ranges, kw):
+    """mpcqp_set_overlap: consecutive device-resident ticks issued as independent index ranges (a range's tick t + 1 is ordered
+    behind its own tick t only, each range has its own fallback queue and workspace) must give bit-identical solutions,
+    multipliers, sweep and iteration counts, fallback counts and world poses, tick after tick -- for host-staged inputs replayed
+    from the device and for the device-resident closed loop."""
+    import torch
+    import mpcqp
+    from scenario import Scenario
+    B = 1201 if n == 16 else (333 if n == 32 else 95)
+    gaits = ["trot", "pace", "bound", "walk"]
+    sc = Scenario(B, n_steps=n, gaits=gaits, seed=43)
+    ref = mpcqp.Engine(batch=B, n_steps=n, **kw)
+    ticks = []
+    for t in range(6):
+        xref, fsteps = sc.inputs()
+        ref.run(t, xref, fsteps)
+        x = ref.solution()
+        ticks.append((xref, fsteps, x.copy(), ref.info(), ref.fallback_count(), ref.world_pose()))
+        sc.advance(x[:, :12] + xref[:, :, 1])
+    ref.close()
+    dx = [torch.from_numpy(tk[0]).cuda() for tk in ticks]
+    df = [torch.from_numpy(tk[1]).cuda() for tk in ticks]
+    torch.cuda.synchronize()
+    eng = mpcqp.Engine(batch=B, n_steps=n, **kw)
+    eng.set_overlap(ranges)
+    # all six ticks in flight at once, then the last one's results; then tick by tick
+    for t in range(6):
+        eng.run_device(t, dx[t].data_ptr(), df[t].data_ptr())
+    np.testing.assert_array_equal(eng.solution(), ticks[5][2])
+    np.testing.assert_array_equal(eng.world_pose(), ticks[5][5])
+    assert eng.fallback_count() == ticks[5][4]
+    eng.reset_warm_start()
+    eng.world_pose(set_to=np.tile([0, 0, 0.2027682, 0, 0, 0], (B, 1)))
+    for t, (xref, fsteps, x, info, nfb, qw) in enumerate(ticks):
+        eng.run_device(t, dx[t].data_ptr(), df[t].data_ptr())
+        got, gi = eng.solution(), eng.info()
+        np.testing.assert_array_equal(got, x)
+        for key in ("status", "sweeps", "iters", "y", "obj", "active", "contact"):
+            np.testing.assert_array_equal(gi[key], info[key])
+        assert eng.fallback_count() == nfb
+    # switching back to host inputs joins the ranges first
+    eng.set_overlap(ranges)
+    eng.reset_warm_start()
+    for t in range(3):
+        eng.run_device(t, dx[t].data_ptr(), df[t].data_ptr())
+    for t in range(3, 6):
+        eng.run(t, ticks[t][0], ticks[t][1])
+    np.testing.assert_array_equal(eng.solution(), ticks[5][2])
+    eng.close()
+
+    # device-resident closed loop: one call of 8 ticks (ranges) against 8 calls of one tick (never overlapped)
+    res = []
+    for how in ("single", "ranges"):
+        scd = Scenario(B, n_steps=n, gaits=gaits, seed=44, noise_kind="hash")
+        e = mpcqp.Engine(batch=B, n_steps=n, **kw)
+        e.scenario_init(scd)
+        if how == "single":
+            e.set_overlap(1)
+            for _ in range(8):
+                e.scenario_run(1)
+        else:
+            e.set_overlap(ranges)
+            e.scenario_run(5)
+            e.scenario_run(3)
+        st = e.scenario_state()
+        res.append((e.solution(), st["state"], st["frame"], st["feet"], e.info()["sweeps"]))
+        e.close()
+    for a, b in zip(res[0], res[1]):
+        np.testing.assert_array_equal(a, b)
