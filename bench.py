@@ -306,6 +306,8 @@ def main():
     ap.add_argument("--latency-ticks", type=int, default=200, help="ticks of the separate latency window (SURVEY 8d: p50 / p99 over >= 200 ticks)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short sub-runs of BASELINE configs[2], [3], [4]")
     ap.add_argument("--no-dropin", action="store_true", help="skip the MPC_Wrapper end-to-end leg")
+    ap.add_argument("--overlap", type=int, default=0, help="index ranges the device-resident ticks are issued as (mpcqp_set_overlap): "
+                    "1 = one tick at a time, 0 = 4 ranges up to 8192 robots per GPU, 2 beyond")
     ap.add_argument("--cpu-ticks", type=int, default=100)
     ap.add_argument("--workload", default="trot", choices=["trot", "sweep", "mixed-sweep"],
                     help="trot = BASELINE configs[1] (the headline line, default); sweep / mixed-sweep = device-resident closed-loop "
@@ -391,7 +393,12 @@ def main():
     # ---- timed, device resident: exactly K ticks between barrier + synchronise
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
 
-    def device_window(n_ticks):
+    def device_window(n_ticks, overlap):
+        """overlap == 1: one tick at a time on the engine's stream, CUDA events around every tick (per-tick latency).
+        overlap >= 2: the ticks are issued as that many independent index ranges (mpcqp_set_overlap: a robot's tick t + 1 is ordered
+        behind its own tick t only, so the last sweeps of a tick overlap the next tick of the other ranges); two events around the
+        whole window, the second one behind mpcqp_join."""
+        eng.set_overlap(overlap)
         eng.reset_warm_start()
         for t in range(W):
             eng.run_device(t, d_x[t].data_ptr(), d_f[t].data_ptr())
@@ -400,6 +407,16 @@ def main():
         eng.synchronize()
         barrier()
         l0 = eng.launches
+        if overlap > 1:
+            a[0].record(stream)
+            for i in range(n_ticks):
+                eng.run_device(W + i, d_x[W + i].data_ptr(), d_f[W + i].data_ptr())
+            eng.join()
+            b[n_ticks - 1].record(stream)
+            eng.synchronize()
+            barrier()
+            eng.set_overlap(1)
+            return a[0].elapsed_time(b[n_ticks - 1]), None, eng.launches - l0
         for i in range(n_ticks):
             a[i].record(stream)
             eng.run_device(W + i, d_x[W + i].data_ptr(), d_f[W + i].data_ptr())
@@ -411,10 +428,16 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.6)                                     # let nvidia-smi finish starting up (it takes driver locks while it does)
-    total_ms, per_step, launches = device_window(K)
+    stagewise_mode = bool(eng.params.mode & 4) and (not (eng.params.mode & 2) or bool(eng.params.mode & 8))
+    overlap = args.overlap if args.overlap > 0 else (4 if B <= 8192 else 2)
+    if not stagewise_mode:
+        overlap = 1                                      # the dense path has no index ranges
+    total_ms, _, launches = device_window(K, overlap)
     total_ms = max_over_ranks(total_ms)
     value = world * B * K / (total_ms * 1e-3)
-    lat_ms, lat_steps, _ = device_window(KL) if KL > K else (total_ms, per_step, 0)
+    lat_ms, lat_steps, _ = device_window(KL, 1)          # one tick at a time: per-tick latency; its first K ticks are the timed ones
+    per_step = lat_steps[:K]
+    serial_ms = max_over_ranks(float(per_step.sum()))
 
     # ---- timed, end to end through the host API (pinned host in, forces out)
     h_out = torch.empty((B, 12), dtype=torch.float64, pin_memory=True)
@@ -569,6 +592,10 @@ def main():
                        "instances_per_gpu": B, "parallelism": "instances sharded by index, no collective",
                        "cpu_affinity": affinity,
                        "settle_ticks": max(args.settle, 0),
+                       "tick_overlap": ("the K timed ticks are issued back to back as %d independent index ranges of the batch "
+                                        "(mpcqp_set_overlap): a robot's tick t+1 runs behind its own tick t only (the warm start, MPC.py:403-406), so "
+                                        "the last sweeps of one tick overlap the next tick of the other ranges; results are bit-identical to "
+                                        "one tick at a time (value_one_tick_at_a_time, latency_ms)" % overlap) if overlap > 1 else "off",
                        "tick_window": "ticks %d..%d of the closed loop are timed (steady operation; the first %d ticks after "
                                       "release from rest run untimed before the %d warm-up ticks)" % (W, W + K - 1, max(args.settle, 0), max(args.warmup, 3)),
                        "l2": "each timed tick reads its own input block (%d x %.1f MB > 126 MB L2 over the run); the "
@@ -580,6 +607,7 @@ def main():
                     "what": "mpcqp_run(host xref, host fsteps) + mpcqp_get_latest_result(host forces) per tick through the C ABI"},
             "e2e_dropin": dropin,
             "gpu_launches": int(launches),
+            "value_one_tick_at_a_time": world * B * K / (serial_ms * 1e-3),
             "latency_ms": {"p50": float(np.percentile(per_step, 50)), "p99": float(np.percentile(per_step, 99)),
                            "what": "device time of one batch tick (CUDA events on the engine stream), the K timed ticks"},
             "latency_window": {"ticks": int(KL), "after_untimed_ticks": int(W),

@@ -147,7 +147,7 @@ void* mpcqp_stream(mpcqp_handle* h);
  * state (results, status, reset, host-input runs, mpcqp_synchronize, mpcqp_join) first makes mpcqp_stream(h) wait for all ranges,
  * so callers of this API always see whole ticks; only work the caller enqueues on mpcqp_stream(h) HIMSELF needs mpcqp_join first.
  * ranges = 1 switches the overlap off; 0 (default) = automatic: off for mpcqp_run, and inside one mpcqp_scenario_run call of two
- * or more ticks two ranges when the batch is between one and eight waves of resident robots, joined before the call returns.
+ * or more ticks four ranges when the batch is one to two waves of resident robots, two up to eight waves, joined before the call returns.
  * Results are bit-identical with and without overlap (tests/test_gpu_canary.py). */
 int mpcqp_set_overlap(mpcqp_handle* h, int ranges);
 /* make mpcqp_stream(h) wait for every index range in flight (no host synchronisation) */
