@@ -54,6 +54,11 @@ extern "C" {
                                        factorisation (any horizon, ~20 factorisations whatever the active set), then active-set
                                        sweeps from the rows it identifies; takes precedence over MPCQP_MODE_ADMM when both are set   */
 
+#define MPCQP_MODE_LANE 16          /* run the active-set stage of the stage-wise path with ONE LANE per robot (no redundant arithmetic, an
+                                       HBM / L2 workspace; built for throughput) whatever the batch size; without this bit it is chosen
+                                       automatically for batches of tens of thousands of robots, where it beats half a warp per robot.
+                                       Needs MPCQP_MODE_STAGEWISE | MPCQP_MODE_IPM.                                                   */
+
 typedef struct mpcqp_handle mpcqp_handle;
 
 /* Everything MPC.__init__ hard-codes (MPC.py:22-82) plus solver settings.  Fill with
@@ -140,14 +145,14 @@ void* mpcqp_stream(mpcqp_handle* h);
 /* Overlap of consecutive ticks.  The robots of a batch are independent (MPC.py holds one robot; tick t + 1 of a robot needs only
  * its own tick t: the shifted warm start, MPC.py:403-406), but a tick issued as one launch ends when its slowest robot does, and a
  * robot whose warm-start guess misses needs a second factorisation sweep -- at 4096 robots a third of a tick's time is that tail.
- * With `ranges` >= 2 (at most 4) a tick issued by mpcqp_run(..., MPCQP_DEVICE) or mpcqp_scenario_run is cut into that many
+ * With `ranges` >= 2 (at most 8) a tick issued by mpcqp_run(..., MPCQP_DEVICE) or mpcqp_scenario_run is cut into that many
  * contiguous index ranges, each on its own internal stream with its own fallback queue: a range's tick t + 1 is ordered behind
  * its own tick t only, so the tail of one range is filled by the other ranges' robots.  The inputs of such a tick must be complete
  * on mpcqp_stream(h) at the time of the call (or the caller synchronised).  Every entry point that reads or changes the handle's
  * state (results, status, reset, host-input runs, mpcqp_synchronize, mpcqp_join) first makes mpcqp_stream(h) wait for all ranges,
  * so callers of this API always see whole ticks; only work the caller enqueues on mpcqp_stream(h) HIMSELF needs mpcqp_join first.
  * ranges = 1 switches the overlap off; 0 (default) = automatic: off for mpcqp_run, and inside one mpcqp_scenario_run call of two
- * or more ticks four ranges when the batch is one to two waves of resident robots, two up to eight waves, joined before the call returns.
+ * or more ticks eight ranges when the batch is one to three waves of resident robots, two up to eight waves, joined before the call returns.
  * Results are bit-identical with and without overlap (tests/test_gpu_canary.py). */
 int mpcqp_set_overlap(mpcqp_handle* h, int ranges);
 /* make mpcqp_stream(h) wait for every index range in flight (no host synchronisation) */

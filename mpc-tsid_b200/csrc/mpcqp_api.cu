@@ -83,6 +83,12 @@ namespace mpcqp {
                         const double* dx, const double* df, double* ws, int first, int pdl);
 RIC_DECL(16) RIC_DECL(32) RIC_DECL(64)
 #undef RIC_DECL
+// one robot per lane (mpcqp_lane_inst.cu): the active-set stage for large batches, and the planner kernel in front of it
+cudaError_t lane_configure(int* ctas_per_sm);
+size_t lane_ws_bytes(int grid, int n);
+void lane_launch(int grid, cudaStream_t s, const DevParams& dp, const DevState& st, const DevScenario& sc, const double* dx,
+                 const double* df, double* ws, int* ctr, int first, int off, int n_inst);
+void plan_launch(int sms, cudaStream_t s, const DevParams& dp, const DevScenario& sc, int off, int n_inst);
 }  // namespace mpcqp
 
 // the capacity class (compiled instantiation) that holds a horizon of n steps
@@ -128,7 +134,7 @@ void launch_solve(bool admm, int grid, cudaStream_t s, const DevParams& dp, cons
     else solve_kernel<N, false><<<grid, 32 * Cfg<N>::NW, sizeof(Smem<N, false>), s>>>(dp, st, sc, dx, df, first, off, n);
 }
 
-constexpr int MAX_RANGES = 4;        // index ranges of a batch that may advance through the ticks independently (mpcqp_set_overlap)
+constexpr int MAX_RANGES = 8;        // index ranges of a batch that may advance through the ticks independently (mpcqp_set_overlap)
 
 struct mpcqp_handle {
     mpcqp_params p;
@@ -137,12 +143,12 @@ struct mpcqp_handle {
     cudaStream_t stream = nullptr;
     // side streams.  Host-input runs: copy + solve of alternate chunks overlap on side[0], side[1] (joined every tick).
     // Overlapped index ranges: range r lives on side[r] from tick to tick with its own counters, queue region and workspace.
-    cudaStream_t side[MAX_RANGES] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_main = nullptr, ev_side[MAX_RANGES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t side[MAX_RANGES] = {};
+    cudaEvent_t ev_main = nullptr, ev_side[MAX_RANGES] = {};
     int ranges = 0;                 // mpcqp_set_overlap: 0 = automatic inside mpcqp_scenario_run only, 1 = off, 2 .. MAX_RANGES
     bool forked = false;            // ranges are in flight on the side streams: the main stream has not been joined yet
     int forked_ranges = 0;
-    int rparity[MAX_RANGES] = {0, 0, 0, 0};
+    int rparity[MAX_RANGES] = {};
     double* d_xref = nullptr;
     double* d_fsteps = nullptr;
     double* d_Minv = nullptr;
@@ -174,10 +180,54 @@ struct mpcqp_handle {
     bool fallback_is_ipm() const { return (p.mode & MPCQP_MODE_STAGEWISE) && (p.mode & MPCQP_MODE_IPM); }
     bool has_fallback() const { return fallback_is_ipm() || (p.mode & MPCQP_MODE_ADMM); }
 
+    // Large batches: the active-set stage runs one robot per lane (mpcqp_lane.cuh) instead of half a warp per robot
+    bool use_lane() const {
+        if (!(p.mode & MPCQP_MODE_STAGEWISE) || !fallback_is_ipm()) return false;
+        return (p.mode & MPCQP_MODE_LANE) || p.batch >= lane_min;
+    }
+    // the lane kernel's workspace of side stream `which` (0 = main), grown on demand (first tick only)
+    cudaError_t lane_ws(int which, int grid, double** out) {
+        const size_t need = lane_ws_bytes(grid, p.n_steps);
+        if (need > lane_ws_cap[which]) {
+            if (d_lane_ws[which]) { cudaDeviceSynchronize(); cudaFree(d_lane_ws[which]); }
+            d_lane_ws[which] = nullptr; lane_ws_cap[which] = 0;
+            const cudaError_t e = cudaMalloc(&d_lane_ws[which], need);
+            if (e != cudaSuccess) return e;
+            lane_ws_cap[which] = need;
+        }
+        *out = d_lane_ws[which];
+        return cudaSuccess;
+    }
+
     void solve(bool admm, int grid, cudaStream_t s, const double* dx, const double* df, int first, int off, int n,
                bool closed_loop = false) {
         DevScenario use = sc;
         use.enabled = closed_loop ? 1 : 0;
+        const bool lane = use_lane();
+        if (lane && closed_loop) {
+            // the planner runs as its own kernel and leaves xref / fsteps in the handle's input buffers; the solve kernels read them
+            // like a caller's (enabled == 2: inputs from memory, integration at the end of the solve)
+            use.enabled = 2; use.xref_out = d_xref; use.fsteps_out = d_fsteps;
+            dx = d_xref; df = d_fsteps;
+        }
+        if (!admm && lane) {
+            const int lane_of_stream = s == side[0] ? 1 : (s == side[1] ? 2 : 0);
+            int g = (n + 31) / 32;
+            if (g > lane_max_ctas) g = lane_max_ctas;
+            double* ws = nullptr;
+            cudaError_t e = lane_ws(lane_of_stream, g, &ws);
+            DevState stl = st;
+            int* ctr = st.fb_count + 1 + lane_of_stream;
+            if (lane_of_stream == 0) { stl.fb_next = ctr_base + 8 * (ctr_parity ^ 1); zero_next = true; }
+            else if (e == cudaSuccess) e = cudaMemsetAsync(ctr, 0, sizeof(int), s);
+            if (e == cudaSuccess) {
+                if (closed_loop) { plan_launch(sms, s, dp, use, off, n); ++launches; }
+                lane_launch(g, s, dp, stl, use, dx, df, ws, ctr, first, off, n);
+            }
+            if (e != cudaSuccess && launch_err == cudaSuccess) launch_err = e;
+            ++launches;
+            return;
+        }
         if (admm && fallback_is_ipm()) {
             // the main stream's workspace: every active-set launch of this tick has been joined into `s` by now
             launch_ipm(ric_capacity(p.n_steps), ipm_max_ctas, s, dp, st, use, dx, df, d_ric_ws, first, 1);
@@ -221,13 +271,13 @@ struct mpcqp_handle {
     }
     // ranges to use for a tick issued now (1 = the ordinary single-stream tick)
     int ranges_for(bool automatic_ok) const {
-        if (!(p.mode & MPCQP_MODE_STAGEWISE) || (has_fallback() && !fallback_is_ipm())) return 1;
+        if (!(p.mode & MPCQP_MODE_STAGEWISE) || (has_fallback() && !fallback_is_ipm()) || use_lane()) return 1;
         int r = ranges;
         if (r == 0) {
-            // automatic: four ranges when the batch is one to two waves of resident robots, two up to eight waves -- there the last sweeps of a tick
+            // automatic: eight ranges when the batch is one to three waves of resident robots, two up to eight waves -- there the last sweeps of a tick
             // leave most of the GPU idle (a robot that needs a second sweep ends its tick a whole sweep after the others)
             if (!automatic_ok) return 1;
-            r = p.batch <= wave() ? 1 : (p.batch <= 2 * wave() ? 4 : (p.batch <= 8 * wave() ? 2 : 1));      // measured: 4096 robots 25.6 / 31.3 / 32.4 M solves/s with 1 / 2 / 4 ranges, 16 384: 38.1 / 42.2 / 40.3
+            r = p.batch <= wave() ? 1 : (p.batch <= 3 * wave() ? 8 : (p.batch <= 8 * wave() ? 2 : 1));      // measured (M solves/s with 1 / 2 / 4 / 8 ranges): 4096 robots 25.6 / 31.3 / 32.4 / 33.3, 8192: 32.9 / 40.2 / 37.7 / 37.5, N = 32 4096: 9.5 / 11.8 / 12.9 / 13.3
             if (const char* e = std::getenv("MPCQP_RANGES")) { const int c = std::atoi(e); if (c >= 1 && c <= MAX_RANGES) r = c; }      // tuning hook
         }
         while (r > 1 && p.batch < 2 * RIC_PER_CTA * r) --r;
@@ -249,6 +299,10 @@ struct mpcqp_handle {
         return e;
     }
 
+    double* d_lane_ws[3] = {nullptr, nullptr, nullptr};     // one robot per lane: workspace of the main stream and the two host-input side streams
+    size_t lane_ws_cap[3] = {0, 0, 0};
+    int lane_max_ctas = 0;
+    int lane_min = 1 << 30;         // batch from which the active-set stage runs one robot per lane
     double* d_ric_ws = nullptr;     // stage-wise path: per-stage gains of the resident robots, x3 (main + two side streams)
     size_t ric_ws_doubles = 0;
     int ric_max_ctas = 0, ipm_max_ctas = 0;
@@ -311,6 +365,7 @@ int mpcqp_destroy(mpcqp_handle* h) {
     cudaFree(h->d_block);
     cudaFree(h->d_scen);
     cudaFree(h->d_ric_ws);
+    for (int i = 0; i < 3; ++i) cudaFree(h->d_lane_ws[i]);
     cudaFree(h->d_all);
     cudaFree(h->d_scratch);
     for (int i = 0; i < 2; ++i) {
@@ -478,6 +533,13 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
         const int slots = h->ric_max_ctas > h->ipm_max_ctas ? h->ric_max_ctas : h->ipm_max_ctas;
         h->ric_ws_doubles = (size_t)slots * RIC_PER_CTA * ric_ws_slot_doubles(cap);
         CUH(cudaMalloc(&h->d_ric_ws, (1 + MAX_RANGES) * h->ric_ws_doubles * sizeof(double)));
+        int lane_per_sm = 0;
+        CUH(lane_configure(&lane_per_sm));
+        if (lane_per_sm < 1) return bail(fail(MPCQP_ERR_CUDA, "the one-robot-per-lane kernel does not fit on this device"));
+        h->lane_max_ctas = lane_per_sm * h->sms;
+        // from this batch on a lane per robot beats half a warp per robot (measured)
+        h->lane_min = 8 * h->lane_max_ctas * 32 / 4;
+        if (const char* e = std::getenv("MPCQP_LANE_MIN")) { const int c = std::atoi(e); if (c > 0) h->lane_min = c; }      // tuning hook
     }
     if (!(p->mode & MPCQP_MODE_ACTIVE_SET)) {
         std::vector<int32_t> all((size_t)B + 1);
@@ -599,6 +661,7 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
     // c is copied and solved on side stream c & 1, so the H2D copy of one chunk overlaps the solve of
     // the previous one and the two solve kernels fill each other's tails.
     int chunk = (h->p.mode & MPCQP_MODE_STAGEWISE) ? h->wave() : 2 * h->wave();
+    if (h->use_lane()) chunk = 2 * h->lane_max_ctas * 32;
     if (const char* e = std::getenv("MPCQP_CHUNK")) { const int c = std::atoi(e); if (c > 0) chunk = c; }      // tuning hook
     if (location == MPCQP_HOST) {
         dx = h->d_xref; df = h->d_fsteps;
@@ -745,11 +808,12 @@ int mpcqp_get_fallback_count(mpcqp_handle* h, int32_t* count) {
     { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     if (h->last_ranges > 1) {
         // the last tick ran as index ranges: each has its own queue
-        int32_t part[MAX_RANGES] = {0, 0, 0, 0};
+        int32_t part[MAX_RANGES] = {};
         for (int r = 0; r < h->last_ranges; ++r)
             CU(cudaMemcpyAsync(&part[r], h->ctr_base + 16 + 16 * r + 8 * h->rparity[r], 4, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        *count = part[0] + part[1] + part[2] + part[3];
+        *count = 0;
+        for (int r = 0; r < MAX_RANGES; ++r) *count += part[r];
         return MPCQP_OK;
     }
     CU(cudaMemcpyAsync(count, h->st.fb_count, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -780,7 +844,7 @@ void* mpcqp_stream(mpcqp_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 // Overlap of consecutive ticks (see include/mpcqp.h)
 int mpcqp_set_overlap(mpcqp_handle* h, int ranges) {
-    if (!h || ranges < 0 || ranges > MAX_RANGES) return fail(MPCQP_ERR_INVALID, "ranges must be 0 (automatic) .. 4");
+    if (!h || ranges < 0 || ranges > MAX_RANGES) return fail(MPCQP_ERR_INVALID, "ranges must be 0 (automatic) .. 8");
     CU(cudaSetDevice(h->p.device));
     { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     h->ranges = ranges;

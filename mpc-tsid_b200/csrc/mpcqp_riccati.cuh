@@ -993,7 +993,7 @@ __device__ __forceinline__ bool ric_load_decode(const DevParams& P, const DevSce
                                                 const double* __restrict__ fsteps_g, int inst, bool valid, int first_tick, int sub, int hl,
                                                 const int n, unsigned int& phase, unsigned& conbits) {
     constexpr int NF = RicInst<N>::NF, ROUNDS = RicInst<N>::ROUNDS;
-    if (SC.enabled) {
+    if (SC.enabled == 1) {
         scenario_inputs<16>(P, SC, sm.sc, inst, sm.xr, sm.fs, n, valid);
     } else {
         if (hl == 0) {

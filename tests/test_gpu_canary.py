@@ -116,8 +116,8 @@ def test_results_do_not_depend_on_scheduling(n, kw):
         del os.environ["MPCQP_RIC_CTAS"]
 
 
-@pytest.mark.parametrize("n,ranges,kw", [(16, 2, {}), (16, 3, {}), (16, 4, {"max_sweeps": 0}), (32, 2, {}), (64, 2, {})],
-                         ids=["N16-2", "N16-3", "N16-4-ipm", "N32-2", "N64-2"])
+@pytest.mark.parametrize("n,ranges,kw", [(16, 2, {}), (16, 3, {}), (16, 8, {}), (16, 4, {"max_sweeps": 0}), (32, 8, {}), (64, 2, {})],
+                         ids=["N16-2", "N16-3", "N16-8", "N16-4-ipm", "N32-8", "N64-2"])
 def test_overlapped_index_ranges_change_nothing(n, ranges, kw):
     """mpcqp_set_overlap: consecutive device-resident ticks issued as independent index ranges (a range's tick t + 1 is ordered
     behind its own tick t only, each range has its own fallback queue and workspace) must give bit-identical solutions,

@@ -35,7 +35,7 @@ def run(B, N=16, ticks=60, settle=25, gaits="trot", variants=(1, 2, 3, 4)):
             B, N, R, best, B / best / 1e3, info["sweeps"].mean(), (info["status"] != 1).sum(), same), flush=True)
     eng.close()
 if __name__ == "__main__":
-    run(4096)
-    run(16384, variants=(1, 2, 4))
-    run(4096, gaits=["trot", "pace", "bound", "walk"], variants=(1, 2))
-    run(2048, N=32, ticks=30, variants=(1, 2))
+    run(4096, variants=(1, 4, 6, 8))
+    run(8192, variants=(1, 2, 4, 8))
+    run(4096, gaits=["trot", "pace", "bound", "walk"], variants=(1, 4, 8))
+    run(4096, N=32, ticks=30, variants=(1, 2, 4, 8))
