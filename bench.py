@@ -604,7 +604,9 @@ def main():
                     "host_buffer_bytes_per_step": B * (12 * (N + 1) + 260) * esz,
                     "ms_per_step": 1e3 * e2e_s / K, "latency_ms_p50": 1e3 * float(np.percentile(lat, 50)),
                     "latency_ms_p99": 1e3 * float(np.percentile(lat, 99)),
-                    "what": "mpcqp_run(host xref, host fsteps) + mpcqp_get_latest_result(host forces) per tick through the C ABI"},
+                    "what": "mpcqp_run(host xref, host fsteps) + mpcqp_get_latest_result(host forces) per tick through the C ABI; the inputs sit in "
+                            "page-locked host memory and are fetched over PCIe by the solve kernel itself, robot by robot (no staging copy); "
+                            "h2d_bytes_per_step = the bytes that cross the bus"},
             "e2e_dropin": dropin,
             "gpu_launches": int(launches),
             "value_one_tick_at_a_time": world * B * K / (serial_ms * 1e-3),

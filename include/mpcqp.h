@@ -54,10 +54,10 @@ extern "C" {
                                        factorisation (any horizon, ~20 factorisations whatever the active set), then active-set
                                        sweeps from the rows it identifies; takes precedence over MPCQP_MODE_ADMM when both are set   */
 
-#define MPCQP_MODE_LANE 16          /* run the active-set stage of the stage-wise path with ONE LANE per robot (no redundant arithmetic, an
-                                       HBM / L2 workspace; built for throughput) whatever the batch size; without this bit it is chosen
-                                       automatically for batches of tens of thousands of robots, where it beats half a warp per robot.
-                                       Needs MPCQP_MODE_STAGEWISE | MPCQP_MODE_IPM.                                                   */
+#define MPCQP_MODE_LANE 16          /* run the active-set stage of the stage-wise path with ONE LANE per robot: no redundant arithmetic, the
+                                       O(N) data of a robot in an HBM / L2 workspace, any horizon with one instantiation.  Opt-in: it gives
+                                       the same answers (tests/test_gpu_lane.py) but, as measured, half the throughput of the default half
+                                       warp per robot.  Needs MPCQP_MODE_STAGEWISE | MPCQP_MODE_IPM.          */
 
 typedef struct mpcqp_handle mpcqp_handle;
 

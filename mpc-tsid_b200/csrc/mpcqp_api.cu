@@ -163,6 +163,7 @@ struct mpcqp_handle {
     bool zero_next = false;         // set by solve(): a main-stream stage-wise launch of this tick zeroes the next tick's copy
     int64_t launches = 0;
     int sms = 0;
+    bool direct_ok = true;          // host inputs in page-locked memory are read by the kernels directly (MPCQP_NO_DIRECT=1 switches it off)
     int last_ranges = 1;            // how the last tick was issued (mpcqp_get_fallback_count sums the ranges' queues)
 
     double* pin[2] = {nullptr, nullptr};            // asynchronous result slots (pinned host memory)
@@ -442,6 +443,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     d.refine = p->refine;           // debug build: refine == 77 makes robot 0 write one element past its state array (detector self-test)
 #endif
     d.ipm_max_iter = p->ipm_max_iter > 0 ? p->ipm_max_iter : 60;
+    d.fs_rows = 20;
 
     // Gram matrices of the double-integrator response and their inverses (constant per handle)
     //   M_c[k,l] = sum_{i >= max(k,l)} ( dt^2 Qp_c (i-k)(i-l) + Qv_c ),  i = 0..N-1
@@ -525,6 +527,7 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
     else if (cap == 32) CUH(ric_configure_32(&ric_per_sm, &ipm_per_sm));
     else CUH(ric_configure_64(&ric_per_sm, &ipm_per_sm));
     if (std::getenv("MPCQP_VERBOSE")) std::fprintf(stderr, "mpcqp: stage-wise kernels fit %d (active-set) / %d (interior-point) CTAs per SM\n", ric_per_sm, ipm_per_sm);
+    if (const char* e = std::getenv("MPCQP_NO_DIRECT")) h->direct_ok = std::atoi(e) == 0;      // A/B hook
     if (const char* e = std::getenv("MPCQP_RIC_CTAS")) { const int c = std::atoi(e); if (c > 0 && c < ric_per_sm) ric_per_sm = c; }      // tuning hook
     if (p->mode & MPCQP_MODE_STAGEWISE) {
         if (ric_per_sm < 1 || ipm_per_sm < 1) return bail(fail(MPCQP_ERR_CUDA, "the stage-wise kernel does not fit on this device"));
@@ -537,8 +540,8 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
         CUH(lane_configure(&lane_per_sm));
         if (lane_per_sm < 1) return bail(fail(MPCQP_ERR_CUDA, "the one-robot-per-lane kernel does not fit on this device"));
         h->lane_max_ctas = lane_per_sm * h->sms;
-        // from this batch on a lane per robot beats half a warp per robot (measured)
-        h->lane_min = 8 * h->lane_max_ctas * 32 / 4;
+        // never chosen by batch size: as measured a lane per robot does not beat half a warp per robot at any batch
+        h->lane_min = 1 << 30;
         if (const char* e = std::getenv("MPCQP_LANE_MIN")) { const int c = std::atoi(e); if (c > 0) h->lane_min = c; }      // tuning hook
     }
     if (!(p->mode & MPCQP_MODE_ACTIVE_SET)) {
@@ -663,6 +666,31 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
     int chunk = (h->p.mode & MPCQP_MODE_STAGEWISE) ? h->wave() : 2 * h->wave();
     if (h->use_lane()) chunk = 2 * h->lane_max_ctas * 32;
     if (const char* e = std::getenv("MPCQP_CHUNK")) { const int c = std::atoi(e); if (c > 0) chunk = c; }      // tuning hook
+    // Host inputs in page-locked memory (mpcqp_host_alloc, cudaHostAlloc, torch pin_memory): the stage-wise kernels fetch every
+    // robot's xref and gait table themselves, with the same bulk asynchronous copies they use on HBM, straight from the caller's
+    // buffers over PCIe -- no staging copy in front of the solve: a robot's inputs travel while other robots factorise, and of a gait
+    // table only rows 0..7 cross the bus unless it is longer.  The buffers must stay unchanged until the tick's results have been
+    // fetched (the same contract as for the asynchronous staging copies).  Pageable memory takes the staged path below.
+    bool direct = false;
+    if (location == MPCQP_HOST && stageA && (h->p.mode & MPCQP_MODE_STAGEWISE) && (!h->has_fallback() || h->fallback_is_ipm()) &&
+        !h->use_lane() && h->direct_ok) {
+        cudaPointerAttributes ax, af;
+        if (cudaPointerGetAttributes(&ax, xref) == cudaSuccess && cudaPointerGetAttributes(&af, fsteps) == cudaSuccess &&
+            ax.type == cudaMemoryTypeHost && af.type == cudaMemoryTypeHost && ax.devicePointer && af.devicePointer) {
+            direct = true;
+            dx = (const double*)ax.devicePointer; df = (const double*)af.devicePointer;
+        } else cudaGetLastError();
+    }
+    if (direct) {
+        h->dp.fs_rows = 8;
+        h->solve(false, B, h->stream, dx, df, first, 0, B);
+        if (h->has_fallback()) h->solve(true, B, h->stream, dx, df, first, 0, B);
+        h->dp.fs_rows = 20;
+        CU(h->launch_err);
+        CU(cudaGetLastError());
+        h->ran = true;
+        return MPCQP_OK;
+    }
     if (location == MPCQP_HOST) {
         dx = h->d_xref; df = h->d_fsteps;
         if (stageA && B > chunk) {

@@ -41,6 +41,8 @@ struct DevParams {
     double wp[6], wv[6];    // state weights: position-like (x y z roll pitch yaw) and velocity-like
     double rho, sigma, alpha, feas_tol, dual_tol;
     int max_sweeps, max_iter, min_iter, check_every, warm_start, mode, refine, ipm_max_iter;
+    int fs_rows;            // stage-wise kernels: rows of a gait table fetched up front (20 = the whole table; 8 = rows 0..7, the rest only for a
+                            // table that does not end within them: inputs read straight from the caller's page-locked host memory)
     const double* Minv_tiled;   // lower block triangle of M^-1 in the smem tile layout
     const double* C2;           // N x N: C2[k,l] = sum_{i >= max(k,l)} (i-k)(i-l)   (C0[k,l] = N - max(k,l))
 };

@@ -996,14 +996,29 @@ __device__ __forceinline__ bool ric_load_decode(const DevParams& P, const DevSce
     if (SC.enabled == 1) {
         scenario_inputs<16>(P, SC, sm.sc, inst, sm.xr, sm.fs, n, valid);
     } else {
+        // rows 0 .. fs_rows - 1 of the gait table up front; the rest only if no row among them ends the table (MPC.py:646) -- over
+        // PCIe (inputs in the caller's page-locked memory) the reference's tables (2 .. 7 rows of 20) cost 832 instead of 2080 bytes
+        const int head = P.fs_rows * 13;
         if (hl == 0) {
             fence_async_smem();
-            mbar_expect_tx(&sm.mbar, (12 * (n + 1) + 260) * 8);
+            mbar_expect_tx(&sm.mbar, (12 * (n + 1) + head) * 8);
             bulk_g2s(sm.xr, xref_g + (size_t)inst * 12 * (n + 1), 12 * (n + 1) * 8, &sm.mbar);
-            bulk_g2s(sm.fs, fsteps_g + (size_t)inst * 260, 260 * 8, &sm.mbar);
+            bulk_g2s(sm.fs, fsteps_g + (size_t)inst * 260, head * 8, &sm.mbar);
         }
         mbar_wait(&sm.mbar, phase);
         phase ^= 1u;
+        if (head < 260) {
+            bool ends = false;                                  // uniform over the half-warp: every lane reads the same counts
+            for (int r = 0; r < P.fs_rows; ++r) ends = ends || !(sm.fs[r * 13] > 0.0);     // a terminator, or a malformed count (decode stops there too)
+            if (!ends) {
+                if (hl == 0) {
+                    mbar_expect_tx(&sm.mbar, (260 - head) * 8);
+                    bulk_g2s(sm.fs + head, fsteps_g + (size_t)inst * 260 + head, (260 - head) * 8, &sm.mbar);
+                }
+                mbar_wait(&sm.mbar, phase);
+                phase ^= 1u;
+            }
+        }
         __syncwarp();
     }
     RPROF_T0();

@@ -12,7 +12,7 @@ HOST, DEVICE = 0, 1
 MODE_ACTIVE_SET, MODE_ADMM = 1, 2
 MODE_STAGEWISE = 4           # active-set stage on the stage-wise (Riccati) factorisation, half a warp per robot
 MODE_IPM = 8                 # fallback stage of the stage-wise path: interior-point iterations on the same factorisation (any horizon)
-MODE_LANE = 16               # active-set stage with one lane per robot (large batches; automatic above ~38 k robots)
+MODE_LANE = 16               # active-set stage with one lane per robot (opt-in variant; same answers, measured slower)
 STATUS = {0: "unsolved", 1: "solved", 2: "max_iter", 3: "bad_input"}
 
 # MPCQP_LIB selects another build of the same library (the debug build libmpcqp_canary.so of `make canary`)

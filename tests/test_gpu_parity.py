@@ -343,14 +343,16 @@ def test_long_gait_tables_take_the_full_copy_path():
     eng.close()
 
 
-@pytest.mark.parametrize("B,gaits", [(5, ["trot", "walk", "pace", "bound"]), (2500, "trot")], ids=["ragged-mixed", "two-waves"])
-def test_pinned_and_pageable_host_inputs_agree(B, gaits):
-    """Host inputs reach the device by asynchronous copies from page-locked buffers (what torch's pin_memory gives; 2500 robots
-    take the two-chunk path whose copies overlap the other chunk's solve) or by the driver's staged copies from pageable numpy
-    arrays.  Same robots, same ticks, both ways: every output must agree bit for bit, including a tick on which one gait table
-    runs past row 7 and the whole batch switches from the rows-0..7 copy to the full-table copy."""
+@pytest.mark.parametrize("B,gaits,kw", [(5, ["trot", "walk", "pace", "bound"], {}), (2500, "trot", {}), (333, ["trot", "walk", "pace", "bound"], {"max_sweeps": 0})],
+                         ids=["ragged-mixed", "two-waves", "ipm-only"])
+def test_pinned_and_pageable_host_inputs_agree(B, gaits, kw):
+    """Host inputs in page-locked buffers (what torch's pin_memory or mpcqp_host_alloc give) are fetched by the solve kernels
+    themselves, robot by robot, straight from the caller's memory (rows 0..7 of a gait table first, the rest only for a table that
+    is longer); pageable numpy arrays go through staged copies (2500 robots: the two-chunk path whose copies overlap the other
+    chunk's solve).  Same robots, same ticks, both ways: every output must agree bit for bit, including a tick on which one gait
+    table runs past row 7, and with every robot sent through the interior-point kernel (which fetches its inputs again)."""
     import torch
-    staged, inplace = mpcqp.Engine(batch=B), mpcqp.Engine(batch=B)
+    staged, inplace = mpcqp.Engine(batch=B, **kw), mpcqp.Engine(batch=B, **kw)
     sc = Scenario(B, gaits=gaits, seed=31)
     px = torch.empty((B, 12, N + 1), dtype=torch.float64, pin_memory=True).numpy()
     pf = torch.empty((B, 20, 13), dtype=torch.float64, pin_memory=True).numpy()
