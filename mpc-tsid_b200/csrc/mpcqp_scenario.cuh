@@ -253,4 +253,35 @@ __device__ inline void scenario_advance(const DevScenario& S, int inst, const do
     S.frame[(size_t)inst * 3] = fx; S.frame[(size_t)inst * 3 + 1] = fy; S.frame[(size_t)inst * 3 + 2] = fyaw;
 }
 
+// The same, spread over the lanes of the group that owns the robot (lanes 0..11 one state component each: the twelve Gaussian
+// samples are most of the cost); `lane` = index inside the group, every lane of the group calls it.  Bit-identical results.
+__device__ inline void scenario_advance_lanes(const DevScenario& S, int inst, const double* xn, int lane) {
+    const double dyaw = xn[5];
+    double sy, cy;
+    sincos(dyaw, &sy, &cy);
+    if (lane < 12) {
+        const int c = lane;
+        double v;
+        if (c == 0 || c == 1 || c == 5) v = 0.0;
+        else if (c == 6) v = cy * xn[6] + sy * xn[7];
+        else if (c == 7) v = -sy * xn[6] + cy * xn[7];
+        else if (c == 9) v = cy * xn[9] + sy * xn[10];
+        else if (c == 10) v = -sy * xn[9] + cy * xn[10];
+        else v = xn[c];
+        const bool zeroed = (c == 0 || c == 1 || c == 5);
+        const double sg = S.sigma[c / 3];
+        const double n = (zeroed || sg == 0.0) ? 0.0 : hash_normal(S.seed, (unsigned long long)inst, (unsigned long long)S.tick, (unsigned long long)c) * sg;
+        S.state[(size_t)inst * 12 + c] = v + n;
+    }
+    if (lane == 12) {
+        double fx = S.frame[(size_t)inst * 3], fy = S.frame[(size_t)inst * 3 + 1], fyaw = S.frame[(size_t)inst * 3 + 2];
+        double sf, cf;
+        sincos(fyaw, &sf, &cf);
+        fx += cf * xn[0] - sf * xn[1];
+        fy += sf * xn[0] + cf * xn[1];
+        fyaw += dyaw;
+        S.frame[(size_t)inst * 3] = fx; S.frame[(size_t)inst * 3 + 1] = fy; S.frame[(size_t)inst * 3 + 2] = fyaw;
+    }
+}
+
 }  // namespace mpcqp

@@ -25,7 +25,7 @@ def run(B, N=16, ticks=12, settle=22, gaits="trot"):
             B, N, name, ms, B / ms / 1e3, info["sweeps"].mean(), (info["iters"] > 0).mean(), (info["status"] != 1).sum(), np.abs(st).sum()), flush=True)
         eng.close()
 if __name__ == "__main__":
-    for B in [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else (4096, 18944, 65536, 131072):
+    for B in [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else (4096, 65536, 131072):
         run(B)
     run(65536, gaits=["trot", "pace", "bound", "walk"])
     run(16384, N=32, ticks=6)
