@@ -307,7 +307,7 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short sub-runs of BASELINE configs[2], [3], [4]")
     ap.add_argument("--no-dropin", action="store_true", help="skip the MPC_Wrapper end-to-end leg")
     ap.add_argument("--overlap", type=int, default=0, help="index ranges the device-resident ticks are issued as (mpcqp_set_overlap): "
-                    "1 = one tick at a time, 0 = 8 ranges up to 6144 robots per GPU, 2 beyond")
+                    "1 = one tick at a time, 0 = 8 ranges up to 6144 robots per GPU (4 when four or more GPU processes share the host), 2 beyond")
     ap.add_argument("--cpu-ticks", type=int, default=100)
     ap.add_argument("--workload", default="trot", choices=["trot", "sweep", "mixed-sweep"],
                     help="trot = BASELINE configs[1] (the headline line, default); sweep / mixed-sweep = device-resident closed-loop "
@@ -429,7 +429,7 @@ def main():
     sampler.start()
     time.sleep(0.6)                                     # let nvidia-smi finish starting up (it takes driver locks while it does)
     stagewise_mode = bool(eng.params.mode & 4) and (not (eng.params.mode & 2) or bool(eng.params.mode & 8))
-    overlap = args.overlap if args.overlap > 0 else (8 if B <= 6144 else 2)
+    overlap = args.overlap if args.overlap > 0 else ((8 if world <= 2 else 4) if B <= 6144 else 2)     # 16 launches per tick and process: with 4+ processes on one host 4 ranges are faster
     if not stagewise_mode:
         overlap = 1                                      # the dense path has no index ranges
     total_ms, _, launches = device_window(K, overlap)
