@@ -275,7 +275,7 @@ def sweep_main(args, torch, mpcqp, Scenario, rank, local_rank, world, dist, barr
     clocks = sampler.stop()
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC.replace("Solo trot", "closed-loop sweep"), "value": r["value"], "unit": UNIT, "n_gpus": world,
+            "metric": METRIC.replace("Solo trot", "closed-loop sweep").replace("N=16", "N=%d" % args.n_steps), "value": r["value"], "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_tick"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "BASELINE.json configs[4] shape: device-resident closed-loop sweep, %d robots per GPU, gaits %s, N=%d: footstep "

@@ -95,7 +95,10 @@ struct alignas(16) RicInst {
     RIC_GUARD(g1)
     double lev[3 * NF];                 // lever arms foothold - xref[0:3, k], struct of arrays
     RIC_GUARD(g2)
-    double Ii[9 * N];                   // inv(R_z(yaw_k) gI) per step, row major
+    // inv(R_z(yaw_k) gI) per step, row major -- or, at capacity 64, only cos / sin of yaw_k (the block is re-formed where it is used:
+    // 3.5 KB less per robot, which is what lets a third CTA fit on an SM there)
+    static constexpr bool COMPACT_II = N >= 64;
+    double Ii[COMPACT_II ? 2 * N : 9 * N];
     RIC_GUARD(g3)
     union {
         double beta[6 * N];             // ubar_k + g (dead once the forward pass is done)
@@ -261,9 +264,19 @@ __device__ __forceinline__ void foot_A(const DevParams& P, const RicInst<N>& sm,
     constexpr int NF = 4 * N;
     const double r[3] = {sm.lev[t], sm.lev[NF + t], sm.lev[2 * NF + t]};
     double Ii[9];
-    const double* src = sm.Ii + 9 * (t >> 2);
+    if constexpr (RicInst<N>::COMPACT_II) {
+        const double cs = sm.Ii[2 * (t >> 2)], sn = sm.Ii[2 * (t >> 2) + 1];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Ii[i] = src[i];
+        for (int a = 0; a < 3; ++a) {                          // step_inertia's arithmetic (mpcqp_foot.cuh)
+            Ii[3 * a + 0] = P.gIinv[3 * a + 0] * cs - P.gIinv[3 * a + 1] * sn;
+            Ii[3 * a + 1] = P.gIinv[3 * a + 0] * sn + P.gIinv[3 * a + 1] * cs;
+            Ii[3 * a + 2] = P.gIinv[3 * a + 2];
+        }
+    } else {
+        const double* src = sm.Ii + 9 * (t >> 2);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Ii[i] = src[i];
+    }
     lever_block(P, Ii, r, A);
 }
 // The LQ solve itself: backward recursion over sm.E (packed E_k) and sm.beta, forward pass, velocity costates.
@@ -1036,10 +1049,16 @@ __device__ __forceinline__ bool ric_load_decode(const DevParams& P, const DevSce
         conbits |= contact ? (1u << r) : 0u;
     }
     for (int k = hl; k < n; k += 16) {
-        double Ii[9];
-        step_inertia(P, sm.xr[5 * (n + 1) + k], Ii);
+        if constexpr (RicInst<N>::COMPACT_II) {
+            double sn, cs;
+            sincos(sm.xr[5 * (n + 1) + k], &sn, &cs);                          // MPC.py:330
+            sm.Ii[2 * k] = cs; sm.Ii[2 * k + 1] = sn;
+        } else {
+            double Ii[9];
+            step_inertia(P, sm.xr[5 * (n + 1) + k], Ii);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) sm.Ii[9 * k + i] = Ii[i];
+            for (int i = 0; i < 9; ++i) sm.Ii[9 * k + i] = Ii[i];
+        }
     }
     for (int i = hl; i < 12 * (n + 1); i += 16) bad = bad || !isfinite(sm.xr[i]);
     const bool any_bad = half_any(bad, sub);
