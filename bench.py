@@ -468,6 +468,31 @@ def main():
     forces_k = out_np.copy()
     e2e_lat_s, e2e_lat = host_window(KL) if KL > K else (e2e_s, lat)
 
+    # ---- the same K ticks through the asynchronous result protocol (MPC_Wrapper.py:116-260, the control loop picks up
+    #      the forces of the previous solve while the current one runs): tick i + 1 is issued before the forces of tick i are waited for
+    def async_window(n_ticks):
+        eng.set_overlap(min(overlap, 4))                # host inputs: every index range stages its own rows on its own stream (6 calls per
+                                                        # range and tick: more than 4 ranges make this leg host-bound; measured 14.9 / 17.5 / 17.4 / 14.6 M at 2 / 3 / 4 / 8)
+        eng.reset_warm_start()
+        for t in range(W):
+            eng.run(t, hx[t], hf[t])
+            eng.forces(out=out_np)
+        barrier()
+        w0 = time.perf_counter()
+        for i in range(n_ticks):
+            eng.run(W + i, hx[W + i], hf[W + i])
+            eng.result_async(i & 1)
+            if i > 0:
+                eng.result_wait((i - 1) & 1, out_np)
+        eng.result_wait((n_ticks - 1) & 1, out_np)
+        dt_s = time.perf_counter() - w0
+        barrier()
+        eng.set_overlap(1)
+        return dt_s
+
+    async_s = max_over_ranks(async_window(K))
+    async_ok = bool(np.abs(out_np - forces_k).max() <= 1e-9)
+
     # ---- the same K ticks through the reference-facing classes: MPC_Wrapper.solve(k, planner) + get_latest_result()
     #      (MPC_Wrapper.py:39-78, processing.py:142-145), host arrays in, forces out
     dropin = None
@@ -607,6 +632,11 @@ def main():
                     "what": "mpcqp_run(host xref, host fsteps) + mpcqp_get_latest_result(host forces) per tick through the C ABI; the inputs sit in "
                             "page-locked host memory and are fetched over PCIe by the solve kernel itself, robot by robot (no staging copy); "
                             "h2d_bytes_per_step = the bytes that cross the bus"},
+            "e2e_async": {"value": world * B * K / async_s, "unit": UNIT, "ms_per_step": 1e3 * async_s / K,
+                          "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * 12 * esz, "forces_match_synchronous_path": async_ok,
+                          "what": "mpcqp_run(host inputs of tick i + 1) is issued before mpcqp_result_wait(forces of tick i): the asynchronous "
+                                  "protocol of MPC_Wrapper.py:116-260 (results one tick late), the ticks issued as overlapped index ranges that stage "
+                                  "their own inputs and copy their own forces back; not the headline e2e"},
             "e2e_dropin": dropin,
             "gpu_launches": int(launches),
             "value_one_tick_at_a_time": world * B * K / (serial_ms * 1e-3),

@@ -145,7 +145,8 @@ void* mpcqp_stream(mpcqp_handle* h);
 /* Overlap of consecutive ticks.  The robots of a batch are independent (MPC.py holds one robot; tick t + 1 of a robot needs only
  * its own tick t: the shifted warm start, MPC.py:403-406), but a tick issued as one launch ends when its slowest robot does, and a
  * robot whose warm-start guess misses needs a second factorisation sweep -- at 4096 robots a third of a tick's time is that tail.
- * With `ranges` >= 2 (at most 8) a tick issued by mpcqp_run(..., MPCQP_DEVICE) or mpcqp_scenario_run is cut into that many
+ * With `ranges` >= 2 (at most 8) a tick issued by mpcqp_run (MPCQP_DEVICE; MPCQP_HOST: every range stages its own rows on its own
+ * stream) or by mpcqp_scenario_run is cut into that many
  * contiguous index ranges, each on its own internal stream with its own fallback queue: a range's tick t + 1 is ordered behind
  * its own tick t only, so the tail of one range is filled by the other ranges' robots.  The inputs of such a tick must be complete
  * on mpcqp_stream(h) at the time of the call (or the caller synchronised).  Every entry point that reads or changes the handle's
@@ -153,6 +154,8 @@ void* mpcqp_stream(mpcqp_handle* h);
  * so callers of this API always see whole ticks; only work the caller enqueues on mpcqp_stream(h) HIMSELF needs mpcqp_join first.
  * ranges = 1 switches the overlap off; 0 (default) = automatic: off for mpcqp_run, and inside one mpcqp_scenario_run call of two
  * or more ticks eight ranges when the batch is one to three waves of resident robots, two up to eight waves, joined before the call returns.
+ * mpcqp_result_async does not join: every range copies its own forces behind its own tick, so a loop that issues tick t + 1 before it
+ * waits for the forces of tick t (the asynchronous protocol below) keeps all ranges busy.
  * Results are bit-identical with and without overlap (tests/test_gpu_canary.py). */
 int mpcqp_set_overlap(mpcqp_handle* h, int ranges);
 /* make mpcqp_stream(h) wait for every index range in flight (no host synchronisation) */

@@ -168,6 +168,8 @@ struct mpcqp_handle {
 
     double* pin[2] = {nullptr, nullptr};            // asynchronous result slots (pinned host memory)
     cudaEvent_t ev_pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev_pin_r[2][MAX_RANGES] = {};       // ... when the slot was filled range by range (overlapped ticks)
+    int pin_ranges[2] = {0, 0};                     // 0: the slot's copy ran on the main stream, R: on the streams of R index ranges
     bool pin_valid[2] = {false, false};
 
     DevScenario sc;                 // device-resident closed loop (disabled unless mpcqp_scenario_init was called)
@@ -372,6 +374,8 @@ int mpcqp_destroy(mpcqp_handle* h) {
     for (int i = 0; i < 2; ++i) {
         if (h->pin[i]) cudaFreeHost(h->pin[i]);
         if (h->ev_pin[i]) cudaEventDestroy(h->ev_pin[i]);
+        for (int r = 0; r < MAX_RANGES; ++r)
+            if (h->ev_pin_r[i][r]) cudaEventDestroy(h->ev_pin_r[i][r]);
     }
     for (int i = 0; i < MAX_RANGES; ++i) {
         if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
@@ -582,15 +586,44 @@ static int join_ranges(mpcqp_handle* h) {
     h->forked = false;
     return MPCQP_OK;
 }
-// one tick of the whole batch as R independent index ranges (even sizes: the two robots of a warp stay in one range)
-static int run_ranges(mpcqp_handle* h, int R, const double* dx, const double* df, int first, bool closed_loop) {
-    int rc = fork_ranges(h, R);
-    if (rc) return rc;
+// Host -> device copy of `n` gait tables (20 x 13 doubles each).  A table ends at its first row whose step count is 0
+// (MPC.py:646); the reference's tables use 2 .. 7 of the 20 rows, the rest is NaN padding.  If row 7 of every table in the
+// batch has a zero count, only rows 0..7 travel (832 of 2080 bytes per robot, one strided copy): the device never reads
+// past a table's terminator, so what an earlier tick left in rows 8..19 does not matter.  One read per robot decides.
+static cudaError_t copy_gait_tables(double* dst, const double* src, size_t n, cudaStream_t s) {
+    constexpr size_t ROW = 13, TABLE = 260, PROBE = 7;
+    bool brief = true;
+    for (size_t b = 0; b < n && brief; ++b) brief = src[b * TABLE + PROBE * ROW] == 0.0;
+    if (!brief) return cudaMemcpyAsync(dst, src, n * TABLE * sizeof(double), cudaMemcpyHostToDevice, s);
+    return cudaMemcpy2DAsync(dst, TABLE * sizeof(double), src, TABLE * sizeof(double), (PROBE + 1) * ROW * sizeof(double), n,
+                             cudaMemcpyHostToDevice, s);
+}
+
+// robots off .. off + n - 1 of range r of R (even sizes: the two robots of a warp stay in one range)
+static void range_of(const mpcqp_handle* h, int R, int r, int* off, int* n) {
     const int B = h->p.batch;
     const int per = ((B + R - 1) / R + 1) & ~1;
+    *off = r * per;
+    *n = B - *off < per ? B - *off : per;
+    if (*n < 0) *n = 0;
+}
+// one tick of the whole batch as R independent index ranges.  hx / hf != null: host inputs; every range first copies its own rows
+// into the handle's input buffers on its own stream (the copy engine moves them at the full bus rate while other ranges solve;
+// the range's previous tick, which read those rows, is ahead of the copy in the same stream).
+static int run_ranges(mpcqp_handle* h, int R, const double* dx, const double* df, int first, bool closed_loop,
+                      const double* hx = nullptr, const double* hf = nullptr) {
+    int rc = fork_ranges(h, R);
+    if (rc) return rc;
+    const size_t xs = (size_t)12 * (h->p.n_steps + 1), fs = 260;
     for (int r = 0; r < R; ++r) {
-        const int off = r * per, n = B - off < per ? B - off : per;
-        if (n > 0) h->solve_range(r, off, n, dx, df, first, closed_loop);
+        int off, n;
+        range_of(h, R, r, &off, &n);
+        if (n <= 0) continue;
+        if (hx) {
+            CU(cudaMemcpyAsync(h->d_xref + off * xs, hx + off * xs, n * xs * sizeof(double), cudaMemcpyHostToDevice, h->side[r]));
+            CU(copy_gait_tables(h->d_fsteps + off * fs, hf + off * fs, n, h->side[r]));
+        }
+        h->solve_range(r, off, n, dx, df, first, closed_loop);
     }
     h->last_ranges = R;
     return MPCQP_OK;
@@ -623,19 +656,6 @@ static int stage_inputs(mpcqp_handle* h, const double* xref, const double* fstep
     return MPCQP_OK;
 }
 
-// Host -> device copy of `n` gait tables (20 x 13 doubles each).  A table ends at its first row whose step count is 0
-// (MPC.py:646); the reference's tables use 2 .. 7 of the 20 rows, the rest is NaN padding.  If row 7 of every table in the
-// batch has a zero count, only rows 0..7 travel (832 of 2080 bytes per robot, one strided copy): the device never reads
-// past a table's terminator, so what an earlier tick left in rows 8..19 does not matter.  One read per robot decides.
-static cudaError_t copy_gait_tables(double* dst, const double* src, size_t n, cudaStream_t s) {
-    constexpr size_t ROW = 13, TABLE = 260, PROBE = 7;
-    bool brief = true;
-    for (size_t b = 0; b < n && brief; ++b) brief = src[b * TABLE + PROBE * ROW] == 0.0;
-    if (!brief) return cudaMemcpyAsync(dst, src, n * TABLE * sizeof(double), cudaMemcpyHostToDevice, s);
-    return cudaMemcpy2DAsync(dst, TABLE * sizeof(double), src, TABLE * sizeof(double), (PROBE + 1) * ROW * sizeof(double), n,
-                             cudaMemcpyHostToDevice, s);
-}
-
 int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fsteps, int location) {
     if (!h || !xref || !fsteps) return fail(MPCQP_ERR_INVALID, "null argument");
     if (location != MPCQP_HOST && location != MPCQP_DEVICE) return fail(MPCQP_ERR_INVALID, "location must be MPCQP_HOST or MPCQP_DEVICE");
@@ -644,28 +664,7 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
     const int first = (k == 0.0) ? 1 : 0;                       // MPC.py:491, 413: only k == 0 vs k > 0 matters
     const size_t xs = (size_t)12 * (N + 1), fs = 260;
     const bool stageA = (h->p.mode & MPCQP_MODE_ACTIVE_SET) != 0;
-    if (location == MPCQP_DEVICE && stageA) {
-        // device-resident inputs with overlap switched on: the tick is issued as independent index ranges, no join
-        const int R = h->ranges_for(false);
-        if (R > 1) {
-            const int rc = run_ranges(h, R, xref, fsteps, first, false);
-            if (rc) return rc;
-            CU(h->launch_err);
-            CU(cudaGetLastError());
-            h->ran = true;
-            return MPCQP_OK;
-        }
-    }
-    { const int rc = join_ranges(h); if (rc) return rc; }
-    h->last_ranges = 1;
-    CU(begin_tick(h));
     const double *dx = xref, *df = fsteps;
-    // Host inputs: the batch is cut into chunks of two full waves (2 x 4 CTAs x #SM instances); chunk
-    // c is copied and solved on side stream c & 1, so the H2D copy of one chunk overlaps the solve of
-    // the previous one and the two solve kernels fill each other's tails.
-    int chunk = (h->p.mode & MPCQP_MODE_STAGEWISE) ? h->wave() : 2 * h->wave();
-    if (h->use_lane()) chunk = 2 * h->lane_max_ctas * 32;
-    if (const char* e = std::getenv("MPCQP_CHUNK")) { const int c = std::atoi(e); if (c > 0) chunk = c; }      // tuning hook
     // Host inputs in page-locked memory (mpcqp_host_alloc, cudaHostAlloc, torch pin_memory): the stage-wise kernels fetch every
     // robot's xref and gait table themselves, with the same bulk asynchronous copies they use on HBM, straight from the caller's
     // buffers over PCIe -- no staging copy in front of the solve: a robot's inputs travel while other robots factorise, and of a gait
@@ -681,6 +680,29 @@ int mpcqp_run(mpcqp_handle* h, double k, const double* xref, const double* fstep
             dx = (const double*)ax.devicePointer; df = (const double*)af.devicePointer;
         } else cudaGetLastError();
     }
+    if (stageA) {
+        // overlap switched on: the tick is issued as independent index ranges, no join.  Host inputs are staged range by range (the
+        // copy engine reaches the full bus rate, 53 GB/s, where robot-by-robot reads by the kernels reach ~36: measured)
+        const int R = h->ranges_for(false);
+        if (R > 1) {
+            const bool host = location == MPCQP_HOST;
+            const int rc = host ? run_ranges(h, R, h->d_xref, h->d_fsteps, first, false, xref, fsteps) : run_ranges(h, R, dx, df, first, false);
+            if (rc) return rc;
+            CU(h->launch_err);
+            CU(cudaGetLastError());
+            h->ran = true;
+            return MPCQP_OK;
+        }
+    }
+    { const int rc = join_ranges(h); if (rc) return rc; }
+    h->last_ranges = 1;
+    CU(begin_tick(h));
+    // Host inputs: the batch is cut into chunks of two full waves (2 x 4 CTAs x #SM instances); chunk
+    // c is copied and solved on side stream c & 1, so the H2D copy of one chunk overlaps the solve of
+    // the previous one and the two solve kernels fill each other's tails.
+    int chunk = (h->p.mode & MPCQP_MODE_STAGEWISE) ? h->wave() : 2 * h->wave();
+    if (h->use_lane()) chunk = 2 * h->lane_max_ctas * 32;
+    if (const char* e = std::getenv("MPCQP_CHUNK")) { const int c = std::atoi(e); if (c > 0) chunk = c; }      // tuning hook
     if (direct) {
         h->dp.fs_rows = 8;
         h->solve(false, B, h->stream, dx, df, first, 0, B);
@@ -1134,14 +1156,30 @@ int mpcqp_result_async(mpcqp_handle* h, int slot) {
     if (!h || slot < 0 || slot > 1) return fail(MPCQP_ERR_INVALID, "bad argument");
     if (!h->ran) return fail(MPCQP_ERR_STATE, "no run has been issued on this handle");
     CU(cudaSetDevice(h->p.device));
-    { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     const size_t bytes = (size_t)h->p.batch * 12 * sizeof(double);
     if (!h->pin[slot]) {
         CU(cudaMallocHost(&h->pin[slot], bytes));
         CU(cudaEventCreateWithFlags(&h->ev_pin[slot], cudaEventDisableTiming));
     }
+    if (h->forked) {
+        // overlapped ticks: every index range copies its own forces on its own stream, behind its tick and in front of its next one
+        // -- no range waits for another, and a range's next tick cannot overwrite what has not been copied yet
+        const int R = h->forked_ranges;
+        for (int r = 0; r < R; ++r) {
+            int off, n;
+            range_of(h, R, r, &off, &n);
+            if (!h->ev_pin_r[slot][r]) CU(cudaEventCreateWithFlags(&h->ev_pin_r[slot][r], cudaEventDisableTiming));
+            if (n > 0) CU(cudaMemcpyAsync(h->pin[slot] + (size_t)off * 12, h->st.f0 + (size_t)off * 12, (size_t)n * 12 * sizeof(double),
+                                          cudaMemcpyDeviceToHost, h->side[r]));
+            CU(cudaEventRecord(h->ev_pin_r[slot][r], h->side[r]));
+        }
+        h->pin_ranges[slot] = R;
+        h->pin_valid[slot] = true;
+        return MPCQP_OK;
+    }
     CU(cudaMemcpyAsync(h->pin[slot], h->st.f0, bytes, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaEventRecord(h->ev_pin[slot], h->stream));
+    h->pin_ranges[slot] = 0;
     h->pin_valid[slot] = true;
     return MPCQP_OK;
 }
@@ -1151,17 +1189,23 @@ int mpcqp_result_ready(mpcqp_handle* h, int slot) {
     if (!h || slot < 0 || slot > 1) return fail(MPCQP_ERR_INVALID, "bad argument");
     if (!h->pin_valid[slot]) return 0;
     cudaSetDevice(h->p.device);
-    const cudaError_t e = cudaEventQuery(h->ev_pin[slot]);
-    if (e == cudaSuccess) return 1;
-    if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
-    return fail(MPCQP_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(e));
+    const int R = h->pin_ranges[slot];
+    for (int r = 0; r < (R > 0 ? R : 1); ++r) {
+        const cudaError_t e = cudaEventQuery(R > 0 ? h->ev_pin_r[slot][r] : h->ev_pin[slot]);
+        if (e == cudaSuccess) continue;
+        if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+        return fail(MPCQP_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(e));
+    }
+    return 1;
 }
 
 int mpcqp_result_wait(mpcqp_handle* h, int slot, double* forces) {
     if (!h || !forces || slot < 0 || slot > 1) return fail(MPCQP_ERR_INVALID, "bad argument");
     if (!h->pin_valid[slot]) return fail(MPCQP_ERR_STATE, "no result was requested in this slot");
     CU(cudaSetDevice(h->p.device));
-    CU(cudaEventSynchronize(h->ev_pin[slot]));
+    if (h->pin_ranges[slot] > 0) {
+        for (int r = 0; r < h->pin_ranges[slot]; ++r) CU(cudaEventSynchronize(h->ev_pin_r[slot][r]));
+    } else CU(cudaEventSynchronize(h->ev_pin[slot]));
     std::memcpy(forces, h->pin[slot], (size_t)h->p.batch * 12 * sizeof(double));
     return MPCQP_OK;
 }

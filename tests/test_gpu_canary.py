@@ -166,6 +166,19 @@ def test_overlapped_index_ranges_change_nothing(n, ranges, kw):
     for t in range(3, 6):
         eng.run(t, ticks[t][0], ticks[t][1])
     np.testing.assert_array_equal(eng.solution(), ticks[5][2])
+    # host inputs overlap too (every range stages its own rows on its own stream); the asynchronous result protocol copies every
+    # range's forces behind its own tick: issue tick t + 1, then wait for the forces of tick t
+    eng.set_overlap(ranges)
+    eng.reset_warm_start()
+    px = [torch.from_numpy(tk[0]).pin_memory().numpy() for tk in ticks]
+    pf = [torch.from_numpy(tk[1]).pin_memory().numpy() for tk in ticks]
+    for t in range(6):
+        eng.run(t, px[t], pf[t])
+        eng.result_async(t & 1)
+        if t > 0:
+            np.testing.assert_array_equal(eng.result_wait((t - 1) & 1), ticks[t - 1][2][:, 12 * n:12 * n + 12])
+    np.testing.assert_array_equal(eng.result_wait(5 & 1), ticks[5][2][:, 12 * n:12 * n + 12])
+    np.testing.assert_array_equal(eng.solution(), ticks[5][2])
     eng.close()
 
     # device-resident closed loop: one call of 8 ticks (ranges) against 8 calls of one tick (never overlapped)
