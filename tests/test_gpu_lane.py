@@ -172,3 +172,20 @@ def test_device_closed_loop_one_robot_per_lane(noise):
         host_sc.advance(xh[:, :12] + xref[:, :, 1])
     np.testing.assert_allclose(dev.scenario_state()["state"], host_sc.state, rtol=0, atol=1e-8)
     host.close(); dev.close()
+
+
+def test_lane_kernel_host_chunks_and_refill():
+    """More robots than resident lanes (18 944 on a B200: every lane refills from the work counter) and more than one host chunk
+    (pageable inputs of a batch above two grids of lanes are staged and solved chunk by chunk on the side streams, each with its own
+    workspace): same answers as the half-warp kernel."""
+    B = 38000
+    sc = Scenario(B, gaits=["trot", "pace", "bound", "walk"], seed=61)
+    a, b = mpcqp.Engine(batch=B), mpcqp.Engine(batch=B, mode=LANE)
+    for t in range(2):
+        xref, fsteps = sc.inputs()
+        a.run(t, xref, fsteps); b.run(t, xref, fsteps)
+        xa, xb = a.solution(), b.solution()
+        assert (b.info(with_y=False)["status"] == 1).all()
+        np.testing.assert_allclose(xb, xa, rtol=0, atol=1e-8)
+        sc.advance(xa[:, :12] + xref[:, :, 1])
+    a.close(); b.close()
