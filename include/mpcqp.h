@@ -179,8 +179,8 @@ int mpcqp_export_build(mpcqp_handle* h, double k, const double* xref, const doub
  * The footstep planner (FootstepPlanner.update_fsteps / getRefStates, FootstepPlanner.py:76-161, 284-445) and the
  * closed-loop state update (MPC.q_next / v_next, MPC.py:448-450, moved into the next local frame as
  * Interface.py:100-132 does) run inside the solve kernel, so a tick needs no host producer and no input copy.
- * Per instance: seq = 64 bits, bit 4*s + j = foot j in contact at step s of the gait period (T_gait / dt <= 16 steps)
- * (FootstepPlanner.py:207-282), phase = offset into that period, vref = 6 commanded velocities, state = 12 initial
+ * Per instance: seq = ceil(period / 16) 64-bit words (period = T_gait / dt <= 64 steps: dt = 0.01 gives 32), bit 4*(s % 16) + j of word
+ * s / 16 = foot j in contact at step s of the gait period (FootstepPlanner.py:207-282; one word per instance while period <= 16), phase = offset into that period, vref = 6 commanded velocities, state = 12 initial
  * measured states; sigma4 = Gaussian noise (position, angle, linear, angular velocity) drawn from a counter-based
  * generator keyed by (seed, instance, tick, component).  All pointers are HOST pointers. */
 int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* phase, const double* vref,

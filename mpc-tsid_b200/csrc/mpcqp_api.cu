@@ -996,17 +996,18 @@ int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* pha
     if (!h || !seq || !phase || !vref || !state || !sigma4) return fail(MPCQP_ERR_INVALID, "null argument");
     const size_t B = h->p.batch;
     const int N = h->p.n_steps;
-    // the gait period is T_gait / dt steps (FootstepPlanner.py:52-63); `seq` holds 4 bits per step, so up to 16 steps
+    // the gait period is T_gait / dt steps (FootstepPlanner.py:52-63); `seq` holds 4 bits per step, 16 steps per 64-bit word
     const int period = (int)std::lround(h->p.T_gait / h->p.dt);
-    if (period < 1 || period > 16 || std::fabs(h->p.T_gait / h->p.dt - period) > 1e-9)
-        return fail(MPCQP_ERR_INVALID, "closed loop needs a gait period T_gait / dt of 1 .. 16 whole steps");
+    if (period < 1 || period > 64 || std::fabs(h->p.T_gait / h->p.dt - period) > 1e-9)
+        return fail(MPCQP_ERR_INVALID, "closed loop needs a gait period T_gait / dt of 1 .. 64 whole steps");
+    const size_t seq_words = (size_t)(period + 15) / 16;
     CU(cudaSetDevice(h->p.device));
     { const int rc_ = join_ranges(h); if (rc_) return rc_; }
     CU(cudaStreamSynchronize(h->stream));
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_state = take(B * 12 * 8), o_frame = take(B * 3 * 8), o_feet = take(B * 8 * 8), o_target = take(B * 8 * 8);
-    const size_t o_vref = take(B * 6 * 8), o_seq = take(B * 8), o_phase = take(B * 4), o_prev = take(B);
+    const size_t o_vref = take(B * 6 * 8), o_seq = take(B * seq_words * 8), o_phase = take(B * 4), o_prev = take(B);
     const size_t o_cmd = take(B * 3 * 8), o_cflag = take(B), o_ctick = take(B * 4);
     if (!h->d_scen) CU(cudaMalloc(&h->d_scen, off));
     CU(cudaMemset(h->d_scen, 0, off));
@@ -1030,7 +1031,7 @@ int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* pha
     CU(cudaMemcpy(base + o_feet, feet.data(), B * 8 * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(base + o_target, feet.data(), B * 8 * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(base + o_vref, vref, B * 6 * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(base + o_seq, seq, B * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(base + o_seq, seq, B * seq_words * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(base + o_phase, phase, B * 4, cudaMemcpyHostToDevice));
     for (int i = 0; i < 4; ++i) s.sigma[i] = sigma4[i];
     // numpy.linspace(start, stop, N): start + i * step with the last element set to stop exactly
@@ -1041,6 +1042,7 @@ int mpcqp_scenario_init(mpcqp_handle* h, const uint64_t* seq, const int32_t* pha
     }
     s.seed = seed;
     s.period = period;
+    s.seq_words = (int)seq_words;
     h->scen_tick = 0;
     h->scen_ready = true;
     CU(mpcqp_reset_warm_start(h) == 0 ? cudaSuccess : cudaErrorUnknown);

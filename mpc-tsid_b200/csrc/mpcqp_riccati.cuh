@@ -204,6 +204,7 @@ __device__ __forceinline__ bool ldl6_regs(double (&a)[21], double (&dinv)[6], do
             for (int c = j + 1; c <= i; ++c)
                 if (!(i == j + 1 && c == j + 1)) a[RIC_TI(i, c)] = fma(-a[RIC_TI(i, j)], t[c], a[RIC_TI(i, c)]);
         // row j of inv(U):  ui[j][c] = -(u[j][c] + sum_{c < k < j} u[j][k] ui[k][c])
+#ifndef RIC_NOINV
 #pragma unroll
         for (int c = 0; c < j; ++c) {
             double acc = a[RIC_TI(j, c)];
@@ -211,6 +212,7 @@ __device__ __forceinline__ bool ldl6_regs(double (&a)[21], double (&dinv)[6], do
             for (int k = c + 1; k < j; ++k) acc = fma(a[RIC_TI(j, k)], ui[RIC_TI(k, c)], acc);
             ui[RIC_TI(j, c)] = -acc;
         }
+#endif
         // the carried rows
         if (j + 1 < 6) {
             double acc = fs[j + 1];
@@ -237,6 +239,19 @@ __device__ __forceinline__ void row_mul1(double (&out)[6], const double (&in)[6]
         for (int r = c + 1; r < 6; ++r) t = fma(in[r], m[RIC_TI(r, c)], t);
         out[c] = t;
     }
+}
+// out = in * inv(m)  (m UNIT lower triangular, packed), by substitution from the last column back:  out[c] = in[c] - sum_{r > c} out[r] m[r][c]
+__device__ __forceinline__ void row_solve1(double (&out)[6], const double (&in)[6], const double (&m)[21]) {
+    double t[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) t[c] = in[c];
+#pragma unroll
+    for (int r = 5; r >= 1; --r) {
+        out[r] = t[r];
+#pragma unroll
+        for (int c = 0; c < r; ++c) t[c] = fma(-out[r], m[RIC_TI(r, c)], t[c]);
+    }
+    out[0] = t[0];
 }
 // out = in * m'  (m UNIT lower triangular, packed):  out[c] = in[c] + sum_{r < c} in[r] m[c][r]
 __device__ __forceinline__ void row_mul1T(double (&out)[6], const double (&in)[6], const double (&m)[21]) {
@@ -370,11 +385,19 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
             double dr[6];
 #pragma unroll
             for (int q = 0; q < 6; ++q) b1[q] *= einv[q];
+#ifdef RIC_NOINV
+            row_solve1(v, b1, G);
+#else
             row_mul1(v, b1, Mi);
+#endif
 #pragma unroll
             for (int q = 0; q < 6; ++q) dr[q] = (y[q] - v[q]) * dinv[q];
             row_mul1T(tr, v, L);
+#ifdef RIC_NOINV
+            row_solve1(kr, dr, L);
+#else
             row_mul1(kr, dr, Li);
+#endif
         }
         if (hl < 13) {
             double* g = ws + (size_t)RIC_GAIN * k + rid;                // gain of impulse component o: coefficient rid

@@ -24,7 +24,7 @@ struct DevScenario {
     double* cmd;            // B x 3   getRefStates' command state: h_rotation_command, and the xref[2, 1:] / xref[8, 1:] it leaves behind
     uint8_t* cmd_flag;      // B       flag_rotation_command (0 idle, 1 commanding, 2 released), FootstepPlanner.py:66, 128-152
     int32_t* cmd_tick;      // B       tick whose command step has been applied (a robot's inputs may be rebuilt by the fallback stage)
-    const unsigned long long* seq;   // B: bit 4 s + j = foot j in contact at step s of the gait period (<= 16 steps)
+    const unsigned long long* seq;   // B x seq_words: bit 4 (s % 16) + j of word s / 16 = foot j in contact at step s of the gait period
     const int32_t* phase;   // B
     uint8_t* prevc;         // B: bits 0..3 contact of the previous tick's first step, bit 7 = valid
     double* xref_out;       // optional B x 12 x (N+1): the inputs generated this tick (parity hook), or null
@@ -34,7 +34,8 @@ struct DevScenario {
     double lin_b[64];       // numpy.linspace(dt, T_gait, N)          (FootstepPlanner.py:114)
     unsigned long long seed;
     int tick;               // closed-loop tick of this launch
-    int period;             // steps per gait period (T_gait / dt), <= 16
+    int period;             // steps per gait period (T_gait / dt), <= 64
+    int seq_words;          // 64-bit words of `seq` per robot: ceil(period / 16)
     int reduced;            // Joystick.reduced: the smaller support polygon of FootstepPlanner.py:330-332
     int enabled;
 };
@@ -94,12 +95,13 @@ __device__ void scenario_inputs(const DevParams& P, const DevScenario& S, Scenar
     const double w = sc.vr[5];
     if (tid == 0) {
         // run-length table of the next N steps of the periodic gait (what FootstepPlanner.roll maintains)
-        const unsigned long long seq = S.seq[inst];
+        unsigned long long seq[4] = {0ull, 0ull, 0ull, 0ull};
+        for (int q = 0; q < S.seq_words; ++q) seq[q] = S.seq[(size_t)inst * S.seq_words + q];
         const int ph = S.phase[inst];
         int rows = 0, prev = -1;
         for (int i = 0; i < N; ++i) {
             const int s = (S.tick + ph + i) % S.period;
-            const int m = (int)((seq >> (4 * s)) & 15ull);
+            const int m = (int)((seq[s >> 4] >> (4 * (s & 15))) & 15ull);
             if (m != prev) { sc.mask[rows] = m; sc.cnt[rows] = 1; ++rows; prev = m; }
             else sc.cnt[rows - 1] += 1;
         }

@@ -309,12 +309,14 @@ class Scenario:
         return self.xref.copy(), self.fsteps.copy()
 
     def seq_bits(self):
-        """The gait period as 64 bits per robot: bit 4*s + j = foot j in contact at step s (libmpcqp's format)."""
-        bits = np.zeros(self.B, dtype=np.uint64)
+        """The gait period as ceil(period / 16) 64-bit words per robot: bit 4*(s % 16) + j of word s // 16 = foot j in contact
+        at step s (libmpcqp's format; shape (B,) while the period fits one word, else (B, words))."""
+        words = (self.period + 15) // 16
+        bits = np.zeros((self.B, words), dtype=np.uint64)
         for s_ in range(self.period):
             for j in range(4):
-                bits |= (self.seq[:, s_, j] == 1.0).astype(np.uint64) << np.uint64(4 * s_ + j)
-        return bits
+                bits[:, s_ // 16] |= (self.seq[:, s_, j] == 1.0).astype(np.uint64) << np.uint64(4 * (s_ % 16) + j)
+        return bits[:, 0] if words == 1 else bits
 
     def _noise(self):
         B = self.B

@@ -128,8 +128,31 @@ def planner_fixture():
     print("wrote planner_trot.npz")
 
 
+def planner_fixture_dt01():
+    """The reference FootstepPlanner at the MPC time step dt = 0.01 (main.py:20: gait period T_gait / dt = 32 steps, N = 32 with one
+    period): same protocol as planner_fixture, its own file (planner_trot_dt01.npz)."""
+    fp = RefPlanner.FootstepPlanner(0.01, 1)
+    N = fp.n_steps
+    assert N == 32
+    sc = Scenario(1, n_steps=N, dt=0.01, T_gait=0.32, gaits="trot", v_ref=[0.35, 0.1, 0, 0, 0, -0.25], phase=[0], random_commands=False)
+    xs, fs, states = [], [], []
+    for k in range(70):
+        sc.inputs()
+        st = sc.state[0].copy()
+        fp.update_fsteps(k, sc.local_feet()[0], st[6:12].reshape(6, 1), sc.v_ref[0].reshape(6, 1), st[2], None, None, False)
+        fp.getRefStates(k, 0.32, st[0:3].reshape(3, 1), st[3:6].reshape(3, 1), st[6:9].reshape(3, 1),
+                        st[9:12].reshape(3, 1), sc.v_ref[0].reshape(6, 1))
+        xs.append(fp.xref.copy()); fs.append(fp.fsteps.copy()); states.append(st)
+        xn = fp.xref[:, 1] + 0.005 * np.sin(np.arange(12) + k)
+        sc.advance(xn[None])
+    np.savez_compressed(os.path.join(HERE, "planner_trot_dt01.npz"), xref=np.array(xs), fsteps=np.array(fs), state=np.array(states),
+                        v_ref=sc.v_ref[0].copy())
+    print("wrote planner_trot_dt01.npz")
+
+
 def main():
     planner_fixture()
+    planner_fixture_dt01()
     # 1. nominal trot, the survey's known-answer start state, with noise
     s = Scenario(1, gaits="trot", v_ref=[0.3, 0, 0, 0, 0, 0.0], phase=[0], random_commands=False, seed=11)
     run_case("trot", s, 20, first_state=np.array([.01, -.005, .21, .02, -.03, 0, .1, .05, -.02, .1, -.1, .05]))
@@ -177,6 +200,8 @@ def general_horizons():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "planner":
         planner_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "planner_dt01":
+        planner_fixture_dt01()
     elif len(sys.argv) > 1 and sys.argv[1] == "horizons":
         general_horizons()
     elif len(sys.argv) > 1 and sys.argv[1] == "long":

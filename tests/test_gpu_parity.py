@@ -480,6 +480,48 @@ def test_device_closed_loop_matches_host_loop(noise):
     host.close(); dev.close()
 
 
+def test_device_closed_loop_with_a_32_step_gait_period():
+    """dt = 0.01 (main.py:20-23): the gait period is T_gait / dt = 32 steps, two 64-bit words of contact flags per robot.  Device
+    planner + closed loop against the host twin (pinned to the reference planner at this dt by
+    tests/test_planner.py::test_trot_planner_matches_reference_at_dt_001) over more than one gait period, every robot certified."""
+    from oracle import mpc_build
+    B, T = 36, 40
+    kw = dict(n_steps=32, dt=0.01, T_gait=0.32, gaits=["trot", "pace", "bound", "walk"], seed=58, noise=(1e-3, 5e-3, 1e-2, 2e-2),
+              noise_kind="hash")
+    host_sc, dev_sc = Scenario(B, **kw), Scenario(B, **kw)
+    assert host_sc.period == 32 and dev_sc.seq_bits().shape == (B, 2)
+    ekw = dict(n_steps=32, dt=0.01, T_gait=0.32)
+    host, dev = mpcqp.Engine(batch=B, **ekw), mpcqp.Engine(batch=B, **ekw)
+    dev.scenario_init(dev_sc)
+    for t in range(T):
+        xref, fsteps = host_sc.inputs()
+        host.run(t, xref, fsteps)
+        xh = host.solution()
+        dev.scenario_run(1, emit_inputs=True)
+        xd_ref, fd = dev.last_inputs()
+        assert np.array_equal(np.isnan(fd), np.isnan(fsteps)), "tick %d: swing pattern" % t
+        np.testing.assert_allclose(np.nan_to_num(fd), np.nan_to_num(fsteps), rtol=0, atol=1e-9)
+        np.testing.assert_allclose(xd_ref, xref, rtol=0, atol=1e-9)
+        info = dev.info()
+        assert (info["status"] == 1).all()
+        np.testing.assert_allclose(dev.forces(), host.forces(), rtol=0, atol=1e-6)
+        if t % 13 == 0:
+            cert = batch_kkt.certificate(xd_ref, fd, dev.solution(), info["y"], mpc_build.Params(n_steps=32, dt=0.01, T_gait=0.32), first_tick=(t == 0))
+            batch_kkt.assert_batch_certified(cert, "tick %d" % t)
+        host_sc.advance(xh[:, :12] + xref[:, :, 1])
+        st = dev.scenario_state()
+        np.testing.assert_allclose(st["state"], host_sc.state, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(st["frame"], host_sc.frame, rtol=0, atol=1e-9)
+    # several ticks in one call (the overlapped index ranges of mpcqp_scenario_run) continue the same trajectory
+    dev.scenario_run(5)
+    for t in range(T, T + 5):
+        xref, fsteps = host_sc.inputs()
+        host.run(t, xref, fsteps)
+        host_sc.advance(host.solution()[:, :12] + xref[:, :, 1])
+    np.testing.assert_allclose(dev.scenario_state()["state"], host_sc.state, rtol=0, atol=1e-8)
+    host.close(); dev.close()
+
+
 def test_device_planner_follows_changing_commands():
     """SURVEY 8f row f1, the rest of the planner: joystick commands that change between ticks, including vz / roll-rate /
     pitch-rate (getRefStates' state machine, FootstepPlanner.py:128-152) and the `reduced` support polygon

@@ -24,6 +24,30 @@ def test_trot_planner_matches_reference(N):
         sc.advance(xn[None])
 
 
+def test_trot_planner_matches_reference_at_dt_001():
+    """dt = 0.01 (main.py:20): the gait period is 32 steps.  Host twin against the reference planner's own xref / fsteps over more
+    than two gait periods; and the period survives the packing the device planner consumes (two 64-bit words per robot)."""
+    D = np.load(os.path.join(os.path.dirname(__file__), "golden", "planner_trot_dt01.npz"))
+    sc = Scenario(1, n_steps=32, dt=0.01, T_gait=0.32, gaits="trot", v_ref=D["v_ref"], phase=[0], random_commands=False)
+    assert sc.period == 32
+    for k in range(D["xref"].shape[0]):
+        xr, fs = sc.inputs()
+        np.testing.assert_allclose(sc.state[0], D["state"][k], rtol=0, atol=1e-15)
+        assert np.array_equal(np.isnan(fs[0]), np.isnan(D["fsteps"][k]))
+        np.testing.assert_allclose(np.nan_to_num(fs[0]), np.nan_to_num(D["fsteps"][k]), rtol=0, atol=1e-14)
+        np.testing.assert_allclose(xr[0], D["xref"][k], rtol=0, atol=1e-14)
+        xn = D["xref"][k][:, 1] + 0.005 * np.sin(np.arange(12) + k)
+        sc.advance(xn[None])
+    bits = Scenario(3, n_steps=32, dt=0.01, T_gait=0.32, gaits=["trot", "walk", "pace"], random_commands=False)
+    words = bits.seq_bits()
+    assert words.shape == (3, 2) and words.dtype == np.uint64
+    for b in range(3):
+        for s_ in range(32):
+            for j in range(4):
+                assert ((int(words[b, s_ // 16]) >> (4 * (s_ % 16) + j)) & 1) == int(bits.seq[b, s_, j])
+    assert Scenario(2, gaits="trot").seq_bits().shape == (2,)      # one word while the period fits it: the layout of rounds 1-2
+
+
 def test_gait_tables():
     for kind in GAIT_KINDS:
         seq = gait_sequence(kind)
