@@ -27,10 +27,11 @@
 // only O(N) state of the recursion that must survive until the forward pass) in an L2-resident workspace.
 // Code size is part of the design: every per-foot loop is rolled (the unrolled version spent 16 % of its stall
 // samples on instruction fetch).
-// The two factorisations of a stage and the inverses of their unit triangular factors are computed redundantly in the
-// REGISTERS of every lane (static indices, no shuffle or memory hop on the pivot chain; pivot to pivot is a 4-instruction
-// reciprocal and one fused multiply-add; the inverse rows are formed in the shadow of the pivots), so every product above is "one row in registers
-// times a register-resident triangular matrix" and a stage needs three warp barriers.
+// The two factorisations of a stage are computed redundantly in the REGISTERS of every lane (static indices, no shuffle or
+// memory hop on the pivot chain; pivot to pivot is a 4-instruction reciprocal and one fused multiply-add), so every product
+// above is "one row in registers times / substituted through a register-resident unit triangular matrix" and a stage needs
+// three warp barriers.  Capacities 16 and 32 substitute with the factors themselves; capacity 64 also forms the inverse
+// rows of the unit factors in the shadow of the pivots and multiplies by them (see ldl6_regs).
 // Replaces MPC.update_ML / update_NK / call_solver / retrieve_result (MPC.py:316-458) like the dense path.
 //
 // Horizons: the kernels are compiled for three CAPACITIES NC = 16, 32, 64 (array sizes, lanes per robot, feet per lane); the
@@ -182,7 +183,10 @@ __device__ __forceinline__ double rcp_fast(double d) {
 // Two row vectors ride along in the shadow of the pivots: `fs` is overwritten by fs U^-T (forward substitution: entry
 // j + 1 needs row j + 1 of U up to column j, final right after pivot j) and, if COLP, `cp_out` receives cp U (entry j needs
 // column j of U, final at the same moment) -- so both are complete one multiply-add after the last pivot.
-template <bool COLP>
+// INV: also form ui; without it the callers substitute with U itself (row_solve1), which is what the capacity-16 / 32 kernels do:
+// 3.5 % faster (profiles/r02_kernel_variants.md).  The capacity-64 kernel keeps the explicit inverse rows: released from rest under
+// 1.5 m/s commands at N = 64 the substitution form left the dynamics rows at 1.7e-8 against the certificate's 1e-8 bar.
+template <bool COLP, bool INV>
 __device__ __forceinline__ bool ldl6_regs(double (&a)[21], double (&dinv)[6], double (&ui)[21], double (&fs)[6], const double (&cp)[6],
                                           double (&cp_out)[6]) {
     bool ok = true;
@@ -204,15 +208,15 @@ __device__ __forceinline__ bool ldl6_regs(double (&a)[21], double (&dinv)[6], do
             for (int c = j + 1; c <= i; ++c)
                 if (!(i == j + 1 && c == j + 1)) a[RIC_TI(i, c)] = fma(-a[RIC_TI(i, j)], t[c], a[RIC_TI(i, c)]);
         // row j of inv(U):  ui[j][c] = -(u[j][c] + sum_{c < k < j} u[j][k] ui[k][c])
-#ifndef RIC_NOINV
+        if constexpr (INV) {
 #pragma unroll
-        for (int c = 0; c < j; ++c) {
-            double acc = a[RIC_TI(j, c)];
+            for (int c = 0; c < j; ++c) {
+                double acc = a[RIC_TI(j, c)];
 #pragma unroll
-            for (int k = c + 1; k < j; ++k) acc = fma(a[RIC_TI(j, k)], ui[RIC_TI(k, c)], acc);
-            ui[RIC_TI(j, c)] = -acc;
+                for (int k = c + 1; k < j; ++k) acc = fma(a[RIC_TI(j, k)], ui[RIC_TI(k, c)], acc);
+                ui[RIC_TI(j, c)] = -acc;
+            }
         }
-#endif
         // the carried rows
         if (j + 1 < 6) {
             double acc = fs[j + 1];
@@ -301,6 +305,7 @@ template <int N>
 __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl, const int n) {
     const double dt = P.dt;
     const int ld = n + 1;                                        // leading dimension of xref
+    constexpr bool EXPLICIT_INV = N >= 64;                       // see ldl6_regs
     RPROF_T0();
     // ---- terminal cost-to-go: P_N = Q, p_N = -Q xref_N
     {
@@ -347,7 +352,7 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
         double tr[6], y[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) y[q] = rho[q];
-        spd = ldl6_regs<true>(L, dinv, Li, y, er, tr) && spd;
+        spd = ldl6_regs<true, EXPLICIT_INV>(L, dinv, Li, y, er, tr) && spd;
         RPROF(2);
         // (2) the rows of T -> shared memory
         if (prow) store_row6(sm.T + 6 * ri, tr);
@@ -376,7 +381,7 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
         double b1[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) b1[q] = y[q] * dinv[q];
-        spd = ldl6_regs<false>(G, einv, Mi, b1, b1, b1) && spd;
+        spd = ldl6_regs<false, EXPLICIT_INV>(G, einv, Mi, b1, b1, b1) && spd;
         RPROF(5);
         // (4) with e = ((y D^-1) W^-T Delta^-1) W^-1:   t = e U' (row of Pt[:, v]),   kr = ((y - e) D^-1) U^-1 (row of
         //     [Ppv; Pvv; pv'] Gamma)
@@ -385,19 +390,11 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
             double dr[6];
 #pragma unroll
             for (int q = 0; q < 6; ++q) b1[q] *= einv[q];
-#ifdef RIC_NOINV
-            row_solve1(v, b1, G);
-#else
-            row_mul1(v, b1, Mi);
-#endif
+            if constexpr (EXPLICIT_INV) row_mul1(v, b1, Mi); else row_solve1(v, b1, G);
 #pragma unroll
             for (int q = 0; q < 6; ++q) dr[q] = (y[q] - v[q]) * dinv[q];
             row_mul1T(tr, v, L);
-#ifdef RIC_NOINV
-            row_solve1(kr, dr, L);
-#else
-            row_mul1(kr, dr, Li);
-#endif
+            if constexpr (EXPLICIT_INV) row_mul1(kr, dr, Li); else row_solve1(kr, dr, L);
         }
         if (hl < 13) {
             double* g = ws + (size_t)RIC_GAIN * k + rid;                // gain of impulse component o: coefficient rid
