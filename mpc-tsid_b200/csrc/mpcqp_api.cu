@@ -448,6 +448,14 @@ int mpcqp_create(const mpcqp_params* p, mpcqp_handle** out) {
 #endif
     d.ipm_max_iter = p->ipm_max_iter > 0 ? p->ipm_max_iter : 60;
     d.fs_rows = 20;
+    // the reciprocals make_face needs, with the kernels' former arithmetic: mu * mu rounded, times m exact, plus one rounded, times w rounded, IEEE division
+    d.inv_wf = 1.0 / d.w_force;
+    for (int m = 0; m < 3; ++m) {
+        volatile double t = d.mu * d.mu;
+        volatile double s1 = 1.0 + t * (double)m;
+        volatile double x = d.w_force * s1;
+        d.dz_tab[m] = 1.0 / x;
+    }
 
     // Gram matrices of the double-integrator response and their inverses (constant per handle)
     //   M_c[k,l] = sum_{i >= max(k,l)} ( dt^2 Qp_c (i-k)(i-l) + Qv_c ),  i = 0..N-1

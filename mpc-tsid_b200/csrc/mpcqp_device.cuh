@@ -43,6 +43,8 @@ struct DevParams {
     int max_sweeps, max_iter, min_iter, check_every, warm_start, mode, refine, ipm_max_iter;
     int fs_rows;            // stage-wise kernels: rows of a gait table fetched up front (20 = the whole table; 8 = rows 0..7, the rest only for a
                             // table that does not end within them: inputs read straight from the caller's page-locked host memory)
+    double inv_wf;          // 1 / w_force
+    double dz_tab[3];       // 1 / (w_force (1 + mu^2 m)), m = sx^2 + sy^2 = 0, 1, 2: the face reciprocals (make_face), IEEE divisions done once on the host
     const double* Minv_tiled;   // lower block triangle of M^-1 in the smem tile layout
     const double* C2;           // N x N: C2[k,l] = sum_{i >= max(k,l)} (i-k)(i-l)   (C0[k,l] = N - max(k,l))
 };

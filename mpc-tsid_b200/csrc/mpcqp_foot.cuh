@@ -24,10 +24,9 @@ __device__ __forceinline__ void make_face(const DevParams& P, bool contact, uint
     fc.zz = live && tz == 0;
     fc.czx = sx * P.mu;
     fc.czy = sy * P.mu;
-    const double w = P.w_force;
-    fc.dx = fc.zx ? 1.0 / w : 0.0;
-    fc.dy = fc.zy ? 1.0 / w : 0.0;
-    fc.dz = fc.zz ? 1.0 / (w * (1.0 + P.mu * P.mu * (double)(sx * sx + sy * sy))) : 0.0;
+    fc.dx = fc.zx ? P.inv_wf : 0.0;                              // 1 / w
+    fc.dy = fc.zy ? P.inv_wf : 0.0;
+    fc.dz = fc.zz ? P.dz_tab[sx * sx + sy * sy] : 0.0;           // 1 / (w (1 + mu^2 (sx^2 + sy^2)))
     const bool top = live && tz == 2;
     fc.pf[0] = top ? fc.czx * P.fz_max : 0.0;
     fc.pf[1] = top ? fc.czy * P.fz_max : 0.0;
@@ -120,16 +119,20 @@ __device__ __forceinline__ void decode_foot(const DevParams& P, const double* xr
 // block instead of the 3x3 product, and forms  A = dt inv(R gI) [r]x  on demand with decode_foot's arithmetic):
 //   contact flag + lever arm r = foothold - xref[0:3, k] of (step k, foot j)            [MPC.py:327, 343, 635-652]
 // `n` is the run-time horizon: xref is 12 x (n + 1).
-__device__ __forceinline__ void decode_lever(const DevParams& P, const double* xr, const double* fs, int n, int k, int j, bool first_tick,
-                                             double r[3], bool& contact, bool& bad) {
-    int row = -1;
-    double cum = 0.0;
-    for (int q = 0; q < 20; ++q) {
-        const double cnt = fs[q * 13];
-        if (cnt == 0.0) break;
-        if (!(cnt > 0.0) || cnt != floor(cnt)) { bad = true; break; }
-        if ((double)k < cum + cnt) { row = q; break; }
-        cum += cnt;
+// A lane asks for increasing steps k: (q, cum, row) carry the row search of decode_foot from one call to the next (rows < q have
+// been passed and validated, cum = their counts; row = the row of the last k, -1 if there was none, -2 once the table has ended) --
+// the rows are visited and validated in the same order as by a search that starts over, so contact, lever arm and `bad` are the same.
+__device__ __forceinline__ void decode_lever_next(const DevParams& P, const double* xr, const double* fs, int n, int k, int j, bool first_tick,
+                                                  double r[3], bool& contact, bool& bad, int& q, double& cum, int& row) {
+    if (row != -2 && !bad) {
+        row = -1;
+        for (; q < 20; ++q) {
+            const double cnt = fs[q * 13];
+            if (cnt == 0.0) { row = -2; break; }
+            if (!(cnt > 0.0) || cnt != floor(cnt)) { bad = true; break; }
+            if ((double)k < cum + cnt) { row = q; break; }
+            cum += cnt;
+        }
     }
     double foot[3] = {0.0, 0.0, 0.0};
     contact = false;

@@ -138,7 +138,7 @@ __device__ __forceinline__ void lane_inertia(const DevParams& P, double cs, doub
 
 // Inputs of robot `inst` -> workspace (reference trajectory, yaw cosines / sines, lever arms, contact bits) and the warm-start
 // signature (the previous tick's, advanced by one step, MPC.py:403-406).  Returns true if the inputs are malformed.
-// Same decoding rules as decode_lever / step_inertia (mpcqp_foot.cuh)                          [MPC.py:316-360, 635-652]
+// Same decoding rules as decode_lever_next / step_inertia (mpcqp_foot.cuh)                          [MPC.py:316-360, 635-652]
 __device__ bool lane_fetch(const DevParams& P, const DevState& st, const LaneWs& L, const double* __restrict__ xref_g,
                            const double* __restrict__ fsteps_g, int inst, int first_tick) {
     const int n = L.n, ld = n + 1;

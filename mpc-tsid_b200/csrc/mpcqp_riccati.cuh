@@ -193,7 +193,9 @@ __device__ __forceinline__ bool ldl6_regs(double (&a)[21], double (&dinv)[6], do
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         const double d = a[RIC_TI(j, j)];
-        ok = ok && (d > 1e-300) && (d < 1e300);
+        // positive, finite and neither tiny nor huge, read off the exponent field with one integer compare (2^-996 <= d < 2^996;
+        // negative values and NaNs wrap past the span) instead of two FP64 compares on the pivot chain's pipe
+        ok = ok && ((unsigned)(__double2hiint(d) - 0x01B00000) < (unsigned)(0x7E300000 - 0x01B00000));
         double sq = 0.0;
         if (j + 1 < 6) sq = a[RIC_TI(j + 1, j)] * a[RIC_TI(j + 1, j)];
         const double r = rcp_fast(d);
@@ -332,12 +334,20 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
     int ie[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) ie[q] = (ri >= q) ? ri * (ri + 1) / 2 + q : q * (q + 1) / 2 + ri;
+    const double* pe[6];                                       // this lane's row of the packed E_k, walked from stage to stage
+#pragma unroll
+    for (int q = 0; q < 6; ++q) pe[q] = sm.E + 21 * (n - 1) + ie[q];
+    // this lane's row of Q = diag(wp, wv): six registers pairs held across the recursion, so that adding the diagonal weight costs one
+    // add per element (the ternary form costs a compare and two selects more, per element and stage, and holds all twelve weights)
+    const double wq = prow ? P.wp[ri] : P.wv[ri];
+    double dq[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) dq[c] = (c == ri) ? wq : 0.0;
 
     bool spd = true;
     for (int k = n - 1; k >= 0; --k) {
         const RicCost& cin = sm.cost[k & 1];
         RicCost& cout = sm.cost[(k & 1) ^ 1];
-        const double* Ek = sm.E + 21 * k;
         // (1) U D U' = Pvv, Ui = inv(U): every lane, in registers (square-root free: L = U D^1/2 never appears)
         double L[21], Li[21], dinv[6];
 #pragma unroll
@@ -347,7 +357,7 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
         double rho[6], er[6];
         load_row6(rho, prow ? cin.Ppv + 6 * ri : (vrow ? cin.Pvv + 6 * ri : cin.pv));
 #pragma unroll
-        for (int q = 0; q < 6; ++q) er[q] = Ek[ie[q]];
+        for (int q = 0; q < 6; ++q) { er[q] = *pe[q]; pe[q] -= 21; }
         // ... carrying along  y = rho U^-T  (so that rho L^-T = y D^-1/2)  and row ri of T = E U
         double tr[6], y[6];
 #pragma unroll
@@ -370,7 +380,8 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
             for (int a = 0; a < 6; ++a)
 #pragma unroll
                 for (int c = 0; c <= a; ++c) {
-                    double t = Tl[RIC_TI(a, c)] + ((a == c) ? dinv[a] : 0.0);       // r = a term: U[a][a] = 1
+                    double t = Tl[RIC_TI(a, c)];                                     // r = a term: U[a][a] = 1
+                    if (a == c) t += dinv[a];                                        // (no "+ 0.0" off the diagonal: it would be issued)
 #pragma unroll
                     for (int r = a + 1; r < 6; ++r) t = fma(L[RIC_TI(r, a)], Tl[RIC_TI(r, c)], t);
                     G[RIC_TI(a, c)] = t;
@@ -434,22 +445,22 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
                 double npp[6], npv[6];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {
-                    npp[c] = wr[c] + ((c == ri) ? P.wp[ri] : 0.0);
+                    npp[c] = wr[c] + dq[c];
                     npv[c] = fma(dt, wr[c], tr[c]);
                 }
                 store_row6(cout.Ppp + 6 * ri, npp);
                 store_row6(cout.Ppv + 6 * ri, npv);
                 sm.hp[ri] = hb;
-                cout.pp[ri] = hb - P.wp[ri] * sm.xr[ri * ld + k];
+                cout.pp[ri] = hb - wq * sm.xr[ri * ld + k];
             }
             __syncwarp();
             if (vrow) {
                 double npv[6], nvv[6];
                 load_row6(npv, cout.Ppv + 6 * ri);
 #pragma unroll
-                for (int c = 0; c < 6; ++c) nvv[c] = fma(dt, npv[c] + wr[c], tr[c]) + ((c == ri) ? P.wv[ri] : 0.0);
+                for (int c = 0; c < 6; ++c) nvv[c] = fma(dt, npv[c] + wr[c], tr[c]) + dq[c];
                 store_row6(cout.Pvv + 6 * ri, nvv);
-                cout.pv[ri] = fma(dt, sm.hp[ri], hb) - P.wv[ri] * sm.xr[(6 + ri) * ld + k];
+                cout.pv[ri] = fma(dt, sm.hp[ri], hb) - wq * sm.xr[(6 + ri) * ld + k];
             }
             __syncwarp();
             RPROF(8);
@@ -937,13 +948,31 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
     __syncwarp();
     double part = 0.0;
     double* xs = st.xs + (size_t)inst * 12 * n;
-    for (int i = hl; i < 12 * n; i += 16) {
-        const int s = i / 12, c = i - 12 * s;
-        const double e = sm.xst[i] - sm.xr[c * ld + s + 1];
-        const double ee = isfinite(e) ? e : 0.0;                                             // malformed input: never NaN out
-        if (commit) xs[i] = ee;                                                              // MPC.x[:12N] (MPC.py:428)
-        if (commit && i < 12) st.x1[(size_t)inst * 12 + i] = isfinite(e) ? sm.xst[i] : 0.0;              // MPC.q_next / v_next (MPC.py:448-450)
-        part = fma(0.5 * (c < 6 ? P.wp[c] : P.wv[c - 6]) * ee, ee, part);
+    {
+        // element i = hl + 16 u + 48 m is component (hl + 16 u) % 12 of step 4 m + (hl + 16 u) / 12: the component, its weight and the
+        // step offset of a lane's three residues are fixed, so the division and the weight lookup leave the loop (same order of
+        // accumulation as i = hl, hl + 16, ...)
+        int xo[3];
+        double wu[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int jj = hl + 16 * u, ds = jj / 12, c = jj - 12 * ds;
+            xo[u] = c * ld + ds + 1;
+            wu[u] = 0.5 * (c < 6 ? P.wp[c] : P.wv[c - 6]);
+        }
+        if (commit && hl < 12) st.x1[(size_t)inst * 12 + hl] = isfinite(sm.xst[hl] - sm.xr[xo[0]]) ? sm.xst[hl] : 0.0;   // MPC.q_next / v_next (MPC.py:448-450)
+        for (int i0 = 0, s0 = 0; i0 < 12 * n; i0 += 48, s0 += 4) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int i = i0 + hl + 16 * u;
+                if (i < 12 * n) {
+                    const double e = sm.xst[i] - sm.xr[xo[u] + s0];
+                    const double ee = isfinite(e) ? e : 0.0;                                 // malformed input: never NaN out
+                    if (commit) xs[i] = ee;                                                  // MPC.x[:12N] (MPC.py:428)
+                    part = fma(wu[u] * ee, ee, part);
+                }
+            }
+        }
     }
     if (hl < 12) sm.xnext[hl] = sm.xst[hl];                                                  // MPC.q_next / v_next (MPC.py:448-450)
 #pragma unroll 1
@@ -990,11 +1019,16 @@ __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>
         const double row[5] = {f[0] - mu * f[2], -f[0] - mu * f[2], f[1] - mu * f[2], -f[1] - mu * f[2], -f[2]};
         const int b0 = 5 * t;
         if (exists) {
+            unsigned m5 = 0u;                                   // the five rows of this foot-step, then at most two words to touch
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 const bool act = (fabs(row[q]) <= tol) || (q == 4 && fabs(row[4] + P.fz_max) <= tol);
-                if (act) atomicOr(&sm.amask[(b0 + q) >> 5], 1u << ((b0 + q) & 31));
+                m5 |= act ? (1u << q) : 0u;
             }
+            const unsigned sh = b0 & 31;
+            const unsigned lo = m5 << sh, hi = (sh > 27) ? (m5 >> (32 - sh)) : 0u;
+            if (lo) atomicOr(&sm.amask[b0 >> 5], lo);
+            if (hi) atomicOr(&sm.amask[(b0 >> 5) + 1], hi);
         }
         const unsigned cb = (__ballot_sync(RIC_FULL, contact) >> (16 * sub)) & 0xFFFFu;      // feet 16 r .. 16 r + 15
         if (hl == 0 && cb) atomicOr(&sm.amask[AWC + (r >> 1)], cb << (16 * (r & 1)));
@@ -1059,12 +1093,14 @@ __device__ __forceinline__ bool ric_load_decode(const DevParams& P, const DevSce
     RPROF(13);
     bool bad = false;
     conbits = 0u;
+    int scan_q = 0, scan_row = -1;                             // a lane's steps grow with r: the row search goes on where it stopped
+    double scan_cum = 0.0;
 #pragma unroll 1
     for (int r = 0; r < ROUNDS; ++r) {
         const int t = hl + 16 * r, k = t >> 2, j = t & 3;
         double lv[3] = {0.0, 0.0, 0.0};
         bool contact = false;
-        if (t < 4 * n) decode_lever(P, sm.xr, sm.fs, n, k, j, first_tick != 0, lv, contact, bad);
+        if (t < 4 * n) decode_lever_next(P, sm.xr, sm.fs, n, k, j, first_tick != 0, lv, contact, bad, scan_q, scan_cum, scan_row);
         sm.lev[t] = lv[0]; sm.lev[NF + t] = lv[1]; sm.lev[2 * NF + t] = lv[2];
         conbits |= contact ? (1u << r) : 0u;
     }
@@ -1080,7 +1116,8 @@ __device__ __forceinline__ bool ric_load_decode(const DevParams& P, const DevSce
             for (int i = 0; i < 9; ++i) sm.Ii[9 * k + i] = Ii[i];
         }
     }
-    for (int i = hl; i < 12 * (n + 1); i += 16) bad = bad || !isfinite(sm.xr[i]);
+    for (int i = hl; i < 12 * (n + 1); i += 16)               // not finite <=> exponent field all ones: an integer test on the high word
+        bad = bad || ((__double2hiint(sm.xr[i]) & 0x7ff00000) == 0x7ff00000);
     const bool any_bad = half_any(bad, sub);
     __syncwarp();                                            // fs is dead from here on (E overwrites it)
     RPROF(14);
