@@ -184,11 +184,12 @@ def flops_per_tick(sweeps, iters, fallbacks, n=96, N=N_STEPS, refine=0):
 def flops_stagewise_sweep(N=N_STEPS):
     """STAGE-WISE path (default), one active-set sweep of one robot, counted from the algorithm of
     mpcqp_riccati.cuh (useful work only: the redundant per-lane copies of the 6x6 factorisations are not counted).
-    Per stage: two 6x6 Cholesky factorisations + triangular inverses (2 x 2 n^3/3), T = E L and G = I + L'T
-    (triangular / symmetric products), 13 rows x 4 triangular row products (21 FMA each), 12 rows x (36 + 6) FMA for
-    Pt[:, p] and pt, 12 x 6 FMA for Pt[:, v] beta, the assembly of P_k."""
+    Per stage: two 6x6 factorisations (2 x n^3/3; the capacity-64 kernel, N > 32, also forms the inverses of the two unit
+    triangular factors, another 2 x n^3/3 -- capacities 16 and 32 substitute with the factors themselves), T = E L and
+    G = I + L'T (triangular / symmetric products), 13 rows x 4 triangular row products or substitutions (21 FMA each),
+    12 rows x (36 + 6) FMA for Pt[:, p] and pt, 12 x 6 FMA for Pt[:, v] beta, the assembly of P_k."""
     n = 6
-    chol = 2 * (2.0 * n ** 3 / 3.0)
+    chol = 2 * (n ** 3 / 3.0) * (2 if N > 32 else 1)
     t_g = 2 * 126 + 2 * 56
     rows = 13 * 4 * 21 * 2
     wpart = 12 * (36 + 6) * 2 + 12 * 6 * 2

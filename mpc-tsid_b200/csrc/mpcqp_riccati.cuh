@@ -550,9 +550,11 @@ __device__ __forceinline__ void ric_assemble(const DevParams& P, RicInst<N>& sm,
 #pragma unroll
         for (int i = 0; i < 6; ++i) ub[i] = 0.0;
         ub[2] = -P.gravity * P.dt;                             // g: only the z velocity, MPC.py:200-201
+        // stance feet only: a swing foot contributes S = 0 and pf = 0, i.e. exactly nothing (sm.sigb holds contact << 7 per foot-step)
+        unsigned cm = *reinterpret_cast<const unsigned*>(sm.sigb + 4 * k) & 0x80808080u;
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-            const int t = 4 * k + j;
+        for (; cm != 0u; cm &= cm - 1u) {
+            const int t = 4 * k + ((__ffs(cm) - 1) >> 3);
             double S[6], pf[3];
             foot_of(t, S, pf);
             double A[9];
