@@ -74,7 +74,7 @@ constexpr unsigned long long RIC_CANARY_WORD = 0xC0FFEE0DDEADBEEFull;
 #else
 #define RIC_GUARD(name)
 #endif
-constexpr int RIC_DEPTH = 4;        // stages of gains the forward pass keeps in flight from the workspace
+constexpr int RIC_DEPTH = 4;        // stages of gains the forward pass keeps in flight from the workspace (5 and 6 measured slower: profiles/r02_kernel_variants.md)
 
 // cost-to-go of one stage, row major 6x6 blocks (double-buffered: stage k reads one, writes the other)
 struct alignas(16) RicCost {
@@ -344,10 +344,12 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
 #pragma unroll
     for (int c = 0; c < 6; ++c) dq[c] = (c == ri) ? wq : 0.0;
 
+    const double* xrp = sm.xr + (prow ? ri : 6 + ri) * ld;
     bool spd = true;
     for (int k = n - 1; k >= 0; --k) {
         const RicCost& cin = sm.cost[k & 1];
         RicCost& cout = sm.cost[(k & 1) ^ 1];
+        const double xrk = xrp[k];                               // this row's reference at stage k, fetched here: it is needed at the very end of the stage
         // (1) U D U' = Pvv, Ui = inv(U): every lane, in registers (square-root free: L = U D^1/2 never appears)
         double L[21], Li[21], dinv[6];
 #pragma unroll
@@ -451,7 +453,7 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
                 store_row6(cout.Ppp + 6 * ri, npp);
                 store_row6(cout.Ppv + 6 * ri, npv);
                 sm.hp[ri] = hb;
-                cout.pp[ri] = hb - wq * sm.xr[ri * ld + k];
+                cout.pp[ri] = hb - wq * xrk;
             }
             __syncwarp();
             if (vrow) {
@@ -460,7 +462,7 @@ __device__ __forceinline__ bool ric_core(const DevParams& P, RicInst<N>& sm, dou
 #pragma unroll
                 for (int c = 0; c < 6; ++c) nvv[c] = fma(dt, npv[c] + wr[c], tr[c]) + dq[c];
                 store_row6(cout.Pvv + 6 * ri, nvv);
-                cout.pv[ri] = fma(dt, sm.hp[ri], hb) - wq * sm.xr[(6 + ri) * ld + k];
+                cout.pv[ri] = fma(dt, sm.hp[ri], hb) - wq * xrk;
             }
             __syncwarp();
             RPROF(8);
