@@ -598,6 +598,19 @@ __device__ __forceinline__ void face_S(const Face& fc, double (&S)[6]) {
     S[3] = fc.dz * fc.czx; S[4] = fc.dz * fc.czy; S[5] = fc.dz;
 }
 
+// The signatures of a lane's foot-steps (one per round), four to a 32-bit word: rolled loops index them with a run-time round, and an
+// array of bytes indexed that way lives in local memory (ncu: 3 % of a launch's samples waited on those loads); at capacity 16 this
+// is one register.
+template <int R>
+struct SigVec {
+    unsigned w[(R + 3) / 4] = {};
+    __device__ __forceinline__ uint8_t operator[](int r) const { return (uint8_t)((w[r >> 2] >> (8 * (r & 3))) & 0xffu); }
+    __device__ __forceinline__ void set(int r, uint8_t v) {
+        const int sh = 8 * (r & 3);
+        w[r >> 2] = (w[r >> 2] & ~(0xffu << sh)) | ((unsigned)v << sh);
+    }
+};
+
 constexpr uint8_t SIG_PIN = 27;    // not a face: the foot-step's force is held at a given value (roll-out of a feasible iterate)
 
 // One equality-constrained solve on the faces `sg` selects + KKT guard.  The 16 lanes of the robot call it.
@@ -609,7 +622,7 @@ constexpr uint8_t SIG_PIN = 27;    // not a face: the foot-step's force is held 
 // certified still leaves with states that belong to its forces.
 template <int N>
 __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl, const int n, unsigned conbits,
-                         const uint8_t (&sg)[RicInst<N>::ROUNDS], uint8_t (&nsg)[RicInst<N>::ROUNDS], const double* __restrict__ pin = nullptr) {
+                         const SigVec<RicInst<N>::ROUNDS>& sg, SigVec<RicInst<N>::ROUNDS>& nsg, const double* __restrict__ pin = nullptr) {
     using S = RicInst<N>;
     constexpr int ROUNDS = S::ROUNDS, NF = S::NF;
     const double lin = P.dt / P.mass;
@@ -638,7 +651,7 @@ __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict_
         const int t = hl + 16 * r, k = t >> 2;
         const bool contact = (conbits >> r) & 1u;
         double f[3] = {0.0, 0.0, 0.0};
-        nsg[r] = sg[r];
+        uint8_t ns = sg[r];
         if (contact && sg[r] == SIG_PIN) {
             if (pin != nullptr) { f[0] = pin[t]; f[1] = pin[NF + t]; f[2] = pin[2 * NF + t]; }
         } else if (contact) {
@@ -655,8 +668,9 @@ __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict_
             f[2] = fc.pf[2] + qz;
             const double grad[3] = {fma(P.w_force, f[0], h[0]), fma(P.w_force, f[1], h[1]), fma(P.w_force, f[2], h[2])};
             FootSol sol;
-            ok = kkt_guard(P, sg[r], f, grad, sol, nsg[r]) && ok;
+            ok = kkt_guard(P, sg[r], f, grad, sol, ns) && ok;
         }
+        nsg.set(r, ns);
         sm.E[3 * t] = f[0]; sm.E[3 * t + 1] = f[1]; sm.E[3 * t + 2] = f[2];
     }
     const bool all_ok = half_all(ok, sub);
@@ -672,11 +686,11 @@ __device__ int ric_sweep(const DevParams& P, RicInst<N>& sm, double* __restrict_
 // sweep sit in shared memory ONLY IF the other half did not go on sweeping -- callers that need them re-run one sweep.
 template <int N>
 __device__ __forceinline__ void ric_active_set(const DevParams& P, RicInst<N>& sm, double* __restrict__ ws, int sub, int hl, const int n,
-                                               unsigned conbits, uint8_t (&sg)[RicInst<N>::ROUNDS], uint8_t (&nsg)[RicInst<N>::ROUNDS],
+                                               unsigned conbits, SigVec<RicInst<N>::ROUNDS>& sg, SigVec<RicInst<N>::ROUNDS>& nsg,
                                                bool want, int max_s, bool allow_careful, int& sweeps, bool& done, int& status) {
     constexpr int ROUNDS = RicInst<N>::ROUNDS;
     // order-sensitive hash of a signature, uniform over the half-warp (cycle detection)
-    auto sig_hash = [&](const uint8_t (&g)[ROUNDS]) {
+    auto sig_hash = [&](const SigVec<ROUNDS>& g) {
         unsigned long long h = 0ull;
 #pragma unroll 1
         for (int r = 0; r < ROUNDS; ++r) {
@@ -723,8 +737,7 @@ __device__ __forceinline__ void ric_active_set(const DevParams& P, RicInst<N>& s
                 careful = true;
                 if (!allow_careful) { stop = true; search = false; }
             } else {
-#pragma unroll 1
-                for (int r = 0; r < ROUNDS; ++r) sg[r] = nsg[r];
+                sg = nsg;
                 search = false;
             }
         }
@@ -738,15 +751,14 @@ __device__ __forceinline__ void ric_active_set(const DevParams& P, RicInst<N>& s
             }
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) { const int q = __shfl_xor_sync(RIC_FULL, tm, o, 16); tm = q < tm ? q : tm; }
-            uint8_t cand[ROUNDS];
+            SigVec<ROUNDS> cand;
 #pragma unroll 1
-            for (int r = 0; r < ROUNDS; ++r) cand[r] = (hl + 16 * r == tm) ? nsg[r] : sg[r];
+            for (int r = 0; r < ROUNDS; ++r) cand.set(r, (hl + 16 * r == tm) ? nsg[r] : sg[r]);
             const unsigned long long hc = sig_hash(cand);
             if (search) {
                 if (tm == 0x7fffffff) { stop = true; search = false; }            // every single change was tried before
                 else if (!seen(hc)) {
-#pragma unroll 1
-                    for (int r = 0; r < ROUNDS; ++r) sg[r] = cand[r];
+                    sg = cand;
                     search = false;
                 } else tlast = tm;
             }
@@ -923,7 +935,7 @@ __device__ bool ric_ipm(const DevParams& P, RicInst<N>& sm, double* __restrict__
 // roll-out of its feasible interior-point iterate (SIG_PIN), `ymax` then points at that iterate's multipliers.
 template <int N>
 __device__ void ric_finish(const DevParams& P, const DevScenario& SC, RicInst<N>& sm, const DevState& st, int inst, int sub, int hl, const int n,
-                           unsigned conbits, const uint8_t (&sg)[RicInst<N>::ROUNDS], bool solved, int status, int sweeps, int iters,
+                           unsigned conbits, const SigVec<RicInst<N>::ROUNDS>& sg, bool solved, int status, int sweeps, int iters,
                            const double* __restrict__ ymax, bool commit) {
     using S = RicInst<N>;
     constexpr int NF = S::NF, ROUNDS = S::ROUNDS, AWC = S::AW, CWC = S::CW;
@@ -1174,26 +1186,26 @@ riccati_kernel(DevParams P, DevState st, DevScenario SC, const double* __restric
         RPROF_T0();
         RPROF_COUNT(12);
         const bool warm = P.warm_start && !first_tick;
-        uint8_t sg[ROUNDS], nsg[ROUNDS];
+        SigVec<ROUNDS> sg, nsg;
         // warm start: the previous tick's signatures advanced by one step (MPC.py:403-406); all loads in flight at once
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const int t = hl + 16 * r, k = t >> 2, j = t & 3, ks = (k + 1 < n) ? k + 1 : 0;
             const uint8_t s8 = (warm && t < 4 * n) ? st.sig[(size_t)inst * 4 * n + 4 * ks + j] : SIG_FREE;
-            sg[r] = s8 > 26 ? SIG_FREE : s8;
+            sg.set(r, s8 > 26 ? SIG_FREE : s8);
         }
         unsigned conbits = 0u;
         const bool any_bad = ric_load_decode<N>(P, SC, sm, xref_g, fsteps_g, inst, valid, first_tick, sub, hl, n, phase, conbits);
 #pragma unroll 1
         for (int r = 0; r < ROUNDS; ++r)
-            if (!((conbits >> r) & 1u)) sg[r] = SIG_FREE;
+            if (!((conbits >> r) & 1u)) sg.set(r, SIG_FREE);
         int sweeps = 0, status = 0;
         bool done = false;
         if (any_bad) {
             status = 3;
             conbits = 0u;
 #pragma unroll 1
-            for (int r = 0; r < ROUNDS; ++r) sg[r] = SIG_FREE;
+            for (int r = 0; r < ROUNDS; ++r) sg.set(r, SIG_FREE);
         }
         ric_active_set<N>(P, sm, ws, sub, hl, n, conbits, sg, nsg, valid && !any_bad, P.max_sweeps, !(P.mode & 8), sweeps, done, status);
         // a robot the sweeps gave up on goes to the fallback stage with its carried state untouched
@@ -1246,14 +1258,14 @@ ipm_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ 
         __syncwarp();
         unsigned conbits = 0u;
         const bool any_bad = ric_load_decode<N>(P, SC, sm, xref_g, fsteps_g, inst, valid, first_tick, sub, hl, n, phase, conbits);
-        uint8_t sg[ROUNDS], nsg[ROUNDS];
+        SigVec<ROUNDS> sg, nsg;
         int sweeps = valid ? st.sweeps[inst] : 0, status = 0, iters = 0;
         bool done = false;
         // ---- start: every stance force well inside its pyramid, gap 1
 #pragma unroll 1
         for (int r = 0; r < ROUNDS; ++r) {
             const int t = hl + 16 * r;
-            sg[r] = SIG_FREE;
+            sg.set(r, SIG_FREE);
             const double f0[3] = {0.0, 0.0, 2.0};
             const double s0[6] = {P.mu * 2.0, P.mu * 2.0, P.mu * 2.0, P.mu * 2.0, 2.0, P.fz_max - 2.0};
 #pragma unroll
@@ -1283,7 +1295,7 @@ ipm_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ 
                     const bool a0 = y[0] > mz - f[0], a1 = y[1] > mz + f[0], a2 = y[2] > mz - f[1], a3 = y[3] > mz + f[1];
                     const bool a4 = y[4] > f[2], a5 = y[5] > P.fz_max - f[2];
                     const bool apex = a4 || (a0 && a1) || (a2 && a3);
-                    sg[r] = sig_pack((a0 ? 1 : 0) - (a1 ? 1 : 0), (a2 ? 1 : 0) - (a3 ? 1 : 0), apex ? 1 : (a5 ? 2 : 0));
+                    sg.set(r, sig_pack((a0 ? 1 : 0) - (a1 ? 1 : 0), (a2 ? 1 : 0) - (a3 ? 1 : 0), apex ? 1 : (a5 ? 2 : 0)));
                 }
             }
             ric_active_set<N>(P, sm, ws, sub, hl, n, conbits, sg, nsg, want && alive, P.max_sweeps > 8 ? P.max_sweeps : 8, false, sweeps, done, status);
@@ -1294,7 +1306,7 @@ ipm_kernel(DevParams P, DevState st, DevScenario SC, const double* __restrict__ 
         if (failed) {
             status = 2;
 #pragma unroll 1
-            for (int r = 0; r < ROUNDS; ++r) sg[r] = SIG_PIN;
+            for (int r = 0; r < ROUNDS; ++r) sg.set(r, SIG_PIN);
         }
         ric_sweep<N>(P, sm, ws, sub, hl, n, conbits, sg, nsg, adm);
         if (any_bad) status = 3;
